@@ -1,0 +1,126 @@
+"""Seeded synthetic genomes and reads (SURVEY.md §8d generator spec).
+
+No genomes exist on disk and there is no network, so every config of
+BASELINE.json is stood in for by a deterministic generator:
+  * genome: uniform ACGT + planted repeat families (copies diverged by a few %),
+  * reads: uniform start, random strand, substitutions, occasional indel, occasional N.
+Only numpy is used; nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_COMP = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+_ASCII = np.frombuffer(b"ACGTN", dtype=np.uint8)
+
+
+def make_genome(length: int, seed: int = 20261017, n_families: int = 5, copies: int = 40,
+                rep_len: int = 1000, divergence: float = 0.02) -> np.ndarray:
+    """Return uint8 codes (0..3) of a synthetic genome of `length` bases."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, size=length, dtype=np.uint8)
+    if length < 4 * rep_len:
+        n_families = 0
+    for _ in range(n_families):
+        unit = rng.integers(0, 4, size=rep_len, dtype=np.uint8)
+        for _ in range(copies):
+            pos = int(rng.integers(0, length - rep_len))
+            cp = unit.copy()
+            mut = rng.random(rep_len) < divergence
+            cp[mut] = (cp[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+            g[pos:pos + rep_len] = cp
+    # keep the text ends free of homopolymer corner cases (first base not A/T, last not A/T):
+    # the fwd+RC text then neither starts nor ends with a T/A run (see DESIGN.md "text end")
+    g[0] = 1
+    g[-1] = 2
+    return g
+
+
+def revcomp(codes: np.ndarray) -> np.ndarray:
+    return _COMP[codes[::-1]]
+
+
+def make_reads(genome: np.ndarray, n_reads: int, read_len: int = 150, seed: int = 7,
+               sub_rate: float = 0.01, indel_frac: float = 0.05, n_frac: float = 0.005,
+               len_jitter: int = 0):
+    """Return (codes, offsets): concatenated read codes (0..3, 4=N) and int64 offsets[n+1].
+
+    len_jitter>0 draws each read length uniformly in [read_len-len_jitter, read_len].
+    """
+    rng = np.random.default_rng(seed)
+    L = genome.shape[0]
+    if len_jitter > 0:
+        lens = rng.integers(read_len - len_jitter, read_len + 1, size=n_reads)
+    else:
+        lens = np.full(n_reads, read_len, dtype=np.int64)
+    starts = rng.integers(0, L - read_len - 8, size=n_reads)
+    strand = rng.random(n_reads) < 0.5
+    has_indel = rng.random(n_reads) < indel_frac
+    has_n = rng.random(n_reads) < n_frac
+    offsets = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    out = np.empty(int(offsets[-1]), dtype=np.uint8)
+    # vectorised fast path for reads without indels
+    for i in range(n_reads):
+        ln = int(lens[i])
+        s = int(starts[i])
+        if has_indel[i]:
+            k = int(rng.integers(1, 4))
+            p = int(rng.integers(10, ln - 10))
+            if rng.random() < 0.5:  # deletion from the read
+                seg = np.concatenate([genome[s:s + p], genome[s + p + k:s + ln + k]])
+            else:  # insertion into the read
+                ins = rng.integers(0, 4, size=k, dtype=np.uint8)
+                seg = np.concatenate([genome[s:s + p], ins, genome[s + p:s + ln - k]])
+        else:
+            seg = genome[s:s + ln].copy()
+        out[offsets[i]:offsets[i + 1]] = seg
+    # substitutions
+    mut = rng.random(out.shape[0]) < sub_rate
+    out[mut] = (out[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    # strand flip + N
+    for i in np.nonzero(strand)[0]:
+        a, b = offsets[i], offsets[i + 1]
+        out[a:b] = _COMP[out[a:b][::-1]]
+    for i in np.nonzero(has_n)[0]:
+        a, b = offsets[i], offsets[i + 1]
+        out[a + int(rng.integers(0, b - a))] = 4
+    return out, offsets
+
+
+def make_reads_fast(genome: np.ndarray, n_reads: int, read_len: int = 150, seed: int = 7,
+                    sub_rate: float = 0.01, n_frac: float = 0.005) -> tuple[np.ndarray, np.ndarray]:
+    """Fully vectorised variant for bench-scale read sets (no indels; fixed length)."""
+    rng = np.random.default_rng(seed)
+    L = genome.shape[0]
+    starts = rng.integers(0, L - read_len, size=n_reads)
+    idx = starts[:, None] + np.arange(read_len)[None, :]
+    reads = genome[idx]
+    mut = rng.random(reads.shape) < sub_rate
+    reads[mut] = (reads[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    strand = rng.random(n_reads) < 0.5
+    reads[strand] = _COMP[reads[strand][:, ::-1]]
+    has_n = np.nonzero(rng.random(n_reads) < n_frac)[0]
+    reads[has_n, rng.integers(0, read_len, size=has_n.shape[0])] = 4
+    offsets = np.arange(n_reads + 1, dtype=np.int64) * read_len
+    return reads.reshape(-1), offsets
+
+
+def write_fasta(path: str, genome: np.ndarray, name: str = "chrS", width: int = 60) -> None:
+    s = _ASCII[genome].tobytes()
+    with open(path, "wb") as f:
+        f.write(b">" + name.encode() + b"\n")
+        for i in range(0, len(s), width):
+            f.write(s[i:i + width] + b"\n")
+
+
+def write_fastq(path: str, codes: np.ndarray, offsets: np.ndarray, prefix: str = "r") -> None:
+    s = _ASCII[codes].tobytes()
+    with open(path, "wb") as f:
+        for i in range(len(offsets) - 1):
+            a, b = int(offsets[i]), int(offsets[i + 1])
+            f.write(b"@%s%d\n" % (prefix.encode(), i))
+            f.write(s[a:b])
+            f.write(b"\n+\n")
+            f.write(b"I" * (b - a))
+            f.write(b"\n")
