@@ -1,0 +1,247 @@
+"""ctypes binding of include/meme_b200.h (the C-ABI shared library libmeme_b200.so).
+
+This is the only way Python code in this repo reaches the CUDA kernels: tests, bench.py and the
+multi-GPU driver all call through the same `extern "C"` entry points a C++ host would.  There is
+no CPU fallback here -- if the library is missing or no GPU is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmeme_b200.so")
+
+SMEM_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("hitbeg", "<i4"), ("hitcount", "<i4"), ("cache_refpos", "<u8")])
+SEQPAIR_DTYPE = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1", "<i4"), ("len2", "<i4"),
+                          ("h0", "<i4"), ("seqid", "<i4"), ("regid", "<i4"), ("score", "<i4"), ("tle", "<i4"),
+                          ("gtle", "<i4"), ("qle", "<i4"), ("gscore", "<i4"), ("max_off", "<i4")])
+RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
+
+EXPORTS = [
+    "meme_index_load", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
+    "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
+    "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_bsw_create", "meme_bsw_free",
+    "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
+    "meme_last_error", "meme_device_count", "meme_version",
+]
+
+
+class SeedOpt(C.Structure):
+    _fields_ = [("min_seed_len", C.c_int32), ("split_len", C.c_int32), ("split_width", C.c_int32),
+                ("max_mem_intv", C.c_int32), ("rounds", C.c_int32), ("max_occ", C.c_int32)]
+
+
+class SeedResult(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_smems", C.c_int64), ("n_hits", C.c_int64), ("smems", C.c_void_p),
+                ("smem_off", C.c_void_p), ("hit_off", C.c_void_p), ("hits", C.c_void_p)]
+
+
+class BswOpt(C.Structure):
+    _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
+                ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+def default_seed_opt(rounds: int = 3, min_seed_len: int = 19, split_factor: float = 1.5, split_width: int = 10,
+                     max_mem_intv: int = 20, max_occ: int = 0) -> SeedOpt:
+    """mem_opt_init defaults (reference src/bwamem.cpp:L126-162)."""
+    return SeedOpt(min_seed_len, int(min_seed_len * split_factor + .499), split_width, max_mem_intv, rounds, max_occ)
+
+
+def default_bsw_opt() -> BswOpt:
+    return BswOpt(6, 1, 6, 1, 100, 5, 1, 4)
+
+
+class MemeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MemeError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        L.meme_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+        L.meme_index_from_host.argtypes = [vp, u64, vp, vp, u64, vp, u64, C.c_int, C.c_int, C.POINTER(vp)]
+        L.meme_index_free.argtypes = [vp]
+        L.meme_index_free.restype = None
+        L.meme_index_sa_num.argtypes = [vp]
+        L.meme_index_sa_num.restype = u64
+        L.meme_index_device_bytes.argtypes = [vp]
+        L.meme_index_device_bytes.restype = u64
+        L.meme_index_set_stream.argtypes = [vp, vp]
+        L.meme_index_download.argtypes = [vp, vp, vp, vp]
+        L.meme_seed_batch.argtypes = [vp, vp, vp, i64, C.POINTER(SeedOpt), C.POINTER(SeedResult)]
+        L.meme_seed_upload.argtypes = [vp, vp, vp, i64]
+        L.meme_seed_run.argtypes = [vp, C.POINTER(SeedOpt)]
+        L.meme_seed_download.argtypes = [vp, C.POINTER(SeedResult)]
+        L.meme_seed_totals.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+        L.meme_seed_counters.argtypes = [vp, C.POINTER(u64 * 8)]
+        L.meme_bsw_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.meme_bsw_free.argtypes = [vp]
+        L.meme_bsw_free.restype = None
+        L.meme_bsw_set_stream.argtypes = [vp, vp]
+        L.meme_bsw_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, C.POINTER(BswOpt)]
+        L.meme_bsw_upload.argtypes = [vp, vp, i64, vp, i64, vp, i64]
+        L.meme_bsw_run.argtypes = [vp, i32, C.POINTER(BswOpt)]
+        L.meme_bsw_download.argtypes = [vp, vp]
+        L.meme_bsw_cells.argtypes = [vp, C.POINTER(u64)]
+        L.meme_last_error.restype = C.c_char_p
+        L.meme_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise MemeError(f"{what} failed with {rc}: {lib().meme_last_error().decode()}")
+
+
+class MemeIndex:
+    """Host mirror of the reference's index ownership in worker_t (sa_position / ref2sa / rc_pac,
+    src/bwamem.h:L231-268) -- here a handle to HBM-resident arrays."""
+
+    def __init__(self, prefix: str | None = None, mode: int = 3, device: int = 0, host_arrays: dict | None = None):
+        L = lib()
+        h = C.c_void_p()
+        if host_arrays is not None:
+            a = host_arrays
+            self._keep = a
+            _check(L.meme_index_from_host(a["text"].ctypes.data, int(a["text"].shape[0]), a["pos_packed"].ctypes.data,
+                                          a["l1"].ctypes.data, int(a["l1"].shape[0]), a["l2"].ctypes.data,
+                                          int(a["l2"].shape[0]), mode, device, C.byref(h)), "meme_index_from_host")
+        else:
+            _check(L.meme_index_load(prefix.encode(), mode, device, C.byref(h)), "meme_index_load")
+        self.h = h
+        self.mode = mode
+        self.device = device
+        self.sa_num = int(L.meme_index_sa_num(h))
+        self.device_bytes = int(L.meme_index_device_bytes(h))
+
+    def close(self):
+        if self.h:
+            lib().meme_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _check(lib().meme_index_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "meme_index_set_stream")
+
+    def download(self, keys=True, pos=True, isa=True):
+        n = self.sa_num
+        k = np.empty(n, np.uint64) if keys else None
+        p = np.empty(n, np.uint64) if pos else None
+        i = np.empty(n, np.uint64) if isa else None
+        _check(lib().meme_index_download(self.h, k.ctypes.data if keys else None, p.ctypes.data if pos else None,
+                                         i.ctypes.data if isa else None), "meme_index_download")
+        return k, p, i
+
+    # ---- seeding ----
+    @staticmethod
+    def _wrap(res: SeedResult) -> dict:
+        n, ns, nh = int(res.n_reads), int(res.n_smems), int(res.n_hits)
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt).copy()
+
+        return {"smems": arr(res.smems, ns, SMEM_DTYPE), "smem_off": arr(res.smem_off, n + 1, np.int64),
+                "hit_off": arr(res.hit_off, n + 1, np.int64), "hits": arr(res.hits, nh, np.uint64)}
+
+    def seed(self, codes: np.ndarray, offsets: np.ndarray, opt: SeedOpt | None = None) -> dict:
+        opt = opt or default_seed_opt()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        res = SeedResult()
+        _check(lib().meme_seed_batch(self.h, codes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(opt),
+                                     C.byref(res)), "meme_seed_batch")
+        return self._wrap(res)
+
+    def seed_upload(self, codes: np.ndarray, offsets: np.ndarray):
+        _check(lib().meme_seed_upload(self.h, codes.ctypes.data, offsets.ctypes.data, len(offsets) - 1), "meme_seed_upload")
+
+    def seed_upload_ptr(self, codes_ptr: int, offsets_ptr: int, n_reads: int):
+        _check(lib().meme_seed_upload(self.h, C.c_void_p(codes_ptr), C.c_void_p(offsets_ptr), n_reads), "meme_seed_upload")
+
+    def seed_run(self, opt: SeedOpt):
+        _check(lib().meme_seed_run(self.h, C.byref(opt)), "meme_seed_run")
+
+    def seed_download(self, copy: bool = True) -> dict:
+        res = SeedResult()
+        _check(lib().meme_seed_download(self.h, C.byref(res)), "meme_seed_download")
+        if not copy:
+            return {"n_reads": int(res.n_reads), "n_smems": int(res.n_smems), "n_hits": int(res.n_hits)}
+        return self._wrap(res)
+
+    def seed_totals(self):
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().meme_seed_totals(self.h, C.byref(a), C.byref(b)), "meme_seed_totals")
+        return int(a.value), int(b.value)
+
+    def seed_counters(self) -> dict:
+        c = (C.c_uint64 * 8)()
+        _check(lib().meme_seed_counters(self.h, C.byref(c)), "meme_seed_counters")
+        return {"searches": int(c[0]), "block_probes": int(c[1]), "kary_rounds": int(c[2]), "ext_rounds": int(c[3]),
+                "overflow_reads": int(c[4]), "launches": int(c[5])}
+
+
+class MemeBsw:
+    """Host mirror of BandedPairWiseSW (reference src/bandedSWA.h:L118-135): construct once, then
+    getScores(pairs, seqBufRef, seqBufQer, numPairs, w)."""
+
+    def __init__(self, opt: BswOpt | None = None, device: int = 0):
+        self.opt = opt or default_bsw_opt()
+        h = C.c_void_p()
+        _check(lib().meme_bsw_create(device, C.byref(h)), "meme_bsw_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().meme_bsw_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _check(lib().meme_bsw_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "meme_bsw_set_stream")
+
+    def get_scores(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int) -> np.ndarray:
+        out = np.ascontiguousarray(pairs.copy())
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        qer = np.ascontiguousarray(qer, dtype=np.uint8)
+        _check(lib().meme_bsw_batch(self.h, out.ctypes.data, len(out), ref.ctypes.data, len(ref), qer.ctypes.data,
+                                    len(qer), w, C.byref(self.opt)), "meme_bsw_batch")
+        return out
+
+    def upload(self, pairs, ref, qer):
+        _check(lib().meme_bsw_upload(self.h, pairs.ctypes.data, len(pairs), ref.ctypes.data, len(ref), qer.ctypes.data,
+                                     len(qer)), "meme_bsw_upload")
+
+    def run(self, w: int):
+        _check(lib().meme_bsw_run(self.h, w, C.byref(self.opt)), "meme_bsw_run")
+
+    def download(self, pairs: np.ndarray):
+        _check(lib().meme_bsw_download(self.h, pairs.ctypes.data), "meme_bsw_download")
+
+    def cells(self) -> int:
+        c = C.c_uint64()
+        _check(lib().meme_bsw_cells(self.h, C.byref(c)), "meme_bsw_cells")
+        return int(c.value)

@@ -1,0 +1,825 @@
+// meme_seed.cu -- kernel A: P-RMI learned-index SMEM seeding on sm_100a.
+//
+// Replaces, for a whole chunk of reads at once, the body of mem_kernel1_core_Learned up to the SMEM
+// sort (reference src/bwamem.cpp:L1249-1397) = Learned_getSMEMsAllPosOneThread (+ reseeding) and
+// Learned_bwtSeedStrategyAllPosOneThread{,_mem_tradeoff} (src/LearnedIndex_seeding.cpp:L913-1466),
+// built on one search primitive that stands for right_smem_search / mem_search / *_tradeoff
+// (L2131-4189).
+//
+// B200 design:
+//   * one warp per read, reads handed out by an atomic counter (persistent grid = SMs x resident CTAs);
+//     the per-read control flow (zig-zag, reseed, third round) is warp-uniform, so there is no
+//     divergence between lanes -- lanes only differ in WHICH suffix-array entry they probe;
+//   * the reference's last-mile search is a chain of ~6 dependent single-entry probes
+//     (binary search in the RMI error window, +-1 linear fix-up, neighbour probes).  Here the 32
+//     lanes load a CONTIGUOUS block of 32 SA entries around the prediction in one coalesced
+//     request (256 B of keys + 128 B of positions) and a __ballot_sync over "suffix < read"
+//     finds the insertion point; the same block already holds the neighbours' LCPs, so the SA
+//     interval, the level drops for min_intv > 1 and the third-round "shortest seed" logic are
+//     evaluated from registers with shuffles.  Windows wider than 32 entries are narrowed 32-ary
+//     (one round trip per factor of 32) and large intervals are bounded by a 32-ary gallop;
+//   * 2-bit compare: XOR of the inline 64-bit key with the read's 32-base word + __ffsll; only
+//     lanes whose first 32 bases match touch the packed reference (funnel-shifted 64-bit words);
+//   * RMI leaf evaluation is the reference's fp64 fma on a 32-byte re-laid-out record (one sector);
+//   * results are canonical (they depend on the suffix array only), which is what makes this
+//     cooperative formulation bit-exact with the reference's sequential one.
+#include <cub/device/device_scan.cuh>
+#include "meme_common.cuh"
+
+#define WARPS_PER_BLOCK 8
+#define RW 12                           // 64-bit words per packed strand (MEME_MAX_READ_LEN/32 + slack)
+#define NMW (MEME_MAX_READ_LEN / 32)    // 32-bit N-mask words per strand
+#define MAXS MEME_MAX_SMEMS_PER_READ
+#define FULL 0xffffffffu
+
+struct RawSmem {            // 16 bytes
+    u32 se;                 // start | end << 16
+    u32 cnt;                // SA interval size
+    u64 lo;                 // first SA index of the interval
+};
+
+struct WarpSm {
+    u64 fw[RW], rc[RW];
+    u32 nfw[NMW], nrc[NMW];
+    RawSmem sm[MAXS];
+};
+
+enum { CT_WORK = 0, CT_POOL = 1, CT_OVF = 2, CT_POOL_OVF = 3, CT_SEARCH = 8, CT_BLOCK = 9, CT_KARY = 10, CT_EXT = 11 };
+enum { START_RMI = 0, START_ISA_EXACT = 1, START_ISA_NEAR = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 interleave32(u32 lo_bits, u32 hi_bits)
+{   // bit k of lo_bits -> bit 2k, bit k of hi_bits -> bit 2k+1
+    u64 a = lo_bits, b = hi_bits;
+    a = (a | (a << 16)) & 0x0000FFFF0000FFFFull; b = (b | (b << 16)) & 0x0000FFFF0000FFFFull;
+    a = (a | (a << 8)) & 0x00FF00FF00FF00FFull;  b = (b | (b << 8)) & 0x00FF00FF00FF00FFull;
+    a = (a | (a << 4)) & 0x0F0F0F0F0F0F0F0Full;  b = (b | (b << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    a = (a | (a << 2)) & 0x3333333333333333ull;  b = (b | (b << 2)) & 0x3333333333333333ull;
+    a = (a | (a << 1)) & 0x5555555555555555ull;  b = (b | (b << 1)) & 0x5555555555555555ull;
+    return a | (b << 1);
+}
+
+__device__ __forceinline__ u64 text32(const u64 *__restrict__ pac, u64 p)
+{
+    u64 w = p >> 5;
+    int sh = (int)(p & 31) * 2;
+    u64 a = __ldg(pac + w);
+    if (sh == 0) return a;
+    return (a >> sh) | (__ldg(pac + w + 1) << (64 - sh));
+}
+
+__device__ __forceinline__ u64 qword(const u64 *qw, int from)
+{   // 32 read bases starting at `from` (shared memory, zero past the end)
+    int w = from >> 5, sh = (from & 31) * 2;
+    if (w >= RW - 1) return w < RW ? qw[w] >> sh : 0;
+    u64 a = qw[w];
+    if (sh == 0) return a;
+    return (a >> sh) | (qw[w + 1] << (64 - sh));
+}
+
+__device__ __forceinline__ int next_n(const u32 *nm, int from, int L)
+{   // first N at or after `from` (or L)
+    int w = from >> 5;
+    u32 m = nm[w] >> (from & 31);
+    if (m) { int p = from + __ffs(m) - 1; return p < L ? p : L; }
+    for (w++; w * 32 < L; w++)
+        if (nm[w]) { int p = w * 32 + __ffs(nm[w]) - 1; return p < L ? p : L; }
+    return L;
+}
+
+__device__ __forceinline__ u64 sa_pos(const IndexView &ix, u64 i)
+{
+    u64 p = __ldg(ix.pos_lo + i);
+    if (ix.pos_wide) p |= (u64)__ldg(ix.pos_hi + i) << 32;
+    return p;
+}
+
+__device__ __forceinline__ u64 isa_at(const IndexView &ix, u64 p)
+{
+    u64 i = __ldg(ix.isa_lo + p);
+    if (ix.pos_wide) i |= (u64)__ldg(ix.isa_hi + p) << 32;
+    return i;
+}
+
+// lcp(i) = min(LCP(T[SA[i]..], Q), V, sa_num - SA[i]) and "suffix < read" -- the contract of
+// compare_read_and_ref_binary* (reference L226-601); exact matches and text-end suffixes are "not less".
+__device__ __forceinline__ int lcp_at(const IndexView &ix, const u64 *qw, int from, int V, u64 idx, bool &less)
+{
+    u64 p = sa_pos(ix, idx);
+    u64 ref_len = ix.sa_num - p;
+    int cap = ref_len < (u64)V ? (int)ref_len : V;
+    u64 r = ix.keys ? __ldg(ix.keys + idx) : text32(ix.pac, p);
+    less = false;
+    for (int k = 0;; k++) {
+        u64 q = qword(qw, from + 32 * k);
+        u64 x = r ^ q;
+        if (x) {
+            int b = (__ffsll((long long)x) - 1) >> 1;
+            int l = 32 * k + b;
+            if (l >= cap) return cap;
+            less = ((r >> (2 * b)) & 3) < ((q >> (2 * b)) & 3);
+            return l;
+        }
+        if (32 * (k + 1) >= cap) return cap;
+        r = text32(ix.pac, p + 32 * (u64)(k + 1));
+    }
+}
+
+// P-RMI inference = learned_index_lookup (reference L186-210): fp64 fma on the leaf record,
+// optional partial third layer, clamp to [0, sa_num-1].
+__device__ __forceinline__ u64 fclamp(double v, double bound)
+{
+    if (v < 0.0) return 0;
+    return v > bound ? (u64)bound : (u64)v;
+}
+
+__device__ __forceinline__ u64 rmi_lookup(const IndexView &ix, u64 key, u64 &cerr, u64 &err)
+{
+    const RmiRec *rec = ix.l2 + (key >> ix.bit_shift);
+    double a = __ldg(&rec->alpha), b = __ldg(&rec->beta);
+    u64 e = __ldg(&rec->err);
+    double kd = __ull2double_rn(key);
+    double p = fma(b, kd, a);
+    if (e >> 63) {
+        u64 st = (e >> 32) & 0x7fffffff;
+        double num = (double)(e & 0xffffffffull);
+        rec = ix.l1 + st + fclamp(p, num - 1);
+        a = __ldg(&rec->alpha); b = __ldg(&rec->beta); e = __ldg(&rec->err);
+        p = fma(b, kd, a);
+    }
+    cerr = (e >> 32) & 0x3fffffff;
+    err = e & 0x7fffffff;
+    return fclamp(p, (double)ix.sa_num - 1.0);
+}
+
+// RMI key = Tokenization (reference L795-901): 32 bases, first base in the MSBs, positions at or
+// after min(V,32) padded with 3.
+__device__ __forceinline__ u64 rmi_key(u64 q0, int V)
+{
+    if (V < 32) q0 |= ~0ull << (2 * V);
+    u64 y = __brevll(q0);
+    return ((y & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((y & 0x5555555555555555ull) << 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-warp search machinery
+// ---------------------------------------------------------------------------------------------
+struct Searcher {
+    const IndexView &ix;
+    WarpSm *ws;
+    int lane;
+    int L;                  // read length
+    int n_sm;               // SMEMs collected so far
+    bool overflow;
+    // statistics
+    u32 st_search, st_block, st_kary, st_ext;
+    // query of the search in flight
+    const u64 *qw; int qfrom;
+    // block state (valid between locate() and the end of the search)
+    u64 base; int nvalid; int lcp;     // lcp: this lane's value (-1 if lane invalid)
+    // level state
+    u64 lo, hi; int nbl, nbr; int lev;
+
+    __device__ Searcher(const IndexView &ix_, WarpSm *ws_, int lane_) : ix(ix_), ws(ws_), lane(lane_) {}
+
+    __device__ __forceinline__ void probe_block(u64 b, int V)
+    {   // contiguous block [b, b+32): full lcp per lane
+        u64 n = ix.sa_num;
+        base = b;
+        u64 idx = b + lane;
+        bool valid = idx < n;
+        bool less = false;
+        lcp = valid ? lcp_at(ix, qw, qfrom, V, idx, less) : -1;
+        nvalid = __popc(__ballot_sync(FULL, valid));
+        lessmask = __ballot_sync(FULL, valid && less);
+        st_block++;
+    }
+    u32 lessmask;
+
+    // Locate a block that contains a suffix with the maximal lcp. center/rad = hint window.
+    __device__ void locate(int V, u64 center, u64 rad_lo, u64 rad_hi)
+    {
+        const u64 n = ix.sa_num;
+        u64 lo_b = 0, hi_b = n;                 // insertion point t in [lo_b, hi_b]
+        for (int it = 0; it < 48; it++) {
+            u64 pa = center > rad_lo ? center - rad_lo : 0;
+            pa = pa < lo_b ? lo_b : (pa > hi_b ? hi_b : pa);
+            u64 pb = center + rad_hi + 1;
+            pb = pb < lo_b ? lo_b : (pb > hi_b ? hi_b : pb);
+            u64 span = pb - pa;
+            if (span <= 30) {
+                // contiguous: entries pa-1 .. pb (span + 2 of them), centred in the block
+                u64 slack = (30 - span) / 2;
+                u64 b = pa > 1 + slack ? pa - 1 - slack : 0;
+                if (n >= 32 && b > n - 32) b = n - 32;
+                probe_block(b, V);
+                int c = lessmask == FULL ? 32 : __ffs(~lessmask) - 1;      // leading "less" lanes
+                bool left_ok = c > 0 || b == 0;
+                bool right_ok = c < nvalid || b + nvalid == n;
+                if (left_ok && right_ok) return;
+                if (!left_ok) hi_b = b; else lo_b = b + nvalid;
+            } else {
+                u64 stride = (span + 31) / 32;
+                u64 idx = pa + (u64)(lane + 1) * stride - 1;
+                bool valid = idx < pb;
+                bool less = false;
+                if (valid) lcp_at(ix, qw, qfrom, V, idx, less);
+                u32 vm = __ballot_sync(FULL, valid), lm = __ballot_sync(FULL, valid && less);
+                int nv = __popc(vm);
+                int c = lm == FULL ? 32 : __ffs(~lm) - 1;
+                if (c > nv) c = nv;
+                if (c > 0) { u64 nl = pa + (u64)c * stride; if (nl > lo_b) lo_b = nl; }
+                if (c < nv) { u64 nh = pa + (u64)(c + 1) * stride - 1; if (nh < hi_b) hi_b = nh; }
+                else if (pb > lo_b && c == nv && nv > 0) { /* all probed entries are smaller */ }
+                st_kary++;
+            }
+            // widen the tentative window (the hint may be wrong: the reference's linear fix-up,
+            // L2297-2357, makes the same guarantee)
+            rad_lo = rad_lo * 32 + 32;
+            rad_hi = rad_hi * 32 + 32;
+        }
+        // not reached for a sorted suffix array; keep the last block
+    }
+
+    // Furthest index in direction dir (+1/-1) reachable from `from` (known to satisfy lcp >= Lreq)
+    // through entries that all satisfy lcp >= Lreq; nb = lcp of the first entry that does not (0 at
+    // the array ends).  32-ary gallop then 32-ary narrowing.  Stops early once `limit` entries
+    // beyond `from` are known to qualify (the exact edge is then not needed).
+    __device__ void extend(int dir, u64 from, int Lreq, u64 limit, u64 &edge, int &nb)
+    {
+        const u64 n = ix.sa_num;
+        u64 cur = from, s = 1;
+        bool up = true;
+        for (;;) {
+            u64 off = (u64)(lane + 1) * s;
+            bool valid;
+            u64 idx;
+            if (dir > 0) { idx = cur + off; valid = idx < n && idx > cur; }
+            else { valid = cur >= off; idx = cur - off; }
+            bool less;
+            int l = valid ? lcp_at(ix, qw, qfrom, Lreq, idx, less) : 0;
+            u32 okm = __ballot_sync(FULL, valid && l >= Lreq);
+            int c = okm == FULL ? 32 : __ffs(~okm) - 1;
+            st_ext++;
+            cur = dir > 0 ? cur + (u64)c * s : cur - (u64)c * s;
+            if (c == 32) {
+                u64 gone = dir > 0 ? cur - from : from - cur;
+                if (gone >= limit) { edge = cur; nb = Lreq; return; }
+                if (up && s < (1ull << 40)) s *= 32;
+                continue;
+            }
+            if (s == 1) { nb = __shfl_sync(FULL, l, c); edge = cur; return; }
+            up = false;
+            s /= 32;
+        }
+    }
+
+    // Start the level walk from the located block: level = maximal lcp, [lo,hi] = its interval.
+    // The interval is made exact (extended past the block) only if it will be emitted
+    // (exact_from <= level) or if it is still smaller than `need`.
+    __device__ void level_init(u64 need, int exact_from)
+    {
+        const u64 n = ix.sa_num;
+        int m = lcp;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+        lev = m;
+        u32 mask = __ballot_sync(FULL, lcp >= lev && lcp >= 0);
+        int anchor = __ffs(mask) - 1;
+        // contiguous run of qualifying lanes that contains the anchor
+        u32 inv = ~mask;
+        u32 above = inv & ~((2u << anchor) - 1);         // zeros above the anchor
+        int last = above ? __ffs(above) - 2 : 31;
+        if (last > nvalid - 1) last = nvalid - 1;
+        int first = anchor;
+        lo = base + first; hi = base + last;
+        const bool exact = lev >= exact_from;
+        if (!exact && hi - lo + 1 >= need) { nbl = nbr = lev; return; }
+        const u64 limit = exact ? ~0ull : need;
+        if (first > 0) nbl = __shfl_sync(FULL, lcp, first - 1);
+        else if (base == 0) nbl = 0;
+        else extend(-1, lo, lev, limit, lo, nbl);
+        if (last < nvalid - 1) nbr = __shfl_sync(FULL, lcp, last + 1);
+        else if (base + nvalid == n) nbr = 0;
+        else extend(+1, hi, lev, limit, hi, nbr);
+    }
+
+    // Drop to the next level (the larger neighbour lcp) and regrow the interval (reference L2569-2574).
+    __device__ void level_next(u64 limit)
+    {
+        const u64 n = ix.sa_num;
+        lev = max(nbl, nbr);
+        if (lev <= 0) { lev = 0; lo = 0; hi = n - 1; nbl = nbr = 0; return; }
+        u32 mask = __ballot_sync(FULL, lcp >= lev && lcp >= 0);
+        if (nbl >= lev) {
+            if (lo > base && lo <= base + (u64)nvalid) {          // lo-1 lies in the block
+                int p = (int)(lo - base);
+                u32 x = ~mask & (p >= 32 ? FULL : ((1u << p) - 1));
+                if (x == 0) {
+                    lo = base;
+                    if (base == 0) nbl = 0; else extend(-1, lo, lev, limit, lo, nbl);
+                } else {
+                    int z = 31 - __clz(x);
+                    lo = base + z + 1;
+                    nbl = __shfl_sync(FULL, lcp, z);
+                }
+            } else if (lo == 0) nbl = 0;
+            else extend(-1, lo, lev, limit, lo, nbl);
+        }
+        if (nbr >= lev) {
+            if (hi + 1 >= base && hi + 1 < base + (u64)nvalid) {  // hi+1 lies in the block
+                int p = (int)(hi + 1 - base);
+                u32 x = ~mask & ~((1u << p) - 1) & (nvalid >= 32 ? FULL : ((1u << nvalid) - 1));
+                if (x == 0) {
+                    hi = base + nvalid - 1;
+                    if (base + nvalid == n) nbr = 0; else extend(+1, hi, lev, limit, hi, nbr);
+                } else {
+                    int z = __ffs(x) - 1;
+                    hi = base + z - 1;
+                    nbr = __shfl_sync(FULL, lcp, z);
+                }
+            } else if (hi == n - 1) nbr = 0;
+            else extend(+1, hi, lev, limit, hi, nbr);
+        }
+    }
+
+    __device__ void begin(int strand, int from, int &V)
+    {
+        qw = strand ? ws->rc : ws->fw;
+        qfrom = from;
+        V = next_n(strand ? ws->nrc : ws->nfw, from, L) - from;
+        st_search++;
+    }
+
+    __device__ void locate_by(int V, int start_mode, u64 hint)
+    {
+        if (start_mode == START_ISA_EXACT) {
+            u64 b = hint > 15 ? hint - 15 : 0;
+            if (ix.sa_num >= 32 && b > ix.sa_num - 32) b = ix.sa_num - 32;
+            probe_block(b, V);
+        } else if (start_mode == START_ISA_NEAR) {
+            locate(V, hint, 8, 8);
+        } else {
+            u64 cerr, err;
+            u64 est = rmi_lookup(ix, rmi_key(qword(qw, qfrom), V), cerr, err);
+            locate(V, est, cerr, err);
+        }
+    }
+
+    __device__ void push(int start, int end, u64 lo_, u64 cnt)
+    {
+        if (n_sm >= MAXS) { overflow = true; return; }
+        if (lane == 0) {
+            RawSmem r;
+            r.se = (u32)start | ((u32)end << 16);
+            r.cnt = cnt > 0xffffffffull ? 0xffffffffu : (u32)cnt;
+            r.lo = lo_;
+            ws->sm[n_sm] = r;
+        }
+        n_sm++;
+    }
+
+    // right_smem_search / mem_search and their _tradeoff twins: level of the query with at least
+    // min_intv occurrences; emits the SMEM when asked and long enough.
+    __device__ int search(int pivot, bool right, bool emit, int min_intv, int min_seed_len, int start_mode, u64 hint,
+                          u64 *pos_out)
+    {
+        int V;
+        begin(right ? 0 : 1, right ? pivot : L - 1 - pivot, V);
+        locate_by(V, start_mode, hint);
+        u64 need = (u64)min_intv;
+        level_init(need, emit ? min_seed_len : 0x7fffffff);
+        // an interval is exact as long as every extension ran to its end; extensions are only cut
+        // short (limit) when the level is too short to be emitted
+        while (hi - lo + 1 < need) {
+            bool exact_needed = emit && max(nbl, nbr) >= min_seed_len;
+            level_next(exact_needed ? ~0ull : need);
+        }
+        if (emit && lev >= min_seed_len) push(pivot, pivot + lev, lo, hi - lo + 1);
+        if (pos_out) *pos_out = lo;
+        return lev;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the seeding kernel
+// ---------------------------------------------------------------------------------------------
+struct ReadState {
+    bool full_match; u64 max_refpos;
+    bool use_cached; int cache_pivot, cache_pivot_end; u64 cache_refpos;
+    int min_intv, min_seed_len;
+};
+
+__device__ __forceinline__ int do_search(Searcher &S, ReadState &R, int pivot, bool right, bool emit)
+{   // start selection of reference L1741-1816 / L1926-2040
+    const IndexView &ix = S.ix;
+    if (ix.mode == 3) {
+        if (R.full_match) {
+            u64 rp = right ? R.max_refpos + pivot : ix.sa_num - R.max_refpos - pivot - 1;
+            return S.search(pivot, right, emit, R.min_intv, R.min_seed_len, START_ISA_EXACT, isa_at(ix, rp), nullptr);
+        }
+        if (R.use_cached) {
+            if (right && R.cache_pivot_end >= pivot + 18 && pivot >= R.cache_pivot)
+                return S.search(pivot, true, emit, R.min_intv, R.min_seed_len, START_ISA_NEAR,
+                                isa_at(ix, R.cache_refpos + pivot - R.cache_pivot), nullptr);
+            if (!right && pivot < R.cache_pivot_end && R.cache_pivot + 18 <= pivot)
+                return S.search(pivot, false, emit, R.min_intv, R.min_seed_len, START_ISA_NEAR,
+                                isa_at(ix, ix.sa_num + R.cache_pivot - R.cache_refpos - pivot - 1), nullptr);
+        }
+    }
+    return S.search(pivot, right, emit, R.min_intv, R.min_seed_len, START_RMI, 0, nullptr);
+}
+
+__device__ __forceinline__ bool is_n(const u32 *nm, int p) { return (nm[p >> 5] >> (p & 31)) & 1; }
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restrict__ read_off, int64_t n_reads,
+       meme_seed_opt_t opt, RawSmem *__restrict__ pool, u64 pool_cap, u64 *__restrict__ rd_pool_off,
+       u32 *__restrict__ rd_nsmem, u64 *__restrict__ rd_nhit, u64 *__restrict__ ctrl)
+{
+    __shared__ WarpSm wsm[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpSm *ws = &wsm[wid];
+    Searcher S(ix, ws, lane);
+    S.st_search = S.st_block = S.st_kary = S.st_ext = 0;
+    for (;;) {
+        u64 r = 0;
+        if (lane == 0) r = atomicAdd((unsigned long long *)&ctrl[CT_WORK], 1ull);
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= (u64)n_reads) break;
+        const int64_t o0 = read_off[r];
+        const int L = (int)(read_off[r + 1] - o0);
+        const uint8_t *seq = codes + o0;
+        __syncwarp();
+        // ---- pack the read and its reverse complement (reference src/bwamem.cpp:L1277-1344) ----
+        for (int w = 0; w < RW; w++) {
+            int p = w * 32 + lane;
+            u32 cf = p < L ? seq[p] : 0, cr = p < L ? seq[L - 1 - p] : 0;
+            bool nf = cf > 3, nr = cr > 3;
+            cf = nf ? 0 : cf;
+            cr = nr ? 0 : 3 - cr;
+            if (p >= L) cr = 0;
+            u32 f0 = __ballot_sync(FULL, cf & 1), f1 = __ballot_sync(FULL, cf & 2);
+            u32 r0 = __ballot_sync(FULL, cr & 1), r1 = __ballot_sync(FULL, cr & 2);
+            u32 mf = __ballot_sync(FULL, nf), mr = __ballot_sync(FULL, nr);
+            if (lane == 0) {
+                ws->fw[w] = interleave32(f0, f1);
+                ws->rc[w] = interleave32(r0, r1);
+                if (w < NMW) { ws->nfw[w] = mf; ws->nrc[w] = mr; }
+            }
+        }
+        __syncwarp();
+        S.L = L; S.n_sm = 0; S.overflow = false;
+        ReadState R;
+        R.full_match = false; R.use_cached = false; R.max_refpos = 0;
+        R.min_intv = 1; R.min_seed_len = opt.min_seed_len;
+        const u32 *nf = ws->nfw;
+        // ---- rounds 1+2: Learned_getSMEMsAllPosOneThread (reference L913-972) ----
+        int pivot = 0;
+        while (pivot < L) {
+            int before = S.n_sm;
+            // --- Learned_getSMEMsOnePosOneThread_step1 (L1691-1894) ---
+            if (is_n(nf, pivot)) {
+                pivot = (L - pivot < R.min_seed_len) ? L : pivot + 1;
+            } else if (pivot != 0 && !is_n(nf, pivot - 1)) {
+                int sp = pivot;
+                while (sp < L) {
+                    if (is_n(nf, sp)) {
+                        if (L - sp < R.min_seed_len) { pivot = L; sp = L; }
+                        else { sp += 1; pivot += 1; }
+                        continue;
+                    }
+                    int l = do_search(S, R, pivot, false, false);
+                    pivot = pivot - l + 1;
+                    if (L - pivot < R.min_seed_len) break;
+                    int rr = do_search(S, R, pivot, true, true);
+                    sp = pivot + rr;
+                    pivot = sp;
+                }
+                pivot = L;
+            } else {
+                u64 pos;
+                int len = S.search(pivot, true, true, 1, R.min_seed_len, START_RMI, 0, &pos);
+                if (ix.mode == 3 && len == L) { R.full_match = true; R.max_refpos = sa_pos(ix, pos); }
+                pivot += len;
+            }
+            int after = S.n_sm;
+            if (opt.rounds < 2) continue;
+            // --- reseeding: Learned_getSMEMsOnePosOneThread (L1897-2126) for long, rare SMEMs ---
+            for (int k = before; k < after && k < MAXS; k++) {
+                RawSmem m = ws->sm[k];
+                int qb = m.se & 0xffff, qe = m.se >> 16;
+                if (qe - qb < opt.split_len || m.cnt > (u32)opt.split_width) continue;
+                R.min_intv = (int)m.cnt + 1;
+                R.use_cached = false;
+                if (ix.mode == 3 && m.cnt >= 1 && m.cnt < 10) {
+                    R.use_cached = true; R.cache_pivot = qb; R.cache_pivot_end = qe;
+                    R.cache_refpos = sa_pos(ix, m.lo);
+                }
+                int p2 = (qb + qe) >> 1;
+                // pivot sits inside an SMEM: not N, predecessor not N
+                int len = do_search(S, R, p2, true, false);
+                int next = p2 + len, sp = p2;
+                while (sp < next) {
+                    int l = do_search(S, R, p2, false, false);
+                    p2 = p2 - l + 1;
+                    if (next - p2 < R.min_seed_len) break;
+                    int rr = do_search(S, R, p2, true, true);
+                    sp = p2 + rr;
+                    p2 = sp;
+                }
+                R.use_cached = false;
+                R.min_intv = 1;
+            }
+        }
+        // ---- round 3: Learned_bwtSeedStrategyAllPosOneThread{,_mem_tradeoff} (L974-1466) ----
+        if (opt.rounds >= 3 && opt.max_mem_intv > 0) {
+            const int msl = opt.min_seed_len + 1, mi = opt.max_mem_intv;
+            pivot = 0;
+            while (pivot < L - msl + 1) {
+                if (is_n(nf, pivot)) { pivot++; continue; }
+                int V;
+                S.begin(0, pivot, V);
+                if (V < msl) { S.st_search--; pivot += V; continue; }
+                if (R.full_match) S.locate_by(V, START_ISA_EXACT, isa_at(ix, R.max_refpos + pivot));
+                else S.locate_by(V, START_RMI, 0);
+                S.level_init((u64)mi, 0x7fffffff);
+                if (S.lev < msl) { pivot += msl; continue; }
+                u64 last_lo = S.lo, last_cnt = 0, cnt;
+                int emit_len;
+                for (;;) {
+                    cnt = S.hi - S.lo + 1;
+                    if (cnt >= (u64)mi) { cnt = last_cnt; emit_len = S.lev + 1; break; }   // L1243-1251
+                    if (max(S.nbl, S.nbr) < msl) { last_lo = S.lo; emit_len = msl; break; } // L1252-1258
+                    last_lo = S.lo; last_cnt = cnt;
+                    S.level_next((u64)mi);
+                }
+                if (cnt > 0 && cnt < (u64)mi) S.push(pivot, pivot + max(emit_len, msl), last_lo, cnt);
+                pivot += emit_len;
+            }
+        }
+        // ---- sort by (start, end, emission order) = ks_introsort(mem_smem_sort_lt_learned), bwamem.cpp:L1397 ----
+        const int ns = S.n_sm;
+        __syncwarp();
+        u64 poff = 0;
+        if (lane == 0) poff = atomicAdd((unsigned long long *)&ctrl[CT_POOL], (unsigned long long)ns);
+        poff = __shfl_sync(FULL, poff, 0);
+        bool fits = poff + ns <= pool_cap;
+        u64 nh = 0;
+        for (int i = lane; i < ns; i += 32) {
+            RawSmem a = ws->sm[i];
+            u32 ka = ((a.se & 0xffff) << 16) | (a.se >> 16);
+            int rank = 0;
+            for (int j = 0; j < ns; j++) {
+                u32 se = ws->sm[j].se;
+                u32 kb = ((se & 0xffff) << 16) | (se >> 16);
+                rank += (kb < ka) || (kb == ka && j < i);
+            }
+            if (fits) pool[poff + rank] = a;
+            u64 c = a.cnt;
+            if (opt.max_occ > 0) {
+                u64 step = c > (u64)opt.max_occ ? c / opt.max_occ : 1;
+                u64 k = (c + step - 1) / step;
+                c = k < (u64)opt.max_occ ? k : (u64)opt.max_occ;
+            }
+            nh += c;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(FULL, nh, o);
+        if (lane == 0) {
+            rd_pool_off[r] = poff;
+            rd_nsmem[r] = fits ? ns : 0;
+            rd_nhit[r] = fits ? nh : 0;
+            if (!fits) atomicExch((unsigned long long *)&ctrl[CT_POOL_OVF], 1ull);
+            if (S.overflow) atomicAdd((unsigned long long *)&ctrl[CT_OVF], 1ull);
+        }
+    }
+    // statistics
+    u32 a = S.st_search, b = S.st_block, c = S.st_kary, d = S.st_ext;
+    if (lane == 0) {
+        atomicAdd((unsigned long long *)&ctrl[CT_SEARCH], (unsigned long long)a);
+        atomicAdd((unsigned long long *)&ctrl[CT_BLOCK], (unsigned long long)b);
+        atomicAdd((unsigned long long *)&ctrl[CT_KARY], (unsigned long long)c);
+        atomicAdd((unsigned long long *)&ctrl[CT_EXT], (unsigned long long)d);
+    }
+}
+
+// per-read counts -> int64 arrays of n+1 entries (last = 0) for the exclusive scans
+__global__ void k_counts(const u32 *__restrict__ nsmem, const u64 *__restrict__ nhit, int64_t n,
+                         int64_t *__restrict__ smem_off, int64_t *__restrict__ hit_off)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    smem_off[i] = i < n ? (int64_t)nsmem[i] : 0;
+    hit_off[i] = i < n ? (int64_t)nhit[i] : 0;
+}
+
+// Materialise the read-ordered SMEM records and hit lists: hits = SA[lo + k*step] (reference L2639-2657,
+// sampled as mem_chain_Learned consumes them when max_occ > 0, src/bwamem.cpp:L1154-1155).
+__global__ void k_gather(IndexView ix, const RawSmem *__restrict__ pool, const u64 *__restrict__ rd_pool_off,
+                         const int64_t *__restrict__ smem_off, const int64_t *__restrict__ hit_off, int64_t n_reads,
+                         int max_occ, meme_smem_t *__restrict__ smems, u64 *__restrict__ hits)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_reads) return;
+    int64_t s0 = smem_off[r];
+    int ns = (int)(smem_off[r + 1] - s0);
+    const RawSmem *src = pool + rd_pool_off[r];
+    u64 *hdst = hits + hit_off[r];
+    int64_t hb = 0;
+    for (int k = 0; k < ns; k++) {
+        RawSmem a = src[k];
+        u64 c = a.cnt, step = 1, take = c;
+        if (max_occ > 0) {
+            step = c > (u64)max_occ ? c / max_occ : 1;
+            take = (c + step - 1) / step;
+            if (take > (u64)max_occ) take = (u64)max_occ;
+        }
+        for (u64 j = lane; j < take; j += 32) hdst[hb + j] = sa_pos(ix, a.lo + j * step);
+        if (lane == 0) {
+            meme_smem_t m;
+            m.start = a.se & 0xffff; m.end = a.se >> 16;
+            m.hitbeg = (int32_t)hb; m.hitcount = (int32_t)a.cnt;
+            m.cache_refpos = sa_pos(ix, a.lo);
+            smems[s0 + k] = m;
+        }
+        hb += (int64_t)take;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host API
+// ---------------------------------------------------------------------------------------------
+extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads)
+{
+    if (!ix || !read_off || n_reads < 0 || (n_reads > 0 && !codes)) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    int64_t n_codes = n_reads ? read_off[n_reads] - read_off[0] : 0;
+    if (n_reads && read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
+    for (int64_t i = 0; i < n_reads; i++) {
+        int64_t len = read_off[i + 1] - read_off[i];
+        if (len < 0 || len > MEME_MAX_READ_LEN) {
+            meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
+            return MEME_E_ARG;
+        }
+    }
+    int rc;
+    cudaStream_t st = ix->stream;
+    if ((rc = meme_grow_device((void **)&ix->d_codes, &ix->cap_codes, (size_t)n_codes + 64, 1, st))) return rc;
+    size_t old_cap = ix->cap_reads;
+    if ((rc = meme_grow_device((void **)&ix->d_read_off, &ix->cap_reads, (size_t)n_reads + 1, 8, st))) return rc;
+    if (ix->cap_reads != old_cap || !ix->d_rd_pool_off) {
+        size_t c = ix->cap_reads, dummy;
+        void **bufs[] = {(void **)&ix->d_rd_pool_off, (void **)&ix->d_rd_nsmem, (void **)&ix->d_rd_nhit,
+                         (void **)&ix->d_smem_off, (void **)&ix->d_hit_off};
+        size_t el[] = {8, 4, 8, 8, 8};
+        for (int k = 0; k < 5; k++) {
+            if (*bufs[k]) { CUDA_TRY(cudaFree(*bufs[k])); *bufs[k] = nullptr; }
+            dummy = 0;
+            if ((rc = meme_grow_device(bufs[k], &dummy, c, el[k], st))) return rc;
+        }
+    }
+    if (n_codes) CUDA_TRY(cudaMemcpyAsync(ix->d_codes, codes, (size_t)n_codes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->d_read_off, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    ix->n_reads = n_reads;
+    ix->n_codes = n_codes;
+    ix->ran = 0;
+    return MEME_OK;
+}
+
+static int seed_launch(meme_index_t *ix, const meme_seed_opt_t *opt)
+{
+    cudaStream_t st = ix->stream;
+    int64_t n = ix->n_reads;
+    int dev_sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, WARPS_PER_BLOCK * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t need_blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int64_t grid = (int64_t)dev_sms * per_sm;
+    if (grid > need_blocks) grid = need_blocks;
+    if (grid < 1) grid = 1;
+    CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, 16 * 8, st));
+    k_seed<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, st>>>(ix->v, ix->d_codes, ix->d_read_off, n, *opt,
+                                                          (RawSmem *)ix->d_pool, ix->cap_pool, ix->d_rd_pool_off,
+                                                          ix->d_rd_nsmem, ix->d_rd_nhit, ix->d_ctrl);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
+{
+    if (!ix || !opt) { meme_set_error("null argument"); return MEME_E_ARG; }
+    if (opt->min_seed_len < 1 || opt->rounds < 1) { meme_set_error("bad seeding options"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int64_t n = ix->n_reads;
+    int rc;
+    ix->last_opt = *opt;
+    if (n == 0) { ix->ran = 1; return MEME_OK; }
+    if (!ix->d_pool) {
+        size_t want = (size_t)n * 24 + 4096;
+        if ((rc = meme_grow_device(&ix->d_pool, &ix->cap_pool, want, sizeof(RawSmem), st))) return rc;
+    }
+    for (int attempt = 0;; attempt++) {
+        if ((rc = seed_launch(ix, opt))) return rc;
+        // the pool is bump-allocated; if it overflowed, grow it to the exact need and rerun
+        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ix->h_ctrl[CT_OVF]) {
+            meme_set_error("%llu read(s) produced more than %d SMEMs", (unsigned long long)ix->h_ctrl[CT_OVF], MAXS);
+            return MEME_E_OVERFLOW;
+        }
+        if (!ix->h_ctrl[CT_POOL_OVF]) break;
+        if (attempt >= 2) { meme_set_error("SMEM pool overflow persists"); return MEME_E_NOMEM; }
+        if ((rc = meme_grow_device(&ix->d_pool, &ix->cap_pool, (size_t)ix->h_ctrl[CT_POOL] + 1024, sizeof(RawSmem), st))) return rc;
+    }
+    // offsets
+    k_counts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(ix->d_rd_nsmem, ix->d_rd_nhit, n, ix->d_smem_off, ix->d_hit_off);
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, ix->d_smem_off, ix->d_smem_off, (int)(n + 1), st);
+    if ((rc = meme_grow_device(&ix->d_scan_tmp, &ix->cap_scan_tmp, tmp + 256, 1, st))) return rc;
+    size_t t2 = ix->cap_scan_tmp;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ix->d_scan_tmp, t2, ix->d_smem_off, ix->d_smem_off, (int)(n + 1), st));
+    t2 = ix->cap_scan_tmp;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ix->d_scan_tmp, t2, ix->d_hit_off, ix->d_hit_off, (int)(n + 1), st));
+    ix->launches += 3;
+    int64_t tot[2];
+    CUDA_TRY(cudaMemcpyAsync(&tot[0], ix->d_smem_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&tot[1], ix->d_hit_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if ((rc = meme_grow_device((void **)&ix->d_smems, &ix->cap_smems, (size_t)tot[0] + 1, sizeof(meme_smem_t), st))) return rc;
+    if ((rc = meme_grow_device((void **)&ix->d_hits, &ix->cap_hits, (size_t)tot[1] + 1, 8, st))) return rc;
+    int64_t threads = n * 32;
+    k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ix->v, (const RawSmem *)ix->d_pool, ix->d_rd_pool_off,
+                                                              ix->d_smem_off, ix->d_hit_off, n, opt->max_occ,
+                                                              ix->d_smems, ix->d_hits);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    ix->h_ctrl[32] = (u64)tot[0];
+    ix->h_ctrl[33] = (u64)tot[1];
+    ix->ran = 1;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits)
+{
+    if (!ix || !ix->ran) { meme_set_error("no completed seeding run"); return MEME_E_ARG; }
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    if (n_smems) *n_smems = ix->n_reads ? (int64_t)ix->h_ctrl[32] : 0;
+    if (n_hits) *n_hits = ix->n_reads ? (int64_t)ix->h_ctrl[33] : 0;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_counters(meme_index_t *ix, uint64_t counters[8])
+{
+    if (!ix || !counters) return MEME_E_ARG;
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    counters[0] = ix->h_ctrl[CT_SEARCH]; counters[1] = ix->h_ctrl[CT_BLOCK]; counters[2] = ix->h_ctrl[CT_KARY];
+    counters[3] = ix->h_ctrl[CT_EXT]; counters[4] = ix->h_ctrl[CT_OVF]; counters[5] = ix->launches;
+    counters[6] = counters[7] = 0;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out)
+{
+    if (!ix || !out || !ix->ran) { meme_set_error("no completed seeding run"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int64_t n = ix->n_reads;
+    int64_t ns = n ? (int64_t)ix->h_ctrl[32] : 0, nh = n ? (int64_t)ix->h_ctrl[33] : 0;
+    int rc;
+    if ((rc = meme_grow_pinned((void **)&ix->h_smems, &ix->hcap_smems, (size_t)ns + 1, sizeof(meme_smem_t)))) return rc;
+    if ((rc = meme_grow_pinned((void **)&ix->h_hits, &ix->hcap_hits, (size_t)nh + 1, 8))) return rc;
+    size_t c0 = ix->hcap_off;
+    if ((rc = meme_grow_pinned((void **)&ix->h_smem_off, &c0, (size_t)n + 1, 8))) return rc;
+    c0 = ix->hcap_off;
+    if ((rc = meme_grow_pinned((void **)&ix->h_hit_off, &c0, (size_t)n + 1, 8))) return rc;
+    ix->hcap_off = c0;
+    if (n) {
+        if (ns) CUDA_TRY(cudaMemcpyAsync(ix->h_smems, ix->d_smems, (size_t)ns * sizeof(meme_smem_t), cudaMemcpyDeviceToHost, st));
+        if (nh) CUDA_TRY(cudaMemcpyAsync(ix->h_hits, ix->d_hits, (size_t)nh * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_smem_off, ix->d_smem_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_hit_off, ix->d_hit_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        ix->h_smem_off[0] = 0; ix->h_hit_off[0] = 0;
+    }
+    out->n_reads = n; out->n_smems = ns; out->n_hits = nh;
+    out->smems = ix->h_smems; out->smem_off = ix->h_smem_off; out->hit_off = ix->h_hit_off; out->hits = (const uint64_t *)ix->h_hits;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                               const meme_seed_opt_t *opt, meme_seed_result_t *out)
+{
+    int rc;
+    if ((rc = meme_seed_upload(ix, codes, read_off, n_reads))) return rc;
+    if ((rc = meme_seed_run(ix, opt))) return rc;
+    return meme_seed_download(ix, out);
+}

@@ -52,21 +52,38 @@ def _segment_bounds(seg: torch.Tensor, nseg: int):
     return start, end, cnt
 
 
-def _fit_lines(kd: torch.Tensor, target: torch.Tensor, start, end, cnt, next_target):
-    """Endpoint line per segment mapping kd -> target; empty segments are constants."""
-    dev = kd.device
-    nz = cnt > 0
-    s = torch.where(nz, start, torch.zeros_like(start))
-    e = torch.where(nz, end - 1, torch.zeros_like(end))
-    k0, k1 = kd[s], kd[e]
-    t0, t1 = target[s], target[e]
-    dk = k1 - k0
-    beta = torch.where(dk > 0, (t1 - t0) / torch.where(dk > 0, dk, torch.ones_like(dk)), torch.zeros_like(dk))
-    # centre the line between the first and last target when all keys are equal
-    alpha = torch.where(dk > 0, t0 - beta * k0, (t0 + t1) * 0.5)
-    alpha = torch.where(nz, alpha, next_target)
-    beta = torch.where(nz, beta, torch.zeros_like(beta))
+def _fit_lines(kd: torch.Tensor, n: int, first: torch.Tensor, last: torch.Tensor, nonempty: torch.Tensor,
+               empty_rank: torch.Tensor):
+    """One line per segment through its two OUTSIDE neighbours: (key[first-1], first-1) and
+    (key[last+1], last+1), `first`/`last` being global ranks of the segment's first/last key.
+    Every key that can fall into the segment lies between those neighbours, so the prediction
+    stays inside [first-1, last+1] for unseen keys too (the reference's trainer also feeds one
+    neighbour point per side into its least-squares fit, two_layer.rs:L52-83).  Empty segments
+    are constants = rank of the next key (two_layer.rs:L1453-1463)."""
+    f = torch.where(nonempty, first, torch.zeros_like(first))
+    l = torch.where(nonempty, last, torch.zeros_like(last))
+    has_prev = f > 0
+    has_next = l < n - 1
+    k_prev = torch.where(has_prev, kd[torch.clamp(f - 1, min=0)], torch.zeros_like(kd[f]))
+    k_next = torch.where(has_next, kd[torch.clamp(l + 1, max=n - 1)], torch.full_like(kd[l], 18446744073709551616.0))
+    t_prev = (f - 1).to(torch.float64)
+    t_next = (l + 1).to(torch.float64)
+    dk = k_next - k_prev
+    ok = dk > 0
+    beta = torch.where(ok, (t_next - t_prev) / torch.where(ok, dk, torch.ones_like(dk)), torch.zeros_like(dk))
+    alpha = torch.where(ok, t_prev - beta * k_prev, (t_prev + t_next) * 0.5)
+    alpha = torch.where(nonempty, alpha, empty_rank)
+    beta = torch.where(nonempty, beta, torch.zeros_like(beta))
     return alpha, beta
+
+
+def _errors(kd, rank, seg, nseg, alpha, beta, n):
+    pred = torch.floor(torch.clamp(beta[seg] * kd + alpha[seg], 0.0, float(n - 1)))
+    diff = (pred - rank).to(torch.int64)
+    dev = kd.device
+    below = torch.zeros(nseg, dtype=torch.int64, device=dev).scatter_reduce_(0, seg, diff, "amax", include_self=True)
+    above = torch.zeros(nseg, dtype=torch.int64, device=dev).scatter_reduce_(0, seg, -diff, "amax", include_self=True)
+    return below, above
 
 
 def train(keys: torch.Tensor, bits: int, verbose: bool = False):
@@ -79,11 +96,8 @@ def train(keys: torch.Tensor, bits: int, verbose: bool = False):
     leaf = ((keys >> (64 - bits)) & (nleaf - 1)).to(torch.int64)
     start, end, cnt = _segment_bounds(leaf, nleaf)
     next_rank = torch.clamp(end, max=n - 1).to(torch.float64)
-    alpha, beta = _fit_lines(kd, rank, start, end, cnt, next_rank)
-    pred = torch.floor(torch.clamp(beta[leaf] * kd + alpha[leaf], 0.0, float(n - 1)))
-    diff = (pred - rank).to(torch.int64)
-    below = torch.zeros(nleaf, dtype=torch.int64, device=dev).scatter_reduce_(0, leaf, diff, "amax", include_self=True)
-    above = torch.zeros(nleaf, dtype=torch.int64, device=dev).scatter_reduce_(0, leaf, -diff, "amax", include_self=True)
+    alpha, beta = _fit_lines(kd, n, start, end - 1, cnt > 0, next_rank)
+    below, above = _errors(kd, rank, leaf, nleaf, alpha, beta, n)
     err = ((below + SLACK) << 32) | (above + SLACK)
 
     # ---- partial third layer for dense leaves -------------------------------------------------
@@ -96,7 +110,7 @@ def train(keys: torch.Tensor, bits: int, verbose: bool = False):
         sub_start = torch.cumsum(nsub, 0) - nsub
         total_sub = int(nsub.sum())
         assert total_sub < (1 << 31)
-        # leaf line now predicts the sub-model index in [0, nsub)
+        # the leaf's line now predicts the sub-model index in [0, nsub) across the leaf's key span
         s, e = start[dense], end[dense] - 1
         k0, k1 = kd[s], kd[e]
         dk = k1 - k0
@@ -111,22 +125,21 @@ def train(keys: torch.Tensor, bits: int, verbose: bool = False):
         is_dense[dense] = True
         dense_slot = torch.zeros(nleaf, dtype=torch.int64, device=dev)
         dense_slot[dense] = torch.arange(dense.numel(), device=dev)
-        kidx = torch.nonzero(is_dense[leaf]).squeeze(1)
+        kidx = torch.nonzero(is_dense[leaf]).squeeze(1)          # global ranks of dense-leaf keys
         kl = dense_slot[leaf[kidx]]
         p = beta[leaf[kidx]] * kd[kidx] + alpha[leaf[kidx]]
         sub = torch.clamp(torch.floor(torch.clamp(p, min=0.0)).to(torch.int64), max=(nsub[kl] - 1))
         gsub = sub_start[kl] + sub  # non-decreasing because keys are sorted within a leaf
-        kd2, rk2 = kd[kidx], rank[kidx]
         st2, en2, cn2 = _segment_bounds(gsub, total_sub)
-        # next rank for empty sub-models: rank of the next key (global), clamped
-        nxt = torch.clamp(kidx[torch.clamp(en2, max=kidx.numel() - 1)], max=n - 1).to(torch.float64)
-        l1_alpha, l1_beta = _fit_lines(kd2, rk2, st2, en2, cn2, nxt)
-        pr = torch.floor(torch.clamp(l1_beta[gsub] * kd2 + l1_alpha[gsub], 0.0, float(n - 1)))
-        d2 = (pr - rk2).to(torch.int64)
-        bl = torch.zeros(total_sub, dtype=torch.int64, device=dev).scatter_reduce_(0, gsub, d2, "amax", include_self=True)
-        ab = torch.zeros(total_sub, dtype=torch.int64, device=dev).scatter_reduce_(0, gsub, -d2, "amax", include_self=True)
-        # an empty sub-model can be hit by unseen keys that sort anywhere inside it: cover the
-        # neighbouring sub-models' spans
+        K = kidx.numel()
+        sub_leaf = torch.repeat_interleave(torch.arange(dense.numel(), device=dev), nsub)
+        first = kidx[torch.clamp(st2, max=K - 1)]
+        last = kidx[torch.clamp(en2 - 1, min=0)]
+        nxt_in_leaf = (en2 < K) & (kl[torch.clamp(en2, max=K - 1)] == sub_leaf)
+        empty_rank = torch.where(nxt_in_leaf, kidx[torch.clamp(en2, max=K - 1)], end[dense][sub_leaf])
+        empty_rank = torch.clamp(empty_rank, max=n - 1).to(torch.float64)
+        l1_alpha, l1_beta = _fit_lines(kd, n, first, last, cn2 > 0, empty_rank)
+        bl, ab = _errors(kd[kidx], rank[kidx], gsub, total_sub, l1_alpha, l1_beta, n)
         l1_err = ((bl + SLACK) << 32) | (ab + SLACK)
     stats = {
         "n_leaf": nleaf,

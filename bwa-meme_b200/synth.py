@@ -64,7 +64,7 @@ def make_reads(genome: np.ndarray, n_reads: int, read_len: int = 150, seed: int 
     for i in range(n_reads):
         ln = int(lens[i])
         s = int(starts[i])
-        if has_indel[i]:
+        if has_indel[i] and ln > 30:
             k = int(rng.integers(1, 4))
             p = int(rng.integers(10, ln - 10))
             if rng.random() < 0.5:  # deletion from the read

@@ -1,0 +1,161 @@
+/* meme_b200.h -- C ABI of the B200-native `bwa-meme mem -7` hot path.
+ *
+ * Drop-in boundary.  The reference has no plugin mechanism; its hot path is cut at
+ * two source-level seams, and every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree, kaist-ina/BWA-MEME):
+ *
+ *   index load + runtime build   memoryAllocLearned()                      src/fastmap.cpp:L351-638
+ *                                 learned_index_load()                      src/LearnedIndex_seeding.cpp:L74-122
+ *   seeding (kernel A)            mem_kernel1_core_Learned() up to the sort src/bwamem.cpp:L1230-1397
+ *                                 = Learned_getSMEMsAllPosOneThread +       src/LearnedIndex_seeding.h:L235-260
+ *                                   Learned_bwtSeedStrategyAllPosOneThread{,_mem_tradeoff}
+ *   seed extension (kernel B)     BandedPairWiseSW::getScores8/16,          src/bandedSWA.h:L118-135, L257-297
+ *                                 scalarBandedSWAWrapper                    src/bandedSWA.cpp:L242-259
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success or a
+ * negative MEME_E_* code; nothing calls exit().  A handle is single-owner (one host thread at a
+ * time), like the reference's worker_t during step 1 of its pipeline (src/fastmap.cpp:L877-888).
+ * Result buffers returned by the library are pinned host memory owned by the handle and stay valid
+ * until the next call on the same handle.
+ */
+#ifndef MEME_B200_H
+#define MEME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEME_OK              0
+#define MEME_E_CUDA         -1   /* a CUDA runtime call failed (see meme_last_error) */
+#define MEME_E_IO           -2   /* index file missing / short / inconsistent */
+#define MEME_E_ARG          -3   /* bad argument (NULL, negative count, read longer than MEME_MAX_READ_LEN) */
+#define MEME_E_NOMEM        -4   /* host or device allocation failed */
+#define MEME_E_OVERFLOW     -5   /* a read produced more than MEME_MAX_SMEMS_PER_READ seeds */
+#define MEME_E_NOGPU        -6   /* no CUDA device: this library has no CPU path */
+
+/* The reference asserts len <= ERT_MAX_READ_LEN (301) on the -7 path, src/bwamem.cpp:L1276. */
+#define MEME_MAX_READ_LEN          320
+#define MEME_MAX_SMEMS_PER_READ    192
+
+typedef struct meme_index meme_index_t;
+typedef struct meme_bsw   meme_bsw_t;
+
+/* Same 24-byte layout as the reference's mem_tl (src/LearnedIndex_seeding.h:L121-127). */
+typedef struct {
+    int32_t  start;         /* SMEM start in the read                                   */
+    int32_t  end;           /* SMEM end (exclusive)                                     */
+    int32_t  hitbeg;        /* index of the first hit in this read's hit list           */
+    int32_t  hitcount;      /* size of the SA interval (before any max_occ sampling)    */
+    uint64_t cache_refpos;  /* reference position of the first hit (SA order)           */
+} meme_smem_t;
+
+/* mem_opt_t fields the path reads (src/bwamem.cpp:L126-162 defaults in brackets). */
+typedef struct {
+    int32_t min_seed_len;   /* [19]                                                       */
+    int32_t split_len;      /* (int)(min_seed_len*split_factor+.499) [28]                 */
+    int32_t split_width;    /* [10]                                                       */
+    int32_t max_mem_intv;   /* [20]; 0 disables the third round                           */
+    int32_t rounds;         /* 3 = production; 1/2 mirror the seeding harness `steps`     */
+    int32_t max_occ;        /* 0: materialise every hit; >0: only the hits mem_chain_Learned
+                               samples (k = 0, step, 2*step.. < hitcount, at most max_occ,
+                               step = hitcount > max_occ ? hitcount / max_occ : 1,
+                               src/bwamem.cpp:L1154-1155)                                 */
+} meme_seed_opt_t;
+
+typedef struct {
+    int64_t      n_reads;
+    int64_t      n_smems;
+    int64_t      n_hits;
+    const meme_smem_t *smems;     /* n_smems, grouped by read, sorted by (start,end) within a read */
+    const int64_t     *smem_off;  /* n_reads+1                                                     */
+    const int64_t     *hit_off;   /* n_reads+1; hits of read r = hits[hit_off[r] .. hit_off[r+1])   */
+    const uint64_t    *hits;      /* reference positions in [0, 2*l_pac), SA order within an SMEM   */
+} meme_seed_result_t;
+
+/* ---- index ------------------------------------------------------------------------------- */
+
+/* Reads <prefix>.0123, <prefix>.pos_packed, <prefix>.suffixarray_uint64_L{1,2}_PARAMETERS, uploads
+ * them to `device`, and builds the 64-bit inline keys and (mode 3) the inverse suffix array on the
+ * GPU.  mode: 1 = positions only, 2 = + inline keys, 3 = + inverse SA (Makefile:L40-46). */
+int meme_index_load(const char *prefix, int mode, int device, meme_index_t **out);
+
+/* Same, from host buffers (what the files would contain). l1/l2 are 24-byte records. */
+int meme_index_from_host(const uint8_t *text0123, uint64_t sa_num, const uint8_t *pos_packed,
+                         const void *l1_params, uint64_t n_l1, const void *l2_params, uint64_t n_l2,
+                         int mode, int device, meme_index_t **out);
+
+void     meme_index_free(meme_index_t *ix);
+uint64_t meme_index_sa_num(const meme_index_t *ix);
+uint64_t meme_index_device_bytes(const meme_index_t *ix);
+/* Use an existing CUDA stream (a cudaStream_t passed as void*); NULL restores the handle's own. */
+int      meme_index_set_stream(meme_index_t *ix, void *cuda_stream);
+
+/* Copies index arrays back (tests): any pointer may be NULL.  keys/pos/isa have sa_num entries. */
+int meme_index_download(const meme_index_t *ix, uint64_t *keys, uint64_t *pos, uint64_t *isa);
+
+/* ---- kernel A: seeding --------------------------------------------------------------------- */
+
+/* reads: base codes 0..3, 4 = N (nst_nt4_table output), concatenated; read r = codes[off[r]..off[r+1]).
+ * One call = upload + run + download. */
+int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                    const meme_seed_opt_t *opt, meme_seed_result_t *out);
+
+/* The same in three steps, so that a caller (and bench.py) can keep inputs resident in HBM. */
+int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads);
+int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);          /* asynchronous on the stream */
+int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out);        /* synchronises               */
+/* Totals of the last run without copying the lists (synchronises). */
+int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits);
+/* Device-side work counters of the last run: [0] searches, [1] SA block probes, [2] k-ary rounds,
+ * [3] extension rounds, [4] reads flagged overflow, [5] kernel launches since the handle was created. */
+int meme_seed_counters(meme_index_t *ix, uint64_t counters[8]);
+
+/* ---- kernel B: banded Smith-Waterman seed extension ------------------------------------------ */
+
+/* Byte-identical to the reference's SeqPair (src/bandedSWA.h:L90-99). */
+typedef struct {
+    int32_t idr, idq, id;
+    int32_t len1, len2;     /* len1: reference length, len2: query length */
+    int32_t h0;
+    int32_t seqid, regid;
+    int32_t score, tle, gtle, qle;
+    int32_t gscore, max_off;
+} meme_seqpair_t;
+
+/* Constructor arguments of BandedPairWiseSW (src/bandedSWA.h:L118-123). */
+typedef struct {
+    int32_t o_del, e_del, o_ins, e_ins, zdrop, end_bonus;
+    int32_t a, b;           /* match score, mismatch penalty (positive); N scores -1 (bwa_fill_scmat) */
+} meme_bsw_opt_t;
+
+int  meme_bsw_create(int device, meme_bsw_t **out);
+void meme_bsw_free(meme_bsw_t *b);
+int  meme_bsw_set_stream(meme_bsw_t *b, void *cuda_stream);
+
+/* Fills score, tle, gtle, qle, gscore, max_off of every pair, exactly as
+ * scalarBandedSWA(len2, qer+idq, len1, ref+idr, w, h0, ...) does.  Sequences are codes 0..4.
+ * No pre-sorting or SIMD-width padding is required (cf. src/bwamem.cpp:L2529-2568). */
+int meme_bsw_batch(meme_bsw_t *b, meme_seqpair_t *pairs, int64_t n_pairs,
+                   const uint8_t *ref, int64_t n_ref, const uint8_t *qer, int64_t n_qer,
+                   int32_t w, const meme_bsw_opt_t *opt);
+
+/* Three-step variant (inputs stay in HBM between run calls). */
+int meme_bsw_upload(meme_bsw_t *b, const meme_seqpair_t *pairs, int64_t n_pairs,
+                    const uint8_t *ref, int64_t n_ref, const uint8_t *qer, int64_t n_qer);
+int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt);
+int meme_bsw_download(meme_bsw_t *b, meme_seqpair_t *pairs);
+/* DP cells evaluated by the last run (band-limited), for GCUPS accounting. */
+int meme_bsw_cells(meme_bsw_t *b, uint64_t *cells);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+const char *meme_last_error(void);     /* thread-local text of the last failure */
+int         meme_device_count(void);
+const char *meme_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEME_B200_H */

@@ -1,0 +1,255 @@
+"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg -- never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+
+
+def build(force: bool = False) -> None:
+    os.makedirs(BUILD, exist_ok=True)
+    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so")):
+        s, o = os.path.join(HERE, src), os.path.join(BUILD, lib)
+        if not os.path.exists(s):
+            continue
+        if force or not os.path.exists(o) or os.path.getmtime(o) < os.path.getmtime(s):
+            subprocess.run(["gcc", "-O2", "-g", "-Wall", "-shared", "-fPIC", "-o", o, s, "-lm"], check=True)
+
+
+class SeedOpt(C.Structure):
+    _fields_ = [("min_seed_len", C.c_int), ("split_len", C.c_int), ("split_width", C.c_int),
+                ("max_mem_intv", C.c_int), ("rounds", C.c_int)]
+
+
+class SeedResult(C.Structure):
+    _fields_ = [("n_smems", C.c_int64), ("n_hits", C.c_int64), ("smems", C.c_void_p),
+                ("smem_off", C.POINTER(C.c_int64)), ("hit_off", C.POINTER(C.c_int64)),
+                ("hits", C.POINTER(C.c_uint64)), ("counters", C.c_uint64 * 8)]
+
+
+SMEM_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("hitbeg", "<i4"), ("hitcount", "<i4"), ("sa_lo", "<u8")])
+COUNTER_NAMES = ("Lk", "Lp", "P", "W", "I", "H", "S", "searches")
+
+
+def default_opt(rounds: int = 3, min_seed_len: int = 19, split_factor: float = 1.5, split_width: int = 10,
+                max_mem_intv: int = 20) -> SeedOpt:
+    return SeedOpt(min_seed_len, int(min_seed_len * split_factor + .499), split_width, max_mem_intv, rounds)
+
+
+_seed_lib = None
+
+
+def seed_lib():
+    global _seed_lib
+    if _seed_lib is None:
+        build()
+        L = C.CDLL(os.path.join(BUILD, "liboracle_seed.so"))
+        L.oracle_index_load.restype = C.c_void_p
+        L.oracle_index_load.argtypes = [C.c_char_p, C.c_int]
+        L.oracle_index_free.argtypes = [C.c_void_p]
+        L.oracle_index_sa_num.restype = C.c_uint64
+        L.oracle_index_sa_num.argtypes = [C.c_void_p]
+        L.oracle_seed_reads.restype = C.POINTER(SeedResult)
+        L.oracle_seed_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SeedOpt)]
+        L.oracle_seed_result_free.argtypes = [C.POINTER(SeedResult)]
+        _seed_lib = L
+    return _seed_lib
+
+
+class OracleIndex:
+    def __init__(self, prefix: str, mode: int = 3):
+        self.lib = seed_lib()
+        self.h = self.lib.oracle_index_load(prefix.encode(), mode)
+        if not self.h:
+            raise FileNotFoundError(f"oracle could not load index {prefix}")
+        self.sa_num = int(self.lib.oracle_index_sa_num(self.h))
+        self.mode = mode
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_index_free(self.h)
+            self.h = None
+
+    def seed(self, codes: np.ndarray, offsets: np.ndarray, opt: SeedOpt | None = None) -> dict:
+        """Returns dict(smems=record array, smem_off, hit_off, hits, counters)."""
+        opt = opt or default_opt()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.shape[0] - 1
+        rp = self.lib.oracle_seed_reads(self.h, codes.ctypes.data, offsets.ctypes.data, n, C.byref(opt))
+        r = rp.contents
+        ns, nh = int(r.n_smems), int(r.n_hits)
+        smems = np.frombuffer(C.string_at(r.smems, ns * SMEM_DTYPE.itemsize), dtype=SMEM_DTYPE).copy() if ns else np.zeros(0, SMEM_DTYPE)
+        out = {
+            "smems": smems,
+            "smem_off": np.ctypeslib.as_array(r.smem_off, shape=(n + 1,)).copy(),
+            "hit_off": np.ctypeslib.as_array(r.hit_off, shape=(n + 1,)).copy(),
+            "hits": np.ctypeslib.as_array(r.hits, shape=(nh,)).copy() if nh else np.zeros(0, np.uint64),
+            "counters": {k: int(r.counters[i]) for i, k in enumerate(COUNTER_NAMES)},
+        }
+        self.lib.oracle_seed_result_free(rp)
+        return out
+
+
+def bytes_seed(counters: dict, total_read_bases: int, mode: int = 3) -> int:
+    """Algorithmic bytes of the seeding path, SURVEY.md §8d:
+    R + 24(Lk+Lp) + SASIZE*P + 8W + 5I + 8H + 24S."""
+    sasize = 5 if mode == 1 else 13
+    c = counters
+    return (total_read_bases + 24 * (c["Lk"] + c["Lp"]) + sasize * c["P"] + 8 * c["W"] + 5 * c["I"]
+            + 8 * c["H"] + 24 * c["S"])
+
+
+# ---- canonical text form shared by the oracle, the CUDA path and the reference harness dump ----
+def canon_lines(smems: np.ndarray, smem_off: np.ndarray, hit_off: np.ndarray, hits: np.ndarray, n_reads: int):
+    """Per read, a sorted list of (start, end, tuple(hits)) -- order-insensitive to ties."""
+    out = []
+    for i in range(n_reads):
+        a, b = int(smem_off[i]), int(smem_off[i + 1])
+        hb = int(hit_off[i])
+        rec = []
+        for k in range(a, b):
+            s = smems[k]
+            h0 = hb + int(s["hitbeg"])
+            rec.append((int(s["start"]), int(s["end"]), tuple(int(x) for x in hits[h0:h0 + int(s["hitcount"])])))
+        rec.sort()
+        out.append(rec)
+    return out
+
+
+def parse_ref_dump(path: str, n_reads: int):
+    """Parse the steps>=4 dump of test/Learned_seeding_big_read.cpp:L288-300:
+    `rid:` line, then `[start,end] [pos,pos,...,]` per SMEM."""
+    out = [[] for _ in range(n_reads)]
+    cur = None
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            if line.endswith(":") and line[:-1].isdigit():
+                cur = int(line[:-1])
+                continue
+            if line.startswith("[") and cur is not None:
+                a, b = line.split("] [")
+                s, e = a[1:].split(",")
+                hs = tuple(int(x) for x in b.rstrip("]").split(",") if x)
+                out[cur].append((int(s), int(e), hs))
+    for rec in out:
+        rec.sort()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# banded Smith-Waterman oracle
+# ------------------------------------------------------------------------------------------------
+SEQPAIR_DTYPE = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1", "<i4"), ("len2", "<i4"),
+                          ("h0", "<i4"), ("seqid", "<i4"), ("regid", "<i4"), ("score", "<i4"), ("tle", "<i4"),
+                          ("gtle", "<i4"), ("qle", "<i4"), ("gscore", "<i4"), ("max_off", "<i4")])
+assert SEQPAIR_DTYPE.itemsize == 56
+RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
+
+
+class BswOpt(C.Structure):
+    _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
+                ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+def default_bsw_opt() -> BswOpt:
+    """mem_opt_init defaults, src/bwamem.cpp:L126-162."""
+    return BswOpt(6, 1, 6, 1, 100, 5, 1, 4)
+
+
+_bsw_lib = None
+
+
+def bsw_lib():
+    global _bsw_lib
+    if _bsw_lib is None:
+        build()
+        L = C.CDLL(os.path.join(BUILD, "liboracle_bsw.so"))
+        L.oracle_bsw_batch.argtypes = [C.POINTER(BswOpt), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _bsw_lib = L
+    return _bsw_lib
+
+
+def bsw_batch(pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int, opt: BswOpt | None = None) -> np.ndarray:
+    """Run the oracle over `pairs` (SEQPAIR_DTYPE); returns a copy with the six result fields filled."""
+    opt = opt or default_bsw_opt()
+    out = np.ascontiguousarray(pairs.copy())
+    ref = np.ascontiguousarray(ref, dtype=np.uint8)
+    qer = np.ascontiguousarray(qer, dtype=np.uint8)
+    bsw_lib().oracle_bsw_batch(C.byref(opt), out.ctypes.data, ref.ctypes.data, qer.ctypes.data, len(out), w)
+    return out
+
+
+def bsw_cells() -> int:
+    return int(C.c_uint64.in_dll(bsw_lib(), "oracle_bsw_cells").value)
+
+
+def make_pairs(n: int, seed: int = 1, max_q: int = 150, max_extra_ref: int = 110, sub: float = 0.03,
+               indel: float = 0.2, with_n: float = 0.02, h0_max: int = 120, lens=None):
+    """Seeded extension-like pairs: query = mutated prefix of the reference window (as the left/right
+    extension pairs of mem_chain2aln_across_reads_V2 are), h0 = a seed score."""
+    rng = np.random.default_rng(seed)
+    pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+    refs, qers = [], []
+    ro = qo = 0
+    for i in range(n):
+        ql = int(rng.integers(1, max_q + 1)) if lens is None else int(lens[i][0])
+        tl = ql + int(rng.integers(0, max_extra_ref + 1)) if lens is None else int(lens[i][1])
+        t = rng.integers(0, 4, size=tl, dtype=np.uint8)
+        kind = rng.random()
+        if kind < 0.1:
+            q = rng.integers(0, 4, size=ql, dtype=np.uint8)          # unrelated
+        else:
+            q = t[:ql].copy() if tl >= ql else np.concatenate([t, rng.integers(0, 4, size=ql - tl, dtype=np.uint8)])
+            m = rng.random(ql) < sub
+            q[m] = (q[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+            if rng.random() < indel and ql > 12:
+                p = int(rng.integers(3, ql - 6)); k = int(rng.integers(1, 6))
+                if rng.random() < 0.5:
+                    q = np.concatenate([q[:p], q[p + k:], rng.integers(0, 4, size=k, dtype=np.uint8)])[:ql]
+                else:
+                    q = np.concatenate([q[:p], rng.integers(0, 4, size=k, dtype=np.uint8), q[p:]])[:ql]
+            if kind > 0.9:   # diverge after a while (exercises z-drop)
+                p = int(rng.integers(0, ql))
+                q[p:] = rng.integers(0, 4, size=ql - p, dtype=np.uint8)
+        if rng.random() < with_n:
+            q[int(rng.integers(0, ql))] = 4
+        if rng.random() < with_n:
+            t[int(rng.integers(0, tl))] = 4
+        pairs[i]["idr"], pairs[i]["idq"], pairs[i]["id"] = ro, qo, i
+        pairs[i]["len1"], pairs[i]["len2"] = tl, ql
+        pairs[i]["h0"] = int(rng.integers(1, h0_max + 1))
+        pairs[i]["seqid"], pairs[i]["regid"] = i, 0
+        refs.append(t); qers.append(q)
+        ro += tl; qo += ql
+    return pairs, np.concatenate(refs), np.concatenate(qers)
+
+
+def run_ref_bsw_shim(binary: str, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int, mode: str,
+                     opt: BswOpt | None = None, tmpdir: str = "/tmp") -> np.ndarray:
+    """Run oracle/_ref/bsw_shim_* (the unmodified reference class) and return pairs with results."""
+    opt = opt or default_bsw_opt()
+    fin = os.path.join(tmpdir, f"bsw_in_{os.getpid()}.bin")
+    fout = os.path.join(tmpdir, f"bsw_out_{os.getpid()}.bin")
+    hdr = np.array([len(pairs), w, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, opt.zdrop, opt.end_bonus,
+                    opt.a, opt.b, len(ref), len(qer)], dtype=np.int32)
+    with open(fin, "wb") as f:
+        f.write(hdr.tobytes()); f.write(pairs.tobytes()); f.write(ref.tobytes()); f.write(qer.tobytes())
+    subprocess.run([binary, fin, fout, mode], check=True, capture_output=True)
+    res = np.fromfile(fout, dtype=np.int32).reshape(-1, 6)
+    out = pairs.copy()
+    for k, name in enumerate(RESULT_FIELDS):
+        out[name] = res[:, k]
+    os.remove(fin); os.remove(fout)
+    return out

@@ -1,0 +1,86 @@
+"""Generate tests/golden/* from the UNMODIFIED reference compiled under oracle/_ref/.
+
+Run here (where /root/reference is mounted):  python tests/golden/make_golden.py
+The fixtures are small and committed; the GPU box only reads them.
+
+  index_sha.json        sha256 of the files `bwa-meme index -a meme` writes for the golden genome
+                        (pins bwa-meme_b200/index_build.py against the reference's own builder)
+  smem_len*.txt         SMEM dumps of test/Learned_seeding_big_read.cpp (steps=4, 1 thread, MODE=3)
+  smem_len*_s{1,2}.json per-read SMEM counts with steps=1 / steps=2 (rounds 1 and 1+2 only)
+  bsw_*.npy             {score,tle,gtle,qle,gscore,max_off} of BandedPairWiseSW::scalarBandedSWAWrapper
+  mem7.sam              `bwa-meme mem -7` SAM (minus @PG) for the len150 reads  (end-to-end reference)
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+ge.load_pkg()
+O = ge.load_oracle()
+from bwa_meme_b200 import synth, index_build  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+ISA = "avx512bw" if "avx512bw" in open("/proc/cpuinfo").read() else "avx2"
+GENOME_LEN, GENOME_SEED = 50000, 101
+READ_SETS = [(150, 300, 0.05, 21), (101, 120, 0.3, 22), (250, 100, 0.05, 23), (33, 80, 0.1, 24)]
+BSW_SETS = [(0, 400, 150, 110, 120), (1, 300, 60, 200, 40), (2, 200, 300, 120, 250)]
+
+
+def sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def main():
+    work = "/tmp/meme_golden"
+    os.makedirs(work, exist_ok=True)
+    g = synth.make_genome(GENOME_LEN, seed=GENOME_SEED, n_families=3, copies=12, rep_len=400)
+    fa = os.path.join(work, "ref.fa")
+    synth.write_fasta(fa, g)
+    subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "index", "-a", "meme", "-t", "4", fa], check=True,
+                   capture_output=True)
+    shas = {ext: sha(fa + ext) for ext in (".pac", ".ann", ".amb", ".0123", ".pos_packed", ".suffixarray_uint64")}
+    json.dump({"genome_len": GENOME_LEN, "genome_seed": GENOME_SEED, "sha256": shas},
+              open(os.path.join(HERE, "index_sha.json"), "w"), indent=1)
+    # parameters from our trainer, written next to the reference-built files
+    mine = os.path.join(work, "mine.fa")
+    index_build.build_index(mine, g, bits=16)
+    for ext in ("_L0_PARAMETERS", "_L1_PARAMETERS", "_L2_PARAMETERS"):
+        src = mine + ".suffixarray_uint64" + ext
+        open(fa + ".suffixarray_uint64" + ext, "wb").write(open(src, "rb").read())
+    for rl, n, nf, seed in READ_SETS:
+        codes, offs = synth.make_reads(g, n, rl, seed=seed, n_frac=nf)
+        fq = os.path.join(work, f"r{rl}.fq")
+        synth.write_fastq(fq, codes, offs)
+        out = os.path.join(HERE, f"smem_len{rl}.txt")
+        with open(out, "w") as fo:
+            subprocess.run([os.path.join(REF, f"learned_seeding_mode3.{ISA}"), fa, fq, "512", "1", "4"], stdout=fo,
+                           stderr=subprocess.DEVNULL, check=True)
+        for steps in (1, 2):
+            p = subprocess.run([os.path.join(REF, f"learned_seeding_mode3.{ISA}"), fa, fq, "512", "1", str(steps)],
+                               capture_output=True, text=True, check=True)
+            tot = [l for l in p.stderr.splitlines() if l.startswith("totalSmems")]
+            json.dump({"totalSmems": int(tot[0].split("=")[1])}, open(os.path.join(HERE, f"smem_len{rl}_s{steps}.json"), "w"))
+        if rl == 150:
+            sam = subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "mem", "-7", "-t", "1", fa, fq],
+                                 capture_output=True, text=True, check=True).stdout
+            open(os.path.join(HERE, "mem7.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
+    shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
+    for seed, n, mq, mx, h0m in BSW_SETS:
+        pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)
+        for w in (100, 200, 7):
+            r = O.run_ref_bsw_shim(shim, pairs, ref, qer, w, "scalar")
+            res = np.stack([r[f] for f in O.RESULT_FIELDS], axis=1).astype(np.int32)
+            np.save(os.path.join(HERE, f"bsw_scalar_s{seed}_w{w}.npy"), res)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

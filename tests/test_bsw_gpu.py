@@ -1,0 +1,84 @@
+"""Parity of the CUDA banded-SW kernel (through the C ABI) with the oracle and the reference's golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_BSW_SETS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bsw(pkg):
+    from bwa_meme_b200 import capi
+    b = capi.MemeBsw()
+    yield b
+    b.close()
+
+
+@pytest.mark.parametrize("cfg", GOLDEN_BSW_SETS)
+@pytest.mark.parametrize("w", [100, 200, 7])
+def test_cuda_matches_reference_vectors(oracle, bsw, cfg, w):
+    seed, n, mq, mx, h0m = cfg
+    pairs, ref, qer = oracle.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)
+    want = np.load(os.path.join(GOLDEN, f"bsw_scalar_s{seed}_w{w}.npy"))
+    got = bsw.get_scores(pairs, ref, qer, w)
+    res = np.stack([got[f] for f in oracle.RESULT_FIELDS], axis=1)
+    bad = np.nonzero((res != want).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} pairs differ; first {bad[:3]}: {res[bad[0]]} vs {want[bad[0]]} len {pairs[bad[0]]}"
+
+
+@pytest.mark.parametrize("mq,mx,h0m,n", [(150, 110, 120, 20000), (31, 40, 30, 5000), (64, 10, 200, 5000),
+                                         (320, 200, 300, 3000), (1, 5, 5, 500)])
+def test_cuda_matches_oracle_random(oracle, bsw, mq, mx, h0m, n):
+    pairs, ref, qer = oracle.make_pairs(n, seed=mq + n, max_q=mq, max_extra_ref=mx, h0_max=h0m)
+    for w in (100, 13):
+        want = oracle.bsw_batch(pairs, ref, qer, w)
+        got = bsw.get_scores(pairs, ref, qer, w)
+        for f in oracle.RESULT_FIELDS:
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert len(bad) == 0, f"{f}: {len(bad)} differ, first {bad[:3]} got {got[f][bad[:3]]} want {want[f][bad[:3]]} {pairs[bad[0]]}"
+
+
+def test_long_queries_take_generic_path(oracle, bsw):
+    pairs, ref, qer = oracle.make_pairs(40, seed=4, max_q=900, max_extra_ref=300, h0_max=400)
+    assert (pairs["len2"] > 383).any()
+    want = oracle.bsw_batch(pairs, ref, qer, 100)
+    got = bsw.get_scores(pairs, ref, qer, 100)
+    for f in oracle.RESULT_FIELDS:
+        assert (got[f] == want[f]).all(), f
+
+
+def test_non_default_penalties(oracle, pkg):
+    from bwa_meme_b200 import capi
+    opt = capi.BswOpt(5, 2, 7, 3, 50, 3, 2, 5)
+    oopt = oracle.BswOpt(5, 2, 7, 3, 50, 3, 2, 5)
+    b = capi.MemeBsw(opt)
+    pairs, ref, qer = oracle.make_pairs(4000, seed=12)
+    want = oracle.bsw_batch(pairs, ref, qer, 60, oopt)
+    got = b.get_scores(pairs, ref, qer, 60)
+    b.close()
+    for f in oracle.RESULT_FIELDS:
+        assert (got[f] == want[f]).all(), f
+
+
+def test_empty_and_bad_input(pkg, bsw, oracle):
+    from bwa_meme_b200 import capi
+    out = bsw.get_scores(np.zeros(0, capi.SEQPAIR_DTYPE), np.zeros(0, np.uint8), np.zeros(0, np.uint8), 100)
+    assert len(out) == 0
+    pairs, ref, qer = oracle.make_pairs(4, seed=1)
+    pairs["idr"][2] = len(ref)          # points past the buffer
+    with pytest.raises(capi.MemeError):
+        bsw.get_scores(pairs, ref, qer, 100)
+
+
+def test_cells_counter_and_determinism(oracle, bsw):
+    pairs, ref, qer = oracle.make_pairs(3000, seed=21)
+    before = oracle.bsw_cells()
+    want = oracle.bsw_batch(pairs, ref, qer, 100)
+    cpu_cells = oracle.bsw_cells() - before
+    a = bsw.get_scores(pairs, ref, qer, 100)
+    assert bsw.cells() == cpu_cells
+    b = bsw.get_scores(pairs, ref, qer, 100)
+    assert (a == b).all() and (a["score"] == want["score"]).all()

@@ -1,0 +1,170 @@
+"""Parity of the CUDA seeding kernel (through the C ABI) with the oracle and the reference's golden dumps."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_READ_SETS
+
+pytestmark = pytest.mark.gpu
+
+
+def _canon(O, r, n):
+    return O.canon_lines(r["smems"], r["smem_off"], r["hit_off"], r["hits"], n)
+
+
+@pytest.fixture(scope="module")
+def gidx(pkg, golden_index):
+    from bwa_meme_b200 import capi
+    out = {m: capi.MemeIndex(golden_index, mode=m) for m in (1, 2, 3)}
+    yield out
+    for v in out.values():
+        v.close()
+
+
+@pytest.mark.parametrize("rl", [s[0] for s in GOLDEN_READ_SETS])
+@pytest.mark.parametrize("mode", [3, 2, 1])
+def test_cuda_matches_reference_dump(oracle, gidx, golden_reads, rl, mode):
+    codes, offs = golden_reads[rl]
+    n = len(offs) - 1
+    want = oracle.parse_ref_dump(os.path.join(GOLDEN, f"smem_len{rl}.txt"), n)
+    got = _canon(oracle, gidx[mode].seed(codes, offs), n)
+    bad = [i for i in range(n) if got[i] != want[i]]
+    assert not bad, f"{len(bad)} reads differ, first {bad[:5]}: {got[bad[0]][:4]} vs {want[bad[0]][:4]}"
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_cuda_matches_oracle_rounds(oracle, pkg, gidx, golden_index, golden_reads, rounds):
+    from bwa_meme_b200 import capi
+    codes, offs = golden_reads[150]
+    n = len(offs) - 1
+    oix = oracle.OracleIndex(golden_index, 3)
+    want = oix.seed(codes, offs, oracle.default_opt(rounds=rounds))
+    oix.close()
+    got = gidx[3].seed(codes, offs, capi.default_seed_opt(rounds=rounds))
+    assert _canon(oracle, got, n) == _canon(oracle, want, n)
+    # identical ordering too (sorted by start,end; ties carry identical hit lists)
+    assert (got["smems"]["start"] == want["smems"]["start"]).all() and (got["smems"]["end"] == want["smems"]["end"]).all()
+    assert (got["smems"]["hitcount"] == want["smems"]["hitcount"]).all()
+    assert (got["smem_off"] == want["smem_off"]).all() and (got["hit_off"] == want["hit_off"]).all()
+    assert (got["hits"] == want["hits"]).all()
+
+
+def test_wide_windows_repeats_and_all_lengths(oracle, pkg, mid_index):
+    """400 kb genome, 2^12 leaves (RMI windows of hundreds of entries -> 32-ary narrowing), 60-copy repeat
+    families (intervals larger than one 32-entry block -> galloping), ragged read lengths 20..320."""
+    from bwa_meme_b200 import capi, synth
+    prefix, g = mid_index
+    codes, offs = synth.make_reads(g, 3000, 320, seed=5, n_frac=0.05, len_jitter=300)
+    n = len(offs) - 1
+    for mode in (3, 1):
+        ix = capi.MemeIndex(prefix, mode=mode)
+        got = ix.seed(codes, offs)
+        cnt = ix.seed_counters()
+        ix.close()
+        oix = oracle.OracleIndex(prefix, mode)
+        want = oix.seed(codes, offs)
+        oix.close()
+        a, b = _canon(oracle, got, n), _canon(oracle, want, n)
+        bad = [i for i in range(n) if a[i] != b[i]]
+        assert not bad, f"mode {mode}: {len(bad)} reads differ, first {bad[:5]}"
+        assert cnt["kary_rounds"] > 0 and cnt["ext_rounds"] > 0, cnt
+
+
+def test_edge_reads(oracle, pkg, gidx, golden_index, golden_genome):
+    g = golden_genome
+    reads = [np.zeros(0, np.uint8), np.full(50, 4, np.uint8), g[100:110].copy(), g[500:650].copy(),
+             np.concatenate([g[700:760], [4], g[761:850]]).astype(np.uint8), np.full(150, 0, np.uint8),
+             np.tile(np.array([0, 1], np.uint8), 75), g[-150:].copy(), (3 - g[:150][::-1]).astype(np.uint8),
+             np.full(1, 2, np.uint8), np.concatenate([[4], g[900:1000], [4]]).astype(np.uint8)]
+    offs = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=offs[1:])
+    codes = np.concatenate(reads).astype(np.uint8)
+    n = len(reads)
+    oix = oracle.OracleIndex(golden_index, 3)
+    want = oix.seed(codes, offs)
+    oix.close()
+    got = gidx[3].seed(codes, offs)
+    assert _canon(oracle, got, n) == _canon(oracle, want, n)
+
+
+def test_empty_batch(pkg, gidx):
+    r = gidx[3].seed(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert len(r["smems"]) == 0 and r["smem_off"].tolist() == [0]
+
+
+def test_too_long_read_is_rejected(pkg, gidx):
+    from bwa_meme_b200 import capi
+    with pytest.raises(capi.MemeError):
+        gidx[3].seed(np.zeros(400, np.uint8), np.array([0, 400], np.int64))
+
+
+def test_max_occ_sampling(oracle, pkg, mid_index):
+    """max_occ > 0 returns exactly the hits mem_chain_Learned would read (bwamem.cpp:L1154-1155)."""
+    from bwa_meme_b200 import capi, synth
+    prefix, g = mid_index
+    codes, offs = synth.make_reads(g, 500, 150, seed=9)
+    ix = capi.MemeIndex(prefix, mode=3)
+    full = ix.seed(codes, offs)
+    occ = 7
+    samp = ix.seed(codes, offs, capi.default_seed_opt(max_occ=occ))
+    ix.close()
+    assert (full["smems"]["hitcount"] == samp["smems"]["hitcount"]).all()
+    n = len(offs) - 1
+    saw_big = False
+    for r in range(n):
+        for k in range(full["smem_off"][r], full["smem_off"][r + 1]):
+            c = int(full["smems"]["hitcount"][k])
+            step = c // occ if c > occ else 1
+            idx = list(range(0, c, step))[:occ]
+            saw_big |= c > occ
+            fh = full["hits"][full["hit_off"][r] + full["smems"]["hitbeg"][k]:][:c]
+            sh = samp["hits"][samp["hit_off"][r] + samp["smems"]["hitbeg"][k]:][:len(idx)]
+            assert sh.tolist() == fh[idx].tolist()
+    assert saw_big
+
+
+def test_invariants_at_scale(oracle, pkg, mid_index):
+    """size-independent properties on a batch the oracle is not run on in full: every hit really matches
+    the read substring on the text; SMEMs sorted; repeated run is bit-identical; shard-and-concatenate equals
+    the whole batch (what the multi-GPU path relies on)."""
+    from bwa_meme_b200 import capi, synth, index_build
+    prefix, g = mid_index
+    text = index_build.fwd_rc_text(g)
+    codes, offs = synth.make_reads_fast(g, 60000, 150, seed=31)
+    n = len(offs) - 1
+    ix = capi.MemeIndex(prefix, mode=3)
+    a = ix.seed(codes, offs)
+    b = ix.seed(codes, offs)
+    for k in ("smems", "smem_off", "hit_off", "hits"):
+        assert (a[k] == b[k]).all()
+    half = n // 2
+    p1 = ix.seed(codes[:offs[half]], offs[:half + 1])
+    p2 = ix.seed(codes[offs[half]:], offs[half:] - offs[half])
+    ix.close()
+    assert (np.concatenate([p1["smems"], p2["smems"]]) == a["smems"]).all()
+    assert (np.concatenate([p1["hits"], p2["hits"]]) == a["hits"]).all()
+    sm = a["smems"]
+    rng = np.random.default_rng(0)
+    for r in rng.integers(0, n, 400):
+        s = sm[a["smem_off"][r]:a["smem_off"][r + 1]]
+        key = s["start"].astype(np.int64) * 1000 + s["end"]
+        assert (np.diff(key) >= 0).all()
+        read = codes[offs[r]:offs[r + 1]]
+        for m in s:
+            hits = a["hits"][a["hit_off"][r] + m["hitbeg"]:][:m["hitcount"]]
+            sub = read[m["start"]:m["end"]]
+            for h in hits[:3]:
+                assert (text[int(h):int(h) + len(sub)] == sub).all()
+    # checksum of checksums against the oracle on a sample
+    sel = rng.choice(n, 1500, replace=False)
+    sel.sort()
+    c2 = np.concatenate([codes[offs[i]:offs[i + 1]] for i in sel])
+    o2 = np.arange(len(sel) + 1, dtype=np.int64) * 150
+    oix = oracle.OracleIndex(prefix, 3)
+    want = oix.seed(c2, o2)
+    oix.close()
+    got_cnt = np.array([a["smem_off"][i + 1] - a["smem_off"][i] for i in sel])
+    assert (got_cnt == np.diff(want["smem_off"])).all()
+    got_hits = np.array([a["hit_off"][i + 1] - a["hit_off"][i] for i in sel])
+    assert (got_hits == np.diff(want["hit_off"])).all()
