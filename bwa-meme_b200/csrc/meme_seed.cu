@@ -172,6 +172,7 @@ struct Searcher {
     int lane;
     int L;                  // read length
     int n_sm;               // SMEMs collected so far
+    int budget;
     bool overflow;
     // statistics
     u32 st_search, st_block, st_kary, st_ext;
@@ -252,7 +253,8 @@ struct Searcher {
         const u64 n = ix.sa_num;
         u64 cur = from, s = 1;
         bool up = true;
-        for (;;) {
+        for (int guard = 0;; guard++) {
+            if (guard > 200) { overflow = true; edge = cur; nb = 0; return; }   // cannot happen on a sorted SA
             u64 off = (u64)(lane + 1) * s;
             bool valid;
             u64 idx;
@@ -390,10 +392,11 @@ struct Searcher {
         begin(right ? 0 : 1, right ? pivot : L - 1 - pivot, V);
         locate_by(V, start_mode, hint);
         u64 need = (u64)min_intv;
+        if (++budget > 20000) overflow = true;                        // runaway guard (never hit on valid input)
         level_init(need, emit ? min_seed_len : 0x7fffffff);
         // an interval is exact as long as every extension ran to its end; extensions are only cut
         // short (limit) when the level is too short to be emitted
-        while (hi - lo + 1 < need) {
+        while (hi - lo + 1 < need && !overflow) {
             bool exact_needed = emit && max(nbl, nbr) >= min_seed_len;
             level_next(exact_needed ? ~0ull : need);
         }
@@ -471,21 +474,21 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
             }
         }
         __syncwarp();
-        S.L = L; S.n_sm = 0; S.overflow = false;
+        S.L = L; S.n_sm = 0; S.overflow = false; S.budget = 0;
         ReadState R;
         R.full_match = false; R.use_cached = false; R.max_refpos = 0;
         R.min_intv = 1; R.min_seed_len = opt.min_seed_len;
         const u32 *nf = ws->nfw;
         // ---- rounds 1+2: Learned_getSMEMsAllPosOneThread (reference L913-972) ----
         int pivot = 0;
-        while (pivot < L) {
+        while (pivot < L && !S.overflow) {
             int before = S.n_sm;
             // --- Learned_getSMEMsOnePosOneThread_step1 (L1691-1894) ---
             if (is_n(nf, pivot)) {
                 pivot = (L - pivot < R.min_seed_len) ? L : pivot + 1;
             } else if (pivot != 0 && !is_n(nf, pivot - 1)) {
                 int sp = pivot;
-                while (sp < L) {
+                while (sp < L && !S.overflow) {
                     if (is_n(nf, sp)) {
                         if (L - sp < R.min_seed_len) { pivot = L; sp = L; }
                         else { sp += 1; pivot += 1; }
@@ -522,7 +525,7 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
                 // pivot sits inside an SMEM: not N, predecessor not N
                 int len = do_search(S, R, p2, true, false);
                 int next = p2 + len, sp = p2;
-                while (sp < next) {
+                while (sp < next && !S.overflow) {
                     int l = do_search(S, R, p2, false, false);
                     p2 = p2 - l + 1;
                     if (next - p2 < R.min_seed_len) break;
@@ -538,10 +541,11 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
         if (opt.rounds >= 3 && opt.max_mem_intv > 0) {
             const int msl = opt.min_seed_len + 1, mi = opt.max_mem_intv;
             pivot = 0;
-            while (pivot < L - msl + 1) {
+            while (pivot < L - msl + 1 && !S.overflow) {
                 if (is_n(nf, pivot)) { pivot++; continue; }
                 int V;
                 S.begin(0, pivot, V);
+                if (++S.budget > 20000) S.overflow = true;
                 if (V < msl) { S.st_search--; pivot += V; continue; }
                 if (R.full_match) S.locate_by(V, START_ISA_EXACT, isa_at(ix, R.max_refpos + pivot));
                 else S.locate_by(V, START_RMI, 0);
@@ -549,7 +553,8 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
                 if (S.lev < msl) { pivot += msl; continue; }
                 u64 last_lo = S.lo, last_cnt = 0, cnt;
                 int emit_len;
-                for (;;) {
+                for (int guard = 0;; guard++) {
+                    if (guard > 400) { S.overflow = true; cnt = 0; emit_len = msl; break; }
                     cnt = S.hi - S.lo + 1;
                     if (cnt >= (u64)mi) { cnt = last_cnt; emit_len = S.lev + 1; break; }   // L1243-1251
                     if (max(S.nbl, S.nbr) < msl) { last_lo = S.lo; emit_len = msl; break; } // L1252-1258
