@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py -- seeding throughput of the B200 hot path (BASELINE.json metric) with roofline + CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm  (one process per GPU under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]      the reference's own CPU seeding path
+
+Workload (N=1): BASELINE.json configs[1] -- chr1-scale reference (248,956,422 bp synthetic stand-in, no genomes
+exist offline), 10 M synthetic 150 bp SE reads, mode-3 P-RMI index, seeding only (the semantics of
+test/Learned_seeding_big_read.cpp with steps=3: SMEMs + reseeding + third round, every hit materialised).
+A "step" is one pass of the seeding path over the whole 10 M-read batch.
+
+value : reads/s with reads and index resident in HBM (meme_seed_run: seeding kernel + offset scans + hit gather)
+e2e   : reads/s through meme_seed_batch with HOST (pinned) buffers: H2D of the reads, kernels, D2H of SMEM/hit lists
+The index and reads are larger than L2 (11 GB / 1.5 GB vs 126 MB), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+CACHE = os.environ.get("MEME_BENCH_CACHE", "/tmp/meme_b200_bench")
+CHR1_LEN = 248_956_422
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("MEME_BENCH_GENOME", CHR1_LEN)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("MEME_BENCH_READS", 10_000_000)))
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--bits", type=int, default=0, help="P-RMI leaf bits (0 = build_rmis_dna.sh rule)")
+    ap.add_argument("--mode", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bsw", action="store_true", help="also time the banded-SW kernel on synthetic extension pairs")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def workload_key(a) -> str:
+    s = f"g{a.genome_len}-b{a.bits}-v3"
+    return hashlib.sha1(s.encode()).hexdigest()[:12]
+
+
+def prepare_index(a, device: str) -> tuple[str, dict]:
+    """Build (once per box) the chr1-scale index in the reference's file formats; return its prefix."""
+    ge.load_pkg()
+    from bwa_meme_b200 import synth, index_build, prmi_train
+    d = os.path.join(CACHE, workload_key(a))
+    prefix = os.path.join(d, "ref.fa")
+    meta_p = os.path.join(d, "meta.json")
+    if os.path.exists(meta_p):
+        return prefix, json.load(open(meta_p))
+    os.makedirs(d, exist_ok=True)
+    t0 = time.time()
+    if a.genome_len >= 20_000_000:
+        g = synth.make_genome_large(a.genome_len)
+    else:
+        g = synth.make_genome(a.genome_len)
+    g.tofile(os.path.join(d, "genome.u8"))
+    log(f"genome {a.genome_len} bp generated in {time.time() - t0:.1f}s; building index on {device}")
+    bits = a.bits or prmi_train.default_bits(2 * a.genome_len)
+    st = index_build.build_index(prefix, g, bits=bits, device=device, write_keys_file=False, verbose=False)
+    st["build_s"] = time.time() - t0
+    json.dump(st, open(meta_p, "w"))
+    log(f"index built in {st['build_s']:.1f}s: {st}")
+    return prefix, st
+
+
+def make_reads(a, d: str, seed: int, device: str):
+    """10 M x 150 bp synthetic reads (uint8 codes [n, L]) as a pinned host tensor."""
+    import torch
+    from bwa_meme_b200 import synth
+    g = np.fromfile(os.path.join(d, "genome.u8"), dtype=np.uint8)
+    gt = torch.from_numpy(g).to(device)
+    r = synth.make_reads_torch(gt, a.reads, a.read_len, seed=seed)
+    host = torch.empty(r.shape, dtype=torch.uint8, pin_memory=(device != "cpu"))
+    host.copy_(r)
+    del r, gt
+    if device != "cpu":
+        torch.cuda.empty_cache()
+    return host
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        mhz, mx, reasons, power = [], [], set(), []
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                mhz.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not mhz:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(mhz), "power_w_max": max(power)}
+
+
+def host_isa() -> str:
+    flags = open("/proc/cpuinfo").read()
+    return "avx512bw" if " avx512bw" in flags else ("avx2" if " avx2" in flags else "")
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def ref_seed_binary(mode: int):
+    isa = host_isa()
+    for cand in ([isa] if isa else []) + ["avx2"]:
+        p = os.path.join(ROOT, "oracle", "_ref", f"ref_seed_bench_mode{mode}.{cand}")
+        if os.path.exists(p) and (cand != "avx512bw" or isa == "avx512bw"):
+            return p
+    return None
+
+
+def run_reference_cpu(a, prefix: str, sample: np.ndarray, warmup: int, steps: int) -> dict:
+    """Time the reference's own seeding functions on host cores (oracle/_ref), else the oracle port."""
+    n, L = sample.shape
+    exe = ref_seed_binary(a.mode)
+    cores = host_cores()
+    if exe:
+        rb = os.path.join(os.path.dirname(prefix), f"sample_{os.getpid()}.bin")
+        with open(rb, "wb") as f:
+            f.write(np.array([n, L], dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(sample).tobytes())
+        t0 = time.time()
+        p = subprocess.run([exe, prefix, rb, str(cores), str(warmup), str(steps), "3"], capture_output=True, text=True)
+        os.remove(rb)
+        if p.returncode == 0:
+            passes = [l.split() for l in p.stdout.splitlines() if l.startswith("PASS")]
+            ms = [float(x[2]) for x in passes][warmup:]
+            tot = [(int(x[3]), int(x[4])) for x in passes]
+            return {"kind": "reference", "cores": cores, "ms": ms, "n_reads": n, "totals": tot[-1],
+                    "wall_s": time.time() - t0, "binary": os.path.basename(exe)}
+        log("reference binary failed:", p.stderr[-400:])
+    # oracle port, one core
+    O = ge.load_oracle()
+    oix = O.OracleIndex(prefix, a.mode)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    ms = []
+    for _ in range(max(1, min(steps, 2))):
+        t0 = time.time()
+        r = oix.seed(sample.reshape(-1), offs)
+        ms.append((time.time() - t0) * 1e3)
+    oix.close()
+    return {"kind": "port", "cores": 1, "ms": ms, "n_reads": n, "totals": (len(r["smems"]), len(r["hits"])), "binary": "oracle/seed_oracle.c"}
+
+
+def measured_peak_hbm() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    device = "cuda:0" if torch.cuda.is_available() else "cpu"
+    prefix, meta = prepare_index(a, device)
+    d = os.path.dirname(prefix)
+    cores = host_cores()
+    n_sample = a.cpu_sample or min(a.reads, max(200_000, 60_000 * cores))
+    keep, a.reads = a.reads, n_sample
+    sample = make_reads(a, d, seed=7, device=device).numpy()
+    a.reads = keep
+    res = run_reference_cpu(a, prefix, sample, a.warmup, a.steps)
+    ms = float(np.mean(res["ms"]))
+    value = res["n_reads"] / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "seeding_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"chr1-scale synthetic ref ({a.genome_len} bp, sa_num {meta['sa_num']}), "
+                               f"{a.read_len} bp SE reads, mode-{a.mode} P-RMI (2^{meta['bits']} leaves), seeding only",
+                   "step": f"one pass over a bounded sample of {res['n_reads']} reads of the 10 M-read workload"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": f"{res['n_reads']} reads x {a.steps} passes, {res['binary']}"},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    ge.build_lib()
+    ge.load_pkg()
+    from bwa_meme_b200 import capi, dist as mdist
+
+    # ---- index (rank 0 builds once per box, everyone loads) ----
+    if rank == 0:
+        prefix, meta = prepare_index(a, device)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        prefix, meta = prepare_index(a, device)
+    d = os.path.dirname(prefix)
+    torch.cuda.empty_cache()
+    t0 = time.time()
+    ix = capi.MemeIndex(prefix, mode=a.mode, device=local)
+    log(f"rank {rank}: index resident in HBM: {ix.device_bytes / 1e9:.2f} GB, loaded in {time.time() - t0:.1f}s")
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
+
+    # ---- reads: every rank owns its shard of the job (weak scaling: 10 M reads per GPU) ----
+    host = make_reads(a, d, seed=7 + rank, device=device)
+    n, L = host.shape
+    offs = torch.arange(n + 1, dtype=torch.int64) * L
+    offs_pinned = torch.empty_like(offs, pin_memory=True)
+    offs_pinned.copy_(offs)
+    opt = capi.default_seed_opt()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- HBM-resident timing: `value` ----
+    ix.seed_upload_ptr(host.data_ptr(), offs_pinned.data_ptr(), n)
+    for _ in range(a.warmup):
+        ix.seed_run(opt)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ix.seed_counters()["launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seed_ms = []
+    ev0.record()
+    for _ in range(a.steps):
+        ix.seed_run(opt)
+        seed_ms.append(ix.seed_last_ms())
+    ev1.record()
+    sync_all()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ix.seed_counters()["launches"] - l0
+    n_smems, n_hits = ix.seed_totals()
+    counters = ix.seed_counters()
+
+    # ---- end-to-end through the C ABI with host buffers: `e2e` ----
+    def e2e_step():
+        ix.seed_upload_ptr(host.data_ptr(), offs_pinned.data_ptr(), n)
+        ix.seed_run(opt)
+        return ix.seed_download(copy=False)
+
+    e2e_step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        tot = e2e_step()
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+    clocks = sampler.stop()
+    h2d = n * L + (n + 1) * 8
+    d2h = tot["n_smems"] * 24 + tot["n_hits"] * 8 + 2 * (n + 1) * 8
+
+    # ---- final hit gather (the one collective of the path): per-rank totals + checksums over NCCL ----
+    summary = mdist.gather_summary(ix, n, world, device)
+
+    # ---- max over ranks ----
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_reads = n * world
+    value = total_reads * a.steps / (dev_ms / 1e3)
+    e2e_value = total_reads * a.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        kseed_ms = float(np.mean([m["seed"] for m in seed_ms]))
+        gather_ms = float(np.mean([m["gather"] for m in seed_ms]))
+        line = {
+            "metric": "seeding_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"chr1-scale synthetic ref ({a.genome_len} bp, sa_num {meta['sa_num']}), "
+                                   f"{n} x {L} bp SE reads per GPU, mode-{a.mode} P-RMI (2^{meta['bits']} leaves), "
+                                   "seeding only (BASELINE.json configs[1])",
+                       "l2": "inputs larger than L2 (index %.1f GB, reads %.2f GB); no flush" % (ix.device_bytes / 1e9, n * L / 1e9),
+                       "index_hbm_gb": round(ix.device_bytes / 1e9, 2), "parallelism": f"reads sharded x{world}, index replicated"},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "results": {"smems_per_read": n_smems / n, "hits_per_read": n_hits / n, "searches_per_read": counters["searches"] / n,
+                        "sa_blocks_per_read": counters["block_probes"] / n, "kary_rounds_per_read": counters["kary_rounds"] / n,
+                        "ext_rounds_per_read": counters["ext_rounds"] / n, "gather": summary},
+            "kernel_ms": {"k_seed": kseed_ms, "k_gather": gather_ms, "offsets": float(np.mean([m["offsets"] for m in seed_ms])),
+                          "k_seed_share_of_step": kseed_ms / (dev_ms / a.steps)},
+        }
+        # ---- roofline + CPU baseline (rank 0, N=1) ----
+        peak, peak_src = measured_peak_hbm()
+        bytes_per_read = None
+        if world == 1 and not a.no_cpu_baseline:
+            O = ge.load_oracle()
+            cores = host_cores()
+            # (a) algorithmic bytes per read + full-scale parity check on a sample, via the oracle
+            ns = min(n, 20000)
+            sample = host[:ns].numpy()
+            soffs = np.arange(ns + 1, dtype=np.int64) * L
+            t0 = time.time()
+            oix = O.OracleIndex(prefix, a.mode)
+            want = oix.seed(sample.reshape(-1), soffs)
+            oix.close()
+            got = ix.seed(sample.reshape(-1), soffs)
+            same = all((got[k] == want[k]).all() for k in ("smem_off", "hit_off", "hits")) and \
+                all((got["smems"][f] == want["smems"][f]).all() for f in ("start", "end", "hitcount", "hitbeg"))
+            bytes_per_read = O.bytes_seed(want["counters"], ns * L, a.mode) / ns
+            line["parity_sample"] = {"reads": ns, "identical_to_oracle": bool(same), "oracle_s": time.time() - t0,
+                                     "oracle_counters_per_read": {k: v / ns for k, v in want["counters"].items()}}
+            # (b) the reference's own CPU seeding on all host cores, bounded sample
+            n_cpu = a.cpu_sample or min(n, max(200_000, 60_000 * cores))
+            res = run_reference_cpu(a, prefix, host[:n_cpu].numpy(), 1, 2)
+            cms = float(np.mean(res["ms"]))
+            line["cpu_baseline"] = {"value": res["n_reads"] / (cms / 1e3), "unit": "reads/s", "cores": res["cores"],
+                                    "kind": res["kind"], "sample": f"{res['n_reads']} reads x 2 passes after 1 warm-up, {res['binary']}"}
+        else:
+            line["cpu_baseline"] = None
+        if bytes_per_read is None:
+            ab = os.path.join(ROOT, "profiles", "algorithmic_bytes.json")
+            if os.path.exists(ab):
+                bytes_per_read = float(json.load(open(ab))["bytes_seed_per_read"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_seed_dram_bytes_per_read")
+                traffic = traffic * n if traffic else None
+            except Exception:
+                traffic = None
+        if bytes_per_read:
+            achieved = bytes_per_read * n / (kseed_ms / 1e3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "traffic": traffic, "kernel": "k_seed", "algorithmic_bytes_per_read": bytes_per_read,
+                                "peak_source": peak_src,
+                                "note": "algorithmic bytes = SURVEY §8d formula with counters from oracle/seed_oracle.c on a "
+                                        "sample of this workload; accesses are 8-24 B random reads, so the sector-granular DRAM "
+                                        "ceiling is well below the streaming peak"}
+        else:
+            line["roofline"] = None
+        if a.bsw:
+            line["bsw"] = bench_bsw(a, local)
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_bsw(a, device: int) -> dict:
+    """Secondary measurement: banded-SW kernel on extension-like pairs (GCUPS; kernel B is issue-bound)."""
+    import torch
+    from bwa_meme_b200 import capi
+    O = ge.load_oracle()
+    pairs, ref, qer = O.make_pairs(200000, seed=5, max_q=150, max_extra_ref=110, h0_max=120)
+    reps = 8
+    big = np.tile(pairs, reps)
+    b = capi.MemeBsw(device=device)
+    b.upload(big, ref, qer)
+    for _ in range(2):
+        b.run(100)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        b.run(100)
+    cells = b.cells()
+    dt = (time.perf_counter() - t0) / 3
+    b.close()
+    return {"pairs_per_s": len(big) / dt, "gcups": cells / dt / 1e9, "pairs": len(big), "ms": dt * 1e3}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

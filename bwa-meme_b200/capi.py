@@ -22,7 +22,7 @@ RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
 EXPORTS = [
     "meme_index_load", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
-    "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_bsw_create", "meme_bsw_free",
+    "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
@@ -84,6 +84,7 @@ def lib():
         L.meme_seed_download.argtypes = [vp, C.POINTER(SeedResult)]
         L.meme_seed_totals.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
         L.meme_seed_counters.argtypes = [vp, C.POINTER(u64 * 8)]
+        L.meme_seed_last_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
         L.meme_bsw_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.meme_bsw_free.argtypes = [vp]
         L.meme_bsw_free.restype = None
@@ -191,6 +192,11 @@ class MemeIndex:
         a, b = C.c_int64(), C.c_int64()
         _check(lib().meme_seed_totals(self.h, C.byref(a), C.byref(b)), "meme_seed_totals")
         return int(a.value), int(b.value)
+
+    def seed_last_ms(self):
+        ms = (C.c_float * 3)()
+        _check(lib().meme_seed_last_ms(self.h, C.byref(ms)), "meme_seed_last_ms")
+        return {"seed": float(ms[0]), "offsets": float(ms[1]), "gather": float(ms[2])}
 
     def seed_counters(self) -> dict:
         c = (C.c_uint64 * 8)()

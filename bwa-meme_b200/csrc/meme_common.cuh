@@ -74,6 +74,8 @@ struct meme_index {
     meme_seed_opt_t last_opt;
     int ran;
     u64 launches;
+    cudaEvent_t ev[6];                    // k_seed start/stop, offsets start/stop, k_gather start/stop
+    int ev_ready;
 };
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);

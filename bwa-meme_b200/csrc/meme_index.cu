@@ -254,6 +254,7 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
     CUDA_TRY(cudaMalloc((void **)&ix->d_ctrl, 64 * 8));
     CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, 64 * 8, st));
     CUDA_TRY(cudaMallocHost((void **)&ix->h_ctrl, 64 * 8));
+    for (int k = 0; k < 6; k++) CUDA_TRY(cudaEventCreate(&ix->ev[k]));
     CUDA_TRY(cudaStreamSynchronize(st));
     ix->launches = 3;
     *out = ix;
@@ -302,6 +303,7 @@ extern "C" void meme_index_free(meme_index_t *ix)
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = {ix->h_smems, ix->h_hits, ix->h_smem_off, ix->h_hit_off, ix->h_ctrl};
     for (void *p : host) if (p) cudaFreeHost(p);
+    for (int k = 0; k < 6; k++) if (ix->ev[k]) cudaEventDestroy(ix->ev[k]);
     cudaStreamDestroy(ix->own_stream);
     free(ix);
 }

@@ -709,10 +709,12 @@ static int seed_launch(meme_index_t *ix, const meme_seed_opt_t *opt)
     if (grid > need_blocks) grid = need_blocks;
     if (grid < 1) grid = 1;
     CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, 16 * 8, st));
+    CUDA_TRY(cudaEventRecord(ix->ev[0], st));
     k_seed<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, st>>>(ix->v, ix->d_codes, ix->d_read_off, n, *opt,
                                                           (RawSmem *)ix->d_pool, ix->cap_pool, ix->d_rd_pool_off,
                                                           ix->d_rd_nsmem, ix->d_rd_nhit, ix->d_ctrl);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ix->ev[1], st));
     ix->launches++;
     return MEME_OK;
 }
@@ -745,6 +747,7 @@ extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
         if ((rc = meme_grow_device(&ix->d_pool, &ix->cap_pool, (size_t)ix->h_ctrl[CT_POOL] + 1024, sizeof(RawSmem), st))) return rc;
     }
     // offsets
+    CUDA_TRY(cudaEventRecord(ix->ev[2], st));
     k_counts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(ix->d_rd_nsmem, ix->d_rd_nhit, n, ix->d_smem_off, ix->d_hit_off);
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, ix->d_smem_off, ix->d_smem_off, (int)(n + 1), st);
@@ -753,6 +756,7 @@ extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(ix->d_scan_tmp, t2, ix->d_smem_off, ix->d_smem_off, (int)(n + 1), st));
     t2 = ix->cap_scan_tmp;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(ix->d_scan_tmp, t2, ix->d_hit_off, ix->d_hit_off, (int)(n + 1), st));
+    CUDA_TRY(cudaEventRecord(ix->ev[3], st));
     ix->launches += 3;
     int64_t tot[2];
     CUDA_TRY(cudaMemcpyAsync(&tot[0], ix->d_smem_off + n, 8, cudaMemcpyDeviceToHost, st));
@@ -761,10 +765,13 @@ extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
     if ((rc = meme_grow_device((void **)&ix->d_smems, &ix->cap_smems, (size_t)tot[0] + 1, sizeof(meme_smem_t), st))) return rc;
     if ((rc = meme_grow_device((void **)&ix->d_hits, &ix->cap_hits, (size_t)tot[1] + 1, 8, st))) return rc;
     int64_t threads = n * 32;
+    CUDA_TRY(cudaEventRecord(ix->ev[4], st));
     k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ix->v, (const RawSmem *)ix->d_pool, ix->d_rd_pool_off,
                                                               ix->d_smem_off, ix->d_hit_off, n, opt->max_occ,
                                                               ix->d_smems, ix->d_hits);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ix->ev[5], st));
+    ix->ev_ready = 1;
     ix->launches++;
     ix->h_ctrl[32] = (u64)tot[0];
     ix->h_ctrl[33] = (u64)tot[1];
@@ -778,6 +785,16 @@ extern "C" int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_h
     CUDA_TRY(cudaStreamSynchronize(ix->stream));
     if (n_smems) *n_smems = ix->n_reads ? (int64_t)ix->h_ctrl[32] : 0;
     if (n_hits) *n_hits = ix->n_reads ? (int64_t)ix->h_ctrl[33] : 0;
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_last_ms(meme_index_t *ix, float ms[3])
+{
+    if (!ix || !ms || !ix->ev_ready) { meme_set_error("no timed seeding run"); return MEME_E_ARG; }
+    CUDA_TRY(cudaEventSynchronize(ix->ev[5]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[0], ix->ev[0], ix->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[1], ix->ev[2], ix->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[2], ix->ev[4], ix->ev[5]));
     return MEME_OK;
 }
 

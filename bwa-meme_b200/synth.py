@@ -124,3 +124,54 @@ def write_fastq(path: str, codes: np.ndarray, offsets: np.ndarray, prefix: str =
             f.write(b"\n+\n")
             f.write(b"I" * (b - a))
             f.write(b"\n")
+
+
+def make_genome_large(length: int, seed: int = 20261017, n_families: int = 300, copies: int = 200,
+                      rep_len: int = 1000, divergence: float = 0.08) -> np.ndarray:
+    """chr1-scale stand-in: uniform ACGT plus many diverged repeat families
+    (~n_families*copies*rep_len bases of repeats), so that seeding meets both unique and repetitive loci."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, size=length, dtype=np.uint8)
+    for _ in range(n_families):
+        unit = rng.integers(0, 4, size=rep_len, dtype=np.uint8)
+        pos = rng.integers(0, length - rep_len, size=copies)
+        div = rng.random() * divergence
+        for p in pos:
+            cp = unit.copy()
+            mut = rng.random(rep_len) < div
+            cp[mut] = (cp[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+            g[p:p + rep_len] = cp
+    g[0] = 1
+    g[-1] = 2
+    return g
+
+
+def make_reads_torch(genome_t, n_reads: int, read_len: int = 150, seed: int = 7, sub_rate: float = 0.01,
+                     n_frac: float = 0.005, chunk: int = 1 << 20):
+    """Bench-scale read generator on a torch device (plumbing): uniform start, random strand, substitutions,
+    0.5 % of reads with one N.  Returns a uint8 tensor [n_reads, read_len] on
+    genome_t's device."""
+    import torch
+    dev = genome_t.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    L = genome_t.numel()
+    out = torch.empty((n_reads, read_len), dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, device=dev)
+    for a in range(0, n_reads, chunk):
+        b = min(n_reads, a + chunk)
+        m = b - a
+        starts = torch.randint(0, L - read_len, (m,), generator=gen, device=dev)
+        r = genome_t[(starts[:, None] + ar[None, :])]
+        mut = torch.rand((m, read_len), generator=gen, device=dev) < sub_rate
+        delta = torch.randint(1, 4, (m, read_len), generator=gen, device=dev, dtype=torch.uint8)
+        r = torch.where(mut, (r + delta) & 3, r)
+        flip = torch.rand((m,), generator=gen, device=dev) < 0.5
+        rc = (3 - r).flip(1)
+        r = torch.where(flip[:, None], rc, r)
+        has_n = torch.rand((m,), generator=gen, device=dev) < n_frac
+        npos = torch.randint(0, read_len, (m,), generator=gen, device=dev)
+        nmask = has_n[:, None] & (ar[None, :] == npos[:, None])
+        r = torch.where(nmask, torch.full_like(r, 4), r)
+        out[a:b] = r
+    return out

@@ -1,0 +1,151 @@
+// oracle/ref_seed_bench.cpp -- TEST / BASELINE INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Times the UNMODIFIED reference seeding path on host cores: the index is loaded by the reference's
+// own memoryAllocLearned (src/fastmap.cpp:L351-638) and every read goes through the reference's own
+// Learned_getSMEMsAllPosOneThread + Learned_bwtSeedStrategyAllPosOneThread{,_mem_tradeoff}
+// (src/LearnedIndex_seeding.cpp), i.e. exactly what test/Learned_seeding_big_read.cpp (`steps=3`)
+// and mem_kernel1_core_Learned (src/bwamem.cpp:L1249-1397) execute per read.
+// Why not the harness binary itself: it re-loads the index on every invocation and reads FASTQ in
+// chunks of 10 M bases x threads, so W warm-up + K timed passes over a bounded sample cannot be
+// separated.  Only main(), the OpenMP loop and the read-buffer preparation below are ours.
+//
+// usage: ref_seed_bench <index prefix> <reads.bin> <threads> <warmup> <steps> [rounds=3] [dump.txt]
+//   reads.bin: int64 n_reads, int64 read_len, n_reads*read_len base codes (0..3, 4 = N)
+// prints one line per pass:  PASS <k> <ms> <total_smems> <total_hits>   and a final RESULT line.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <omp.h>
+#include "bwa.h"
+#include "bwamem.h"
+#include "fastmap.h"
+#include "FMI_search.h"
+#include "LearnedIndex_seeding.h"
+
+uint64_t proc_freq, tprof[LIM_R][LIM_C], prof[LIM_R];
+void memoryAllocLearned(ktp_aux_t *aux, worker_t &w, int32_t nreads, int32_t nthreads, char *idx_prefix);
+
+struct ReadBufs {
+    // 4 alignments x 2 strands of the 2-bit packed read; byte i of alignment s holds bases
+    // 4i-(4-s) .. 4i-(4-s)+3, first base in the low bits (bwamem.cpp:L1283-1344)
+    uint8_t fw[4][192], rc[4][192];
+    uint8_t rcseq[512];
+};
+
+static void pack(const uint8_t *seq, int len, uint8_t out[4][192])
+{
+    for (int s = 1; s <= 4; s++) {
+        int nbytes = ((len + 3) >> 2) + 1;
+        for (int i = 0; i < nbytes; i++) {
+            int b0 = 4 * i - (4 - s);
+            uint8_t v = 0;
+            for (int t = 0; t < 4; t++) {
+                int p = b0 + t;
+                uint8_t c = (p >= 0 && p < len && seq[p] < 4) ? seq[p] : 0;
+                v |= c << (2 * t);
+            }
+            out[s - 1][i] = v;
+        }
+    }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 6) { fprintf(stderr, "usage: %s prefix reads.bin threads warmup steps [rounds] [dump]\n", argv[0]); return 2; }
+    char *prefix = argv[1];
+    int threads = atoi(argv[3]), warmup = atoi(argv[4]), steps = atoi(argv[5]);
+    int rounds = argc > 6 ? atoi(argv[6]) : 3;
+    const char *dump = argc > 7 ? argv[7] : nullptr;
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) { perror(argv[2]); return 1; }
+    int64_t hdr[2];
+    if (fread(hdr, 8, 2, f) != 2) return 1;
+    int64_t n = hdr[0]; int L = (int)hdr[1];
+    std::vector<uint8_t> codes((size_t)n * L);
+    if (fread(codes.data(), 1, codes.size(), f) != codes.size()) return 1;
+    fclose(f);
+
+    FMI_search *fmi = new FMI_search(prefix);
+    fmi->load_index_other_elements(BWA_IDX_BNS | BWA_IDX_PAC);
+    ktp_aux_t aux;
+    memset(&aux, 0, sizeof aux);
+    aux.opt = mem_opt_init();
+    aux.fmi = fmi;
+    worker_t w;
+    memset(&w, 0, sizeof w);
+    auto t0 = std::chrono::steady_clock::now();
+    memoryAllocLearned(&aux, w, 1024, 1, prefix);
+    double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[ref_seed_bench] index load + runtime build: %.2f s\n", load_s);
+
+    const int min_seed_len = aux.opt->min_seed_len;
+    const int split_len = (int)(min_seed_len * aux.opt->split_factor + .499);
+    const int split_width = aux.opt->split_width, max_mem_intv = aux.opt->max_mem_intv;
+    omp_set_num_threads(threads);
+    std::vector<mem_tlv> smv(threads);
+    std::vector<u64v> hv(threads);
+    for (int t = 0; t < threads; t++) { kv_init_base(mem_tl, smv[t], 4096); kv_init_base(uint64_t, hv[t], 1 << 16); }
+    FILE *fd = dump ? fopen(dump, "w") : nullptr;
+    double best_ms = 1e30, sum_ms = 0;
+    for (int pass = 0; pass < warmup + steps; pass++) {
+        int64_t tot_smem = 0, tot_hits = 0;
+        auto p0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 512) reduction(+ : tot_smem, tot_hits)
+        for (int64_t r = 0; r < n; r++) {
+            int tid = omp_get_thread_num();
+            mem_tlv *smems = &smv[tid];
+            u64v *hits = &hv[tid];
+            smems->n = 0; hits->n = 0;
+            uint8_t *seq = codes.data() + r * L;
+            ReadBufs B;
+            bool hasN = false;
+            for (int k = 0; k < L; k++) { B.rcseq[L - 1 - k] = seq[k] < 4 ? 3 - seq[k] : 4; hasN |= seq[k] > 3; }
+            pack(seq, L, B.fw);
+            pack(B.rcseq, L, B.rc);
+            Learned_read_aux_t raux;
+            memset(&raux, 0, sizeof raux);
+            raux.unpacked_queue_binary_buf_shift1 = B.fw[0]; raux.unpacked_queue_binary_buf_shift2 = B.fw[1];
+            raux.unpacked_queue_binary_buf_shift3 = B.fw[2]; raux.unpacked_queue_binary_buf_shift4 = B.fw[3];
+            raux.unpacked_rc_queue_binary_buf_shift1 = B.rc[0]; raux.unpacked_rc_queue_binary_buf_shift2 = B.rc[1];
+            raux.unpacked_rc_queue_binary_buf_shift3 = B.rc[2]; raux.unpacked_rc_queue_binary_buf_shift4 = B.rc[3];
+            Learned_index_aux_t iaux;
+            iaux.sa_pos = w.sa_position; iaux.ref2sa = w.ref2sa; iaux.bns = fmi->idx->bns; iaux.pac = w.rc_pac;
+            iaux.ref_string = nullptr; iaux.bwt = nullptr;
+            raux.min_seed_len = min_seed_len; raux.l_seq = L; raux.max_l_seq = 0;
+            raux.unpacked_queue_buf = seq; raux.unpacked_rc_queue_buf = B.rcseq; raux.min_intv_limit = 1;
+            if (rounds > 1) Learned_getSMEMsAllPosOneThread(&iaux, &raux, smems, hits, hasN, split_len, split_width);
+            else Learned_getSMEMsAllPosOneThread_step1only(&iaux, &raux, smems, hits, hasN, split_len, split_width);
+            if (rounds > 2 && max_mem_intv > 0) {
+                raux.min_intv_limit = max_mem_intv;
+                raux.min_seed_len = min_seed_len + 1;
+#if MODE == 3
+                if (raux.max_l_seq != 0) Learned_bwtSeedStrategyAllPosOneThread_mem_tradeoff(&iaux, &raux, smems, hits, hasN);
+                else
+#endif
+                    Learned_bwtSeedStrategyAllPosOneThread(&iaux, &raux, smems, hits, hasN);
+            }
+            tot_smem += smems->n;
+            tot_hits += hits->n;
+            if (fd && pass == 0) {
+#pragma omp critical
+                {
+                    fprintf(fd, "%ld:\n", (long)r);
+                    for (size_t l = 0; l < smems->n; l++) {
+                        fprintf(fd, "[%d,%d] [", smems->a[l].start, smems->a[l].end);
+                        for (int k = 0; k < smems->a[l].hitcount; k++) fprintf(fd, "%lu,", hits->a[smems->a[l].hitbeg + k]);
+                        fprintf(fd, "]\n");
+                    }
+                }
+            }
+        }
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p0).count();
+        printf("PASS %d %.3f %ld %ld\n", pass, ms, (long)tot_smem, (long)tot_hits);
+        if (pass >= warmup) { sum_ms += ms; if (ms < best_ms) best_ms = ms; }
+    }
+    if (fd) fclose(fd);
+    printf("RESULT reads %ld read_len %d threads %d steps %d mean_ms %.3f best_ms %.3f load_s %.2f\n", (long)n, L, threads,
+           steps, steps ? sum_ms / steps : 0.0, best_ms, load_s);
+    return 0;
+}
