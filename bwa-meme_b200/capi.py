@@ -202,7 +202,7 @@ class MemeIndex:
         c = (C.c_uint64 * 8)()
         _check(lib().meme_seed_counters(self.h, C.byref(c)), "meme_seed_counters")
         return {"searches": int(c[0]), "block_probes": int(c[1]), "kary_rounds": int(c[2]), "ext_rounds": int(c[3]),
-                "overflow_reads": int(c[4]), "launches": int(c[5])}
+                "overflow_reads": int(c[4]), "launches": int(c[5]), "redo_reads": int(c[6]), "group": int(c[7])}
 
 
 class MemeBsw:

@@ -58,7 +58,7 @@ struct meme_index {
     int64_t *d_read_off; size_t cap_reads;
     int64_t n_reads; int64_t n_codes;
     // per-read: raw pool offset, smem count, hit count (after sampling)
-    u64 *d_rd_pool_off; u32 *d_rd_nsmem; u64 *d_rd_nhit;
+    u64 *d_rd_pool_off; u32 *d_rd_nsmem; u64 *d_rd_nhit; u32 *d_redo;
     int64_t *d_smem_off, *d_hit_off;      // n_reads+1 exclusive scans
     // raw SMEM pool written by the seed kernel: {start,end,cnt,lo}
     void *d_pool; size_t cap_pool;        // in records

@@ -26,7 +26,7 @@
 #include <cub/device/device_scan.cuh>
 #include "meme_common.cuh"
 
-#define WARPS_PER_BLOCK 8
+#define BLOCK_THREADS 256
 #define RW 12                           // 64-bit words per packed strand (MEME_MAX_READ_LEN/32 + slack)
 #define NMW (MEME_MAX_READ_LEN / 32)    // 32-bit N-mask words per strand
 #define MAXS MEME_MAX_SMEMS_PER_READ
@@ -38,13 +38,14 @@ struct RawSmem {            // 16 bytes
     u64 lo;                 // first SA index of the interval
 };
 
-struct WarpSm {
+template <int MAXS_T>
+struct GroupSm {
     u64 fw[RW], rc[RW];
     u32 nfw[NMW], nrc[NMW];
-    RawSmem sm[MAXS];
+    RawSmem sm[MAXS_T];
 };
 
-enum { CT_WORK = 0, CT_POOL = 1, CT_OVF = 2, CT_POOL_OVF = 3, CT_SEARCH = 8, CT_BLOCK = 9, CT_KARY = 10, CT_EXT = 11 };
+enum { CT_WORK = 0, CT_POOL = 1, CT_OVF = 2, CT_POOL_OVF = 3, CT_REDO = 4, CT_SEARCH = 8, CT_BLOCK = 9, CT_KARY = 10, CT_EXT = 11 };
 enum { START_RMI = 0, START_ISA_EXACT = 1, START_ISA_NEAR = 2 };
 
 // ---------------------------------------------------------------------------------------------
@@ -105,25 +106,48 @@ __device__ __forceinline__ u64 isa_at(const IndexView &ix, u64 p)
 
 // lcp(i) = min(LCP(T[SA[i]..], Q), V, sa_num - SA[i]) and "suffix < read" -- the contract of
 // compare_read_and_ref_binary* (reference L226-601); exact matches and text-end suffixes are "not less".
-__device__ __forceinline__ int lcp_at(const IndexView &ix, const u64 *qw, int from, int V, u64 idx, bool &less)
+// The inline key and the position are fetched together; once the first 32 bases match, up to four
+// further 32-base words of the packed reference are requested at once (one DRAM round trip).
+__device__ __noinline__ int lcp_at(const IndexView &ix, const u64 *qw, int from, int V, u64 idx, bool &less)
 {
     u64 p = sa_pos(ix, idx);
+    u64 r = ix.keys ? __ldg(ix.keys + idx) : 0;
     u64 ref_len = ix.sa_num - p;
     int cap = ref_len < (u64)V ? (int)ref_len : V;
-    u64 r = ix.keys ? __ldg(ix.keys + idx) : text32(ix.pac, p);
+    if (!ix.keys) r = text32(ix.pac, p);
     less = false;
-    for (int k = 0;; k++) {
-        u64 q = qword(qw, from + 32 * k);
+    {
+        u64 q = qword(qw, from);
         u64 x = r ^ q;
         if (x) {
             int b = (__ffsll((long long)x) - 1) >> 1;
-            int l = 32 * k + b;
-            if (l >= cap) return cap;
+            if (b >= cap) return cap;
             less = ((r >> (2 * b)) & 3) < ((q >> (2 * b)) & 3);
-            return l;
+            return b;
         }
-        if (32 * (k + 1) >= cap) return cap;
-        r = text32(ix.pac, p + 32 * (u64)(k + 1));
+        if (32 >= cap) return cap;
+    }
+    const u64 *wp = ix.pac + (p >> 5);
+    const int sh = (int)(p & 31) * 2;
+    for (int k0 = 1;; k0 += 4) {
+        u64 a[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) a[j] = (j == 0 || 32 * (k0 + j - 1) < cap) ? __ldg(wp + k0 + j) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int k = k0 + j;
+            if (32 * k >= cap) return cap;
+            u64 rr = sh ? (a[j] >> sh) | (a[j + 1] << (64 - sh)) : a[j];
+            u64 q = qword(qw, from + 32 * k);
+            u64 x = rr ^ q;
+            if (x) {
+                int b = (__ffsll((long long)x) - 1) >> 1;
+                int l = 32 * k + b;
+                if (l >= cap) return cap;
+                less = ((rr >> (2 * b)) & 3) < ((q >> (2 * b)) & 3);
+                return l;
+            }
+        }
     }
 }
 
@@ -135,7 +159,7 @@ __device__ __forceinline__ u64 fclamp(double v, double bound)
     return v > bound ? (u64)bound : (u64)v;
 }
 
-__device__ __forceinline__ u64 rmi_lookup(const IndexView &ix, u64 key, u64 &cerr, u64 &err)
+__device__ __noinline__ u64 rmi_lookup(const IndexView &ix, u64 key, u64 &cerr, u64 &err)
 {
     const RmiRec *rec = ix.l2 + (key >> ix.bit_shift);
     double a = __ldg(&rec->alpha), b = __ldg(&rec->beta);
@@ -164,135 +188,151 @@ __device__ __forceinline__ u64 rmi_key(u64 q0, int V)
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-warp search machinery
+// per-group search machinery: G lanes (8, 16 or 32) cooperate on one read
 // ---------------------------------------------------------------------------------------------
+template <int G, int MAXS_T>
 struct Searcher {
+    static constexpr u32 GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1);
     const IndexView &ix;
-    WarpSm *ws;
-    int lane;
+    GroupSm<MAXS_T> *ws;
+    int gl;                 // lane within the group
+    int gshift;             // first warp lane of the group
+    u32 gmask;              // warp mask of the group
     int L;                  // read length
     int n_sm;               // SMEMs collected so far
     int budget;
     bool overflow;
-    // statistics
     u32 st_search, st_block, st_kary, st_ext;
-    // query of the search in flight
-    const u64 *qw; int qfrom;
-    // block state (valid between locate() and the end of the search)
-    u64 base; int nvalid; int lcp;     // lcp: this lane's value (-1 if lane invalid)
-    // level state
-    u64 lo, hi; int nbl, nbr; int lev;
+    const u64 *qw; int qfrom;           // query of the search in flight
+    u64 base; int nvalid; int lcp;      // block state; lcp: this lane's value (-1 if lane invalid)
+    u32 lessmask;
+    u64 lo, hi; int nbl, nbr; int lev;  // level state
 
-    __device__ Searcher(const IndexView &ix_, WarpSm *ws_, int lane_) : ix(ix_), ws(ws_), lane(lane_) {}
+    __device__ Searcher(const IndexView &ix_, GroupSm<MAXS_T> *ws_, int lane) : ix(ix_), ws(ws_)
+    {
+        gl = lane % G;
+        gshift = lane - gl;
+        gmask = GM << gshift;
+    }
+    __device__ __forceinline__ u32 gballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & GM; }
+    template <typename T> __device__ __forceinline__ T gshfl(T v, int src) const { return __shfl_sync(gmask, v, src, G); }
+    __device__ __forceinline__ static int lead(u32 m) { return m == GM ? G : __ffs(~m) - 1; }   // leading ones
 
-    __device__ __forceinline__ void probe_block(u64 b, int V)
-    {   // contiguous block [b, b+32): full lcp per lane
+    __device__ __noinline__ void probe_block(u64 b, int V)
+    {   // contiguous block [b, b+G): full lcp per lane
         u64 n = ix.sa_num;
         base = b;
-        u64 idx = b + lane;
+        u64 idx = b + gl;
         bool valid = idx < n;
         bool less = false;
         lcp = valid ? lcp_at(ix, qw, qfrom, V, idx, less) : -1;
-        nvalid = __popc(__ballot_sync(FULL, valid));
-        lessmask = __ballot_sync(FULL, valid && less);
+        nvalid = __popc(gballot(valid));
+        lessmask = gballot(valid && less);
         st_block++;
     }
-    u32 lessmask;
 
     // Locate a block that contains a suffix with the maximal lcp. center/rad = hint window.
-    __device__ void locate(int V, u64 center, u64 rad_lo, u64 rad_hi)
+    __device__ __noinline__ void locate(int V, u64 center, u64 rad_lo, u64 rad_hi)
     {
         const u64 n = ix.sa_num;
         u64 lo_b = 0, hi_b = n;                 // insertion point t in [lo_b, hi_b]
+        // the prediction error is concentrated near zero: if the window is not much wider than a
+        // block, first try the block centred on the prediction itself
+        if (rad_lo + rad_hi + 2 > (u64)G && rad_lo + rad_hi <= (u64)(3 * G)) {
+            u64 b = center > (u64)(G / 2) ? center - G / 2 : 0;
+            if (n >= (u64)G && b > n - G) b = n - G;
+            probe_block(b, V);
+            int c = lead(lessmask);
+            bool left_ok = c > 0 || b == 0;
+            bool right_ok = c < nvalid || b + nvalid == n;
+            if (left_ok && right_ok) return;
+            if (!left_ok) hi_b = b; else lo_b = b + nvalid;
+        }
         for (int it = 0; it < 48; it++) {
             u64 pa = center > rad_lo ? center - rad_lo : 0;
             pa = pa < lo_b ? lo_b : (pa > hi_b ? hi_b : pa);
             u64 pb = center + rad_hi + 1;
             pb = pb < lo_b ? lo_b : (pb > hi_b ? hi_b : pb);
             u64 span = pb - pa;
-            if (span <= 30) {
+            if (span <= (u64)(G - 2)) {
                 // contiguous: entries pa-1 .. pb (span + 2 of them), centred in the block
-                u64 slack = (30 - span) / 2;
+                u64 slack = (G - 2 - span) / 2;
                 u64 b = pa > 1 + slack ? pa - 1 - slack : 0;
-                if (n >= 32 && b > n - 32) b = n - 32;
+                if (n >= (u64)G && b > n - G) b = n - G;
                 probe_block(b, V);
-                int c = lessmask == FULL ? 32 : __ffs(~lessmask) - 1;      // leading "less" lanes
+                int c = lead(lessmask);
                 bool left_ok = c > 0 || b == 0;
                 bool right_ok = c < nvalid || b + nvalid == n;
                 if (left_ok && right_ok) return;
                 if (!left_ok) hi_b = b; else lo_b = b + nvalid;
             } else {
-                u64 stride = (span + 31) / 32;
-                u64 idx = pa + (u64)(lane + 1) * stride - 1;
+                u64 stride = (span + G - 1) / G;
+                u64 idx = pa + (u64)(gl + 1) * stride - 1;
                 bool valid = idx < pb;
                 bool less = false;
                 if (valid) lcp_at(ix, qw, qfrom, V, idx, less);
-                u32 vm = __ballot_sync(FULL, valid), lm = __ballot_sync(FULL, valid && less);
-                int nv = __popc(vm);
-                int c = lm == FULL ? 32 : __ffs(~lm) - 1;
+                int nv = __popc(gballot(valid));
+                int c = lead(gballot(valid && less));
                 if (c > nv) c = nv;
                 if (c > 0) { u64 nl = pa + (u64)c * stride; if (nl > lo_b) lo_b = nl; }
                 if (c < nv) { u64 nh = pa + (u64)(c + 1) * stride - 1; if (nh < hi_b) hi_b = nh; }
-                else if (pb > lo_b && c == nv && nv > 0) { /* all probed entries are smaller */ }
                 st_kary++;
             }
             // widen the tentative window (the hint may be wrong: the reference's linear fix-up,
             // L2297-2357, makes the same guarantee)
-            rad_lo = rad_lo * 32 + 32;
-            rad_hi = rad_hi * 32 + 32;
+            rad_lo = rad_lo * G + G;
+            rad_hi = rad_hi * G + G;
         }
         // not reached for a sorted suffix array; keep the last block
     }
 
     // Furthest index in direction dir (+1/-1) reachable from `from` (known to satisfy lcp >= Lreq)
     // through entries that all satisfy lcp >= Lreq; nb = lcp of the first entry that does not (0 at
-    // the array ends).  32-ary gallop then 32-ary narrowing.  Stops early once `limit` entries
+    // the array ends).  G-ary gallop then G-ary narrowing.  Stops early once `limit` entries
     // beyond `from` are known to qualify (the exact edge is then not needed).
-    __device__ void extend(int dir, u64 from, int Lreq, u64 limit, u64 &edge, int &nb)
+    __device__ __noinline__ void extend(int dir, u64 from, int Lreq, u64 limit, u64 &edge, int &nb)
     {
         const u64 n = ix.sa_num;
         u64 cur = from, s = 1;
         bool up = true;
         for (int guard = 0;; guard++) {
-            if (guard > 200) { overflow = true; edge = cur; nb = 0; return; }   // cannot happen on a sorted SA
-            u64 off = (u64)(lane + 1) * s;
+            if (guard > 400) { overflow = true; edge = cur; nb = 0; return; }   // cannot happen on a sorted SA
+            u64 off = (u64)(gl + 1) * s;
             bool valid;
             u64 idx;
             if (dir > 0) { idx = cur + off; valid = idx < n && idx > cur; }
             else { valid = cur >= off; idx = cur - off; }
             bool less;
             int l = valid ? lcp_at(ix, qw, qfrom, Lreq, idx, less) : 0;
-            u32 okm = __ballot_sync(FULL, valid && l >= Lreq);
-            int c = okm == FULL ? 32 : __ffs(~okm) - 1;
+            int c = lead(gballot(valid && l >= Lreq));
             st_ext++;
             cur = dir > 0 ? cur + (u64)c * s : cur - (u64)c * s;
-            if (c == 32) {
+            if (c == G) {
                 u64 gone = dir > 0 ? cur - from : from - cur;
                 if (gone >= limit) { edge = cur; nb = Lreq; return; }
-                if (up && s < (1ull << 40)) s *= 32;
+                if (up && s < (1ull << 40)) s *= G;
                 continue;
             }
-            if (s == 1) { nb = __shfl_sync(FULL, l, c); edge = cur; return; }
+            if (s == 1) { nb = gshfl(l, c); edge = cur; return; }
             up = false;
-            s /= 32;
+            s /= G;
         }
     }
 
     // Start the level walk from the located block: level = maximal lcp, [lo,hi] = its interval.
     // The interval is made exact (extended past the block) only if it will be emitted
     // (exact_from <= level) or if it is still smaller than `need`.
-    __device__ void level_init(u64 need, int exact_from)
+    __device__ __noinline__ void level_init(u64 need, int exact_from)
     {
         const u64 n = ix.sa_num;
         int m = lcp;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+        for (int o = G / 2; o; o >>= 1) m = max(m, __shfl_xor_sync(gmask, m, o, G));
         lev = m;
-        u32 mask = __ballot_sync(FULL, lcp >= lev && lcp >= 0);
+        u32 mask = gballot(lcp >= lev && lcp >= 0);
         int anchor = __ffs(mask) - 1;
         // contiguous run of qualifying lanes that contains the anchor
-        u32 inv = ~mask;
-        u32 above = inv & ~((2u << anchor) - 1);         // zeros above the anchor
+        u32 above = ~mask & ~((2u << anchor) - 1);       // zeros above the anchor (bits >= G count as zeros of the run)
         int last = above ? __ffs(above) - 2 : 31;
         if (last > nvalid - 1) last = nvalid - 1;
         int first = anchor;
@@ -300,21 +340,21 @@ struct Searcher {
         const bool exact = lev >= exact_from;
         if (!exact && hi - lo + 1 >= need) { nbl = nbr = lev; return; }
         const u64 limit = exact ? ~0ull : need;
-        if (first > 0) nbl = __shfl_sync(FULL, lcp, first - 1);
+        if (first > 0) nbl = gshfl(lcp, first - 1);
         else if (base == 0) nbl = 0;
         else extend(-1, lo, lev, limit, lo, nbl);
-        if (last < nvalid - 1) nbr = __shfl_sync(FULL, lcp, last + 1);
+        if (last < nvalid - 1) nbr = gshfl(lcp, last + 1);
         else if (base + nvalid == n) nbr = 0;
         else extend(+1, hi, lev, limit, hi, nbr);
     }
 
     // Drop to the next level (the larger neighbour lcp) and regrow the interval (reference L2569-2574).
-    __device__ void level_next(u64 limit)
+    __device__ __noinline__ void level_next(u64 limit)
     {
         const u64 n = ix.sa_num;
         lev = max(nbl, nbr);
         if (lev <= 0) { lev = 0; lo = 0; hi = n - 1; nbl = nbr = 0; return; }
-        u32 mask = __ballot_sync(FULL, lcp >= lev && lcp >= 0);
+        u32 mask = gballot(lcp >= lev && lcp >= 0);
         if (nbl >= lev) {
             if (lo > base && lo <= base + (u64)nvalid) {          // lo-1 lies in the block
                 int p = (int)(lo - base);
@@ -325,7 +365,7 @@ struct Searcher {
                 } else {
                     int z = 31 - __clz(x);
                     lo = base + z + 1;
-                    nbl = __shfl_sync(FULL, lcp, z);
+                    nbl = gshfl(lcp, z);
                 }
             } else if (lo == 0) nbl = 0;
             else extend(-1, lo, lev, limit, lo, nbl);
@@ -340,7 +380,7 @@ struct Searcher {
                 } else {
                     int z = __ffs(x) - 1;
                     hi = base + z - 1;
-                    nbr = __shfl_sync(FULL, lcp, z);
+                    nbr = gshfl(lcp, z);
                 }
             } else if (hi == n - 1) nbr = 0;
             else extend(+1, hi, lev, limit, hi, nbr);
@@ -355,14 +395,14 @@ struct Searcher {
         st_search++;
     }
 
-    __device__ void locate_by(int V, int start_mode, u64 hint)
+    __device__ __noinline__ void locate_by(int V, int start_mode, u64 hint)
     {
         if (start_mode == START_ISA_EXACT) {
-            u64 b = hint > 15 ? hint - 15 : 0;
-            if (ix.sa_num >= 32 && b > ix.sa_num - 32) b = ix.sa_num - 32;
+            u64 b = hint > (u64)(G / 2 - 1) ? hint - (G / 2 - 1) : 0;
+            if (ix.sa_num >= (u64)G && b > ix.sa_num - G) b = ix.sa_num - G;
             probe_block(b, V);
         } else if (start_mode == START_ISA_NEAR) {
-            locate(V, hint, 8, 8);
+            locate(V, hint, G / 4, G / 4);
         } else {
             u64 cerr, err;
             u64 est = rmi_lookup(ix, rmi_key(qword(qw, qfrom), V), cerr, err);
@@ -372,8 +412,8 @@ struct Searcher {
 
     __device__ void push(int start, int end, u64 lo_, u64 cnt)
     {
-        if (n_sm >= MAXS) { overflow = true; return; }
-        if (lane == 0) {
+        if (n_sm >= MAXS_T) { overflow = true; return; }
+        if (gl == 0) {
             RawSmem r;
             r.se = (u32)start | ((u32)end << 16);
             r.cnt = cnt > 0xffffffffull ? 0xffffffffu : (u32)cnt;
@@ -385,7 +425,7 @@ struct Searcher {
 
     // right_smem_search / mem_search and their _tradeoff twins: level of the query with at least
     // min_intv occurrences; emits the SMEM when asked and long enough.
-    __device__ int search(int pivot, bool right, bool emit, int min_intv, int min_seed_len, int start_mode, u64 hint,
+    __device__ __noinline__ int search(int pivot, bool right, bool emit, int min_intv, int min_seed_len, int start_mode, u64 hint,
                           u64 *pos_out)
     {
         int V;
@@ -415,7 +455,8 @@ struct ReadState {
     int min_intv, min_seed_len;
 };
 
-__device__ __forceinline__ int do_search(Searcher &S, ReadState &R, int pivot, bool right, bool emit)
+template <class S_t>
+__device__ __noinline__ int do_search(S_t &S, ReadState &R, int pivot, bool right, bool emit)
 {   // start selection of reference L1741-1816 / L1926-2040
     const IndexView &ix = S.ix;
     if (ix.mode == 3) {
@@ -437,43 +478,62 @@ __device__ __forceinline__ int do_search(Searcher &S, ReadState &R, int pivot, b
 
 __device__ __forceinline__ bool is_n(const u32 *nm, int p) { return (nm[p >> 5] >> (p & 31)) & 1; }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restrict__ read_off, int64_t n_reads,
-       meme_seed_opt_t opt, RawSmem *__restrict__ pool, u64 pool_cap, u64 *__restrict__ rd_pool_off,
-       u32 *__restrict__ rd_nsmem, u64 *__restrict__ rd_nhit, u64 *__restrict__ ctrl)
+struct SeedArgs {
+    const uint8_t *codes; const int64_t *read_off; int64_t n_reads;
+    const u32 *worklist; int64_t n_work;        // null: work items are reads 0..n_reads-1
+    u32 *redo;                                  // null in the fallback launch
+    RawSmem *pool; u64 pool_cap;
+    u64 *rd_pool_off; u32 *rd_nsmem; u64 *rd_nhit; u64 *ctrl;
+    meme_seed_opt_t opt;
+};
+
+template <int G, int MAXS_T, int MINB>
+__global__ void __launch_bounds__(BLOCK_THREADS, MINB) k_seed(IndexView ix, SeedArgs A)
 {
-    __shared__ WarpSm wsm[WARPS_PER_BLOCK];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSm *ws = &wsm[wid];
-    Searcher S(ix, ws, lane);
+    constexpr int GROUPS = BLOCK_THREADS / G;
+    __shared__ GroupSm<MAXS_T> gsm[GROUPS];
+    const int lane = threadIdx.x & 31;
+    typedef Searcher<G, MAXS_T> S_t;
+    GroupSm<MAXS_T> *ws = &gsm[threadIdx.x / G];
+    S_t S(ix, ws, lane);
+    const int gl = S.gl;
+    const u32 gmask = S.gmask;
+    const meme_seed_opt_t &opt = A.opt;
     S.st_search = S.st_block = S.st_kary = S.st_ext = 0;
     for (;;) {
-        u64 r = 0;
-        if (lane == 0) r = atomicAdd((unsigned long long *)&ctrl[CT_WORK], 1ull);
-        r = __shfl_sync(FULL, r, 0);
-        if (r >= (u64)n_reads) break;
-        const int64_t o0 = read_off[r];
-        const int L = (int)(read_off[r + 1] - o0);
-        const uint8_t *seq = codes + o0;
-        __syncwarp();
+        u64 wi = 0;
+        if (gl == 0) wi = atomicAdd((unsigned long long *)&A.ctrl[CT_WORK], 1ull);
+        wi = S.gshfl(wi, 0);
+        if (wi >= (u64)A.n_work) break;
+        const u64 r = A.worklist ? A.worklist[wi] : wi;
+        const int64_t o0 = A.read_off[r];
+        const int L = (int)(A.read_off[r + 1] - o0);
+        const uint8_t *seq = A.codes + o0;
+        __syncwarp(gmask);
         // ---- pack the read and its reverse complement (reference src/bwamem.cpp:L1277-1344) ----
+        const int nw = (L + 31) >> 5;
         for (int w = 0; w < RW; w++) {
-            int p = w * 32 + lane;
-            u32 cf = p < L ? seq[p] : 0, cr = p < L ? seq[L - 1 - p] : 0;
-            bool nf = cf > 3, nr = cr > 3;
-            cf = nf ? 0 : cf;
-            cr = nr ? 0 : 3 - cr;
-            if (p >= L) cr = 0;
-            u32 f0 = __ballot_sync(FULL, cf & 1), f1 = __ballot_sync(FULL, cf & 2);
-            u32 r0 = __ballot_sync(FULL, cr & 1), r1 = __ballot_sync(FULL, cr & 2);
-            u32 mf = __ballot_sync(FULL, nf), mr = __ballot_sync(FULL, nr);
-            if (lane == 0) {
+            u32 f0 = 0, f1 = 0, r0 = 0, r1 = 0, mf = 0, mr = 0;
+            if (w < nw) {
+#pragma unroll
+                for (int sub = 0; sub < 32 / G; sub++) {
+                    int p = w * 32 + sub * G + gl;
+                    u32 cf = p < L ? seq[p] : 0, cr = p < L ? seq[L - 1 - p] : 0;
+                    bool nf = cf > 3, nr = cr > 3;
+                    cf = nf ? 0 : cf;
+                    cr = (nr || p >= L) ? 0 : 3 - cr;
+                    f0 |= S.gballot(cf & 1) << (sub * G); f1 |= S.gballot(cf & 2) << (sub * G);
+                    r0 |= S.gballot(cr & 1) << (sub * G); r1 |= S.gballot(cr & 2) << (sub * G);
+                    mf |= S.gballot(nf) << (sub * G); mr |= S.gballot(nr) << (sub * G);
+                }
+            }
+            if (gl == 0) {
                 ws->fw[w] = interleave32(f0, f1);
                 ws->rc[w] = interleave32(r0, r1);
                 if (w < NMW) { ws->nfw[w] = mf; ws->nrc[w] = mr; }
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
         S.L = L; S.n_sm = 0; S.overflow = false; S.budget = 0;
         ReadState R;
         R.full_match = false; R.use_cached = false; R.max_refpos = 0;
@@ -511,7 +571,8 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
             int after = S.n_sm;
             if (opt.rounds < 2) continue;
             // --- reseeding: Learned_getSMEMsOnePosOneThread (L1897-2126) for long, rare SMEMs ---
-            for (int k = before; k < after && k < MAXS; k++) {
+            __syncwarp(gmask);
+            for (int k = before; k < after && k < MAXS_T && !S.overflow; k++) {
                 RawSmem m = ws->sm[k];
                 int qb = m.se & 0xffff, qe = m.se >> 16;
                 if (qe - qb < opt.split_len || m.cnt > (u32)opt.split_width) continue;
@@ -532,6 +593,7 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
                     int rr = do_search(S, R, p2, true, true);
                     sp = p2 + rr;
                     p2 = sp;
+                    __syncwarp(gmask);
                 }
                 R.use_cached = false;
                 R.min_intv = 1;
@@ -566,14 +628,23 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
             }
         }
         // ---- sort by (start, end, emission order) = ks_introsort(mem_smem_sort_lt_learned), bwamem.cpp:L1397 ----
+        __syncwarp(gmask);
+        if (S.overflow && A.redo) {
+            // too many SMEMs for the group's shared-memory list: hand the read to the wide fallback launch
+            if (gl == 0) {
+                u64 k = atomicAdd((unsigned long long *)&A.ctrl[CT_REDO], 1ull);
+                A.redo[k] = (u32)r;
+                A.rd_pool_off[r] = 0; A.rd_nsmem[r] = 0; A.rd_nhit[r] = 0;
+            }
+            continue;
+        }
         const int ns = S.n_sm;
-        __syncwarp();
         u64 poff = 0;
-        if (lane == 0) poff = atomicAdd((unsigned long long *)&ctrl[CT_POOL], (unsigned long long)ns);
-        poff = __shfl_sync(FULL, poff, 0);
-        bool fits = poff + ns <= pool_cap;
+        if (gl == 0) poff = atomicAdd((unsigned long long *)&A.ctrl[CT_POOL], (unsigned long long)ns);
+        poff = S.gshfl(poff, 0);
+        bool fits = poff + ns <= A.pool_cap;
         u64 nh = 0;
-        for (int i = lane; i < ns; i += 32) {
+        for (int i = gl; i < ns; i += G) {
             RawSmem a = ws->sm[i];
             u32 ka = ((a.se & 0xffff) << 16) | (a.se >> 16);
             int rank = 0;
@@ -582,7 +653,7 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
                 u32 kb = ((se & 0xffff) << 16) | (se >> 16);
                 rank += (kb < ka) || (kb == ka && j < i);
             }
-            if (fits) pool[poff + rank] = a;
+            if (fits) A.pool[poff + rank] = a;
             u64 c = a.cnt;
             if (opt.max_occ > 0) {
                 u64 step = c > (u64)opt.max_occ ? c / opt.max_occ : 1;
@@ -592,22 +663,21 @@ k_seed(IndexView ix, const uint8_t *__restrict__ codes, const int64_t *__restric
             nh += c;
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(FULL, nh, o);
-        if (lane == 0) {
-            rd_pool_off[r] = poff;
-            rd_nsmem[r] = fits ? ns : 0;
-            rd_nhit[r] = fits ? nh : 0;
-            if (!fits) atomicExch((unsigned long long *)&ctrl[CT_POOL_OVF], 1ull);
-            if (S.overflow) atomicAdd((unsigned long long *)&ctrl[CT_OVF], 1ull);
+        for (int o = G / 2; o; o >>= 1) nh += __shfl_xor_sync(gmask, nh, o, G);
+        if (gl == 0) {
+            A.rd_pool_off[r] = poff;
+            A.rd_nsmem[r] = fits ? ns : 0;
+            A.rd_nhit[r] = fits ? nh : 0;
+            if (!fits) atomicExch((unsigned long long *)&A.ctrl[CT_POOL_OVF], 1ull);
+            if (S.overflow) atomicAdd((unsigned long long *)&A.ctrl[CT_OVF], 1ull);
         }
     }
     // statistics
-    u32 a = S.st_search, b = S.st_block, c = S.st_kary, d = S.st_ext;
-    if (lane == 0) {
-        atomicAdd((unsigned long long *)&ctrl[CT_SEARCH], (unsigned long long)a);
-        atomicAdd((unsigned long long *)&ctrl[CT_BLOCK], (unsigned long long)b);
-        atomicAdd((unsigned long long *)&ctrl[CT_KARY], (unsigned long long)c);
-        atomicAdd((unsigned long long *)&ctrl[CT_EXT], (unsigned long long)d);
+    if (gl == 0) {
+        atomicAdd((unsigned long long *)&A.ctrl[CT_SEARCH], (unsigned long long)S.st_search);
+        atomicAdd((unsigned long long *)&A.ctrl[CT_BLOCK], (unsigned long long)S.st_block);
+        atomicAdd((unsigned long long *)&A.ctrl[CT_KARY], (unsigned long long)S.st_kary);
+        atomicAdd((unsigned long long *)&A.ctrl[CT_EXT], (unsigned long long)S.st_ext);
     }
 }
 
@@ -679,9 +749,9 @@ extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const in
     if (ix->cap_reads != old_cap || !ix->d_rd_pool_off) {
         size_t c = ix->cap_reads, dummy;
         void **bufs[] = {(void **)&ix->d_rd_pool_off, (void **)&ix->d_rd_nsmem, (void **)&ix->d_rd_nhit,
-                         (void **)&ix->d_smem_off, (void **)&ix->d_hit_off};
-        size_t el[] = {8, 4, 8, 8, 8};
-        for (int k = 0; k < 5; k++) {
+                         (void **)&ix->d_smem_off, (void **)&ix->d_hit_off, (void **)&ix->d_redo};
+        size_t el[] = {8, 4, 8, 8, 8, 4};
+        for (int k = 0; k < 6; k++) {
             if (*bufs[k]) { CUDA_TRY(cudaFree(*bufs[k])); *bufs[k] = nullptr; }
             dummy = 0;
             if ((rc = meme_grow_device(bufs[k], &dummy, c, el[k], st))) return rc;
@@ -695,27 +765,74 @@ extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const in
     return MEME_OK;
 }
 
+template <int G, int MAXS_T, int MINB>
+static int launch_one(meme_index_t *ix, const SeedArgs &A)
+{
+    int dev_sms = 0, per_sm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed<G, MAXS_T, MINB>, BLOCK_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int groups = BLOCK_THREADS / G;
+    int64_t need_blocks = (A.n_work + groups - 1) / groups;
+    int64_t grid = (int64_t)dev_sms * per_sm;           // persistent: one wave of resident CTAs
+    if (grid > need_blocks) grid = need_blocks;
+    if (grid < 1) grid = 1;
+    k_seed<G, MAXS_T, MINB><<<(unsigned)grid, BLOCK_THREADS, 0, ix->stream>>>(ix->v, A);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    return MEME_OK;
+}
+
+// lanes per read of the main launch: 8, 16 or 32 (MEME_SEED_GROUP overrides)
+static int seed_group()
+{
+    static int g = 0;
+    if (!g) {
+        const char *e = getenv("MEME_SEED_GROUP");
+        g = e ? atoi(e) : 8;
+        if (g != 8 && g != 16 && g != 32) g = 8;
+    }
+    return g;
+}
+
 static int seed_launch(meme_index_t *ix, const meme_seed_opt_t *opt)
 {
     cudaStream_t st = ix->stream;
-    int64_t n = ix->n_reads;
-    int dev_sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, WARPS_PER_BLOCK * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    int64_t need_blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    int64_t grid = (int64_t)dev_sms * per_sm;
-    if (grid > need_blocks) grid = need_blocks;
-    if (grid < 1) grid = 1;
+    SeedArgs A;
+    A.codes = ix->d_codes; A.read_off = ix->d_read_off; A.n_reads = ix->n_reads;
+    A.worklist = nullptr; A.n_work = ix->n_reads; A.redo = ix->d_redo;
+    A.pool = (RawSmem *)ix->d_pool; A.pool_cap = ix->cap_pool;
+    A.rd_pool_off = ix->d_rd_pool_off; A.rd_nsmem = ix->d_rd_nsmem; A.rd_nhit = ix->d_rd_nhit; A.ctrl = ix->d_ctrl;
+    A.opt = *opt;
     CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, 16 * 8, st));
     CUDA_TRY(cudaEventRecord(ix->ev[0], st));
-    k_seed<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, st>>>(ix->v, ix->d_codes, ix->d_read_off, n, *opt,
-                                                          (RawSmem *)ix->d_pool, ix->cap_pool, ix->d_rd_pool_off,
-                                                          ix->d_rd_nsmem, ix->d_rd_nhit, ix->d_ctrl);
-    CUDA_TRY(cudaGetLastError());
+    int rc;
+    static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 0;
+    switch (seed_group() * 10 + minb) {
+    case 320: case 323: rc = launch_one<32, 64, 3>(ix, A); break;
+    case 324: rc = launch_one<32, 64, 4>(ix, A); break;
+    case 160: case 163: rc = launch_one<16, 64, 3>(ix, A); break;
+    case 164: rc = launch_one<16, 64, 4>(ix, A); break;
+    case 162: rc = launch_one<16, 64, 2>(ix, A); break;
+    case 83: rc = launch_one<8, 48, 3>(ix, A); break;
+    case 84: rc = launch_one<8, 48, 4>(ix, A); break;
+    default: rc = launch_one<8, 48, 2>(ix, A); break;
+    }
+    if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ix->ev[1], st));
-    ix->launches++;
+    CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    u64 n_redo = ix->h_ctrl[CT_REDO];
+    if (n_redo) {
+        // reads whose SMEM list outgrew the group's shared-memory slot: one warp per read, long list
+        A.worklist = ix->d_redo; A.n_work = (int64_t)n_redo; A.redo = nullptr;
+        CUDA_TRY(cudaMemsetAsync(ix->d_ctrl + CT_WORK, 0, 8, st));
+        if ((rc = launch_one<32, MAXS, 1>(ix, A))) return rc;
+        CUDA_TRY(cudaEventRecord(ix->ev[1], st));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ix->h_ctrl[CT_REDO] = n_redo;
+    }
     return MEME_OK;
 }
 
@@ -735,13 +852,11 @@ extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
     }
     for (int attempt = 0;; attempt++) {
         if ((rc = seed_launch(ix, opt))) return rc;
-        // the pool is bump-allocated; if it overflowed, grow it to the exact need and rerun
-        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
         if (ix->h_ctrl[CT_OVF]) {
             meme_set_error("%llu read(s) produced more than %d SMEMs", (unsigned long long)ix->h_ctrl[CT_OVF], MAXS);
             return MEME_E_OVERFLOW;
         }
+        // the pool is bump-allocated; if it overflowed, grow it to the exact need and rerun
         if (!ix->h_ctrl[CT_POOL_OVF]) break;
         if (attempt >= 2) { meme_set_error("SMEM pool overflow persists"); return MEME_E_NOMEM; }
         if ((rc = meme_grow_device(&ix->d_pool, &ix->cap_pool, (size_t)ix->h_ctrl[CT_POOL] + 1024, sizeof(RawSmem), st))) return rc;
@@ -804,7 +919,7 @@ extern "C" int meme_seed_counters(meme_index_t *ix, uint64_t counters[8])
     CUDA_TRY(cudaStreamSynchronize(ix->stream));
     counters[0] = ix->h_ctrl[CT_SEARCH]; counters[1] = ix->h_ctrl[CT_BLOCK]; counters[2] = ix->h_ctrl[CT_KARY];
     counters[3] = ix->h_ctrl[CT_EXT]; counters[4] = ix->h_ctrl[CT_OVF]; counters[5] = ix->launches;
-    counters[6] = counters[7] = 0;
+    counters[6] = ix->h_ctrl[CT_REDO]; counters[7] = (u64)seed_group();
     return MEME_OK;
 }
 

@@ -110,7 +110,8 @@ int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out);        /* syn
 /* Totals of the last run without copying the lists (synchronises). */
 int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits);
 /* Device-side work counters of the last run: [0] searches, [1] SA block probes, [2] k-ary rounds,
- * [3] extension rounds, [4] reads flagged overflow, [5] kernel launches since the handle was created. */
+ * [3] extension rounds, [4] reads flagged overflow, [5] kernel launches since the handle was created,
+ * [6] reads re-run by the wide fallback launch, [7] lanes per read of the main launch. */
 int meme_seed_counters(meme_index_t *ix, uint64_t counters[8]);
 /* CUDA-event durations (ms) of the last meme_seed_run on its stream: [0] the seeding kernel,
  * [1] offset scans, [2] the hit-materialisation kernel. */
