@@ -74,9 +74,16 @@ struct meme_index {
     meme_seed_opt_t last_opt;
     int ran;
     u64 launches;
+    // ---- thread-per-task seeding path (meme_seed_tpr.cu) ----
+    u64 *d_packed; size_t cap_packed; u32 *d_nmask; size_t cap_nmask;
+    uint8_t *d_rd_full; size_t cap_rd_full; u64 *d_rd_maxref; size_t cap_rd_maxref;
+    u64 *d_pool_keys; size_t cap_pool_keys; void *d_pool_vals; size_t cap_pool_vals;
+    u64 *d_pool_keys2; size_t cap_pool_keys2; void *d_pool_vals2; size_t cap_pool_vals2;
+    void *d_t2; size_t cap_t2;
     cudaEvent_t ev[6];                    // k_seed start/stop, offsets start/stop, k_gather start/stop
     int ev_ready;
 };
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);
 int meme_grow_pinned(void **p, size_t *cap, size_t need, size_t elem);
+int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);

@@ -299,7 +299,9 @@ extern "C" void meme_index_free(meme_index_t *ix)
     cudaStreamSynchronize(ix->stream);
     void *dev[] = {ix->d_keys, ix->d_pos_lo, ix->d_pos_hi, ix->d_isa_lo, ix->d_isa_hi, ix->d_pac, ix->d_l1, ix->d_l2,
                    ix->d_codes, ix->d_read_off, ix->d_rd_pool_off, ix->d_rd_nsmem, ix->d_rd_nhit, ix->d_smem_off,
-                   ix->d_hit_off, ix->d_pool, ix->d_ctrl, ix->d_scan_tmp, ix->d_smems, ix->d_hits, ix->d_redo};
+                   ix->d_hit_off, ix->d_pool, ix->d_ctrl, ix->d_scan_tmp, ix->d_smems, ix->d_hits, ix->d_redo,
+                   ix->d_packed, ix->d_nmask, ix->d_rd_full, ix->d_rd_maxref, ix->d_pool_keys, ix->d_pool_vals, ix->d_pool_keys2,
+                   ix->d_pool_vals2, ix->d_t2};
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = {ix->h_smems, ix->h_hits, ix->h_smem_off, ix->h_hit_off, ix->h_ctrl};
     for (void *p : host) if (p) cudaFreeHost(p);
