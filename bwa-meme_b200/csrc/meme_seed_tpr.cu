@@ -224,7 +224,7 @@ struct Thread {
     {
         epc = 0; e_dir = dir; e_from = from; e_L = Lreq; e_limit = limit;
     }
-    __device__ __noinline__ bool E_step()
+    __device__ __forceinline__ bool E_step()
     {
         const u64 n = ix.sa_num;
         switch (epc) {
@@ -263,7 +263,7 @@ struct Thread {
     }
 
     // ---------------------------------------------------------------- one level drop (reference L2569-2574)
-    __device__ __noinline__ bool LV_step()
+    __device__ __forceinline__ bool LV_step()
     {
         const u64 n = ix.sa_num;
         switch (lvpc) {
@@ -334,7 +334,7 @@ struct Thread {
         start_search(pv, right, emit, min_intv, min_seed_len, ST_RMI, 0, false);
     }
 
-    __device__ __noinline__ bool S_step()
+    __device__ __forceinline__ bool S_step()
     {
         const u64 n = ix.sa_num;
         switch (spc) {
@@ -465,7 +465,7 @@ struct Thread {
 
     // ---------------------------------------------------------------- drivers
     // T1: zig-zag pass (reference L913-972 outer loop + L1691-1894)
-    __device__ __noinline__ bool D1_step()
+    __device__ __forceinline__ bool D1_step()
     {
         switch (dpc) {
         case 0:
@@ -508,7 +508,7 @@ struct Thread {
     }
 
     // T2: reseeding of one SMEM (reference L1897-2126); the task fetch preloaded pivot/min_intv/cache fields
-    __device__ __noinline__ bool D2_step()
+    __device__ __forceinline__ bool D2_step()
     {
         switch (dpc) {
         case 0:
@@ -535,7 +535,7 @@ struct Thread {
     }
 
     // T3: third round (reference L974-1466)
-    __device__ __noinline__ bool D3_step()
+    __device__ __forceinline__ bool D3_step()
     {
         const int msl = A.opt.min_seed_len + 1, mi = A.opt.max_mem_intv;
         switch (dpc) {
@@ -860,26 +860,44 @@ __global__ void k_gather2(IndexView ix, const u64 *__restrict__ keys, const Pool
 
 }  // namespace tpr
 
+#include "meme_seed_flat.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // host pipeline
 // ---------------------------------------------------------------------------------------------
 using namespace tpr;
 
-template <int KIND>
-static int launch_tpr(meme_index_t *ix, const Args &A)
+// MEME_SEED_IMPL: "flat" (default) = flat state machine, "tpr" = coroutine formulation, "coop" = group per read
+static int tpr_variant()
 {
-    if (A.n_tasks <= 0) return MEME_OK;
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MEME_SEED_IMPL"); v = (e && !strcmp(e, "tpr")) ? 1 : 0; }
+    return v;
+}
+
+template <class K>
+static int launch_kernel(meme_index_t *ix, const Args &A, K kernel)
+{
     int sms = 0, per_sm = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tpr<KIND>, TPR_THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPR_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sms * per_sm, need = (A.n_tasks + TPR_THREADS - 1) / TPR_THREADS;
     if (grid > need) grid = need;
     CUDA_TRY(cudaMemsetAsync(ix->d_ctrl + C_WORK, 0, 8, ix->stream));
-    k_tpr<KIND><<<(unsigned)grid, TPR_THREADS, 0, ix->stream>>>(ix->v, A);
+    kernel<<<(unsigned)grid, TPR_THREADS, 0, ix->stream>>>(ix->v, A);
     CUDA_TRY(cudaGetLastError());
     ix->launches++;
     return MEME_OK;
+}
+
+template <int KIND>
+static int launch_tpr(meme_index_t *ix, const Args &A)
+{
+    if (A.n_tasks <= 0) return MEME_OK;
+    if (tpr_variant() == 1) return launch_kernel(ix, A, k_tpr<KIND>);
+    if (ix->v.pos_wide) return launch_kernel(ix, A, k_flat<KIND, true>);
+    return launch_kernel(ix, A, k_flat<KIND, false>);
 }
 
 int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
