@@ -23,8 +23,8 @@ enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 template <bool WIDE> struct IdxT { typedef u32 type; };
 template <> struct IdxT<true> { typedef u64 type; };
 
-template <int KIND, bool WIDE>
-__global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
+template <int KIND, bool WIDE, int MINB>
+__global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A)
 {
     typedef typename IdxT<WIDE>::type idx_t;
     __shared__ u32 smem[TPR_THREADS * TPR_SW];
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
     u64 lv_limit = 0; int lv_ret = 0;
     // ---- extension ----
     int e_dir = 0, e_L = 0, e_cnt = 0, e_nb = 0, e_guard = 0, e_ret = 0; bool e_up = true;
-    idx_t e_from = 0, e_cur = 0, e_edge = 0; u64 e_s = 1, e_limit = 0;
+    idx_t e_from = 0, e_cur = 0, e_edge = 0; u64 e_s = 1, e_limit = 0; int e_sh = 0;
     // ---- driver ----
     int pivot = 0, sp = 0, next = 0, min_intv = 1, min_seed_len = opt_msl, cache_pivot = 0, cache_pivot_end = 0;
     bool full_match = false, use_cached = false;
@@ -119,11 +119,12 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
             A.pool_vals[k] = v;
         } else atomicExch((unsigned long long *)&A.ctrl[C_POOL_OVF], 1ull);
         n_emit++;
-        u64 c = c32;
+        u32 c = c32;
         if (A.opt.max_occ > 0) {
-            u64 step = c > (u64)A.opt.max_occ ? c / A.opt.max_occ : 1;
-            u64 t = (c + step - 1) / step;
-            c = t < (u64)A.opt.max_occ ? t : (u64)A.opt.max_occ;
+            u32 mo = (u32)A.opt.max_occ;
+            u32 step = c > mo ? c / mo : 1;
+            u32 t = (c - 1) / step + 1;
+            c = c == 0 ? 0 : (t < mo ? t : mo);
         }
         n_hit += c;
         if (KIND == 1 && A.opt.rounds >= 2 && end - start >= A.opt.split_len && c32 <= (u32)A.opt.split_width) {
@@ -469,15 +470,15 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
 
             // ------------------------------------------------ extension: 8-ary gallop, then 8-ary narrowing
             e_begin:
-                e_cur = e_from; e_s = 1; e_up = true; e_guard = 0;
+                e_cur = e_from; e_s = 1; e_sh = 0; e_up = true; e_guard = 0;
             e_probe:
                 if (++e_guard > 400) { e_edge = e_cur; e_nb = 0; goto e_done; }
                 if (e_dir > 0) {
-                    u64 room = (u64)(n - 1 - e_cur) / e_s;
+                    u64 room = (u64)(n - 1 - e_cur) >> e_sh;
                     e_cnt = room < 8 ? (int)room : 8;
                     req_block(e_cur + (idx_t)e_s, (long long)e_s, e_cnt, e_L);
                 } else {
-                    u64 room = (u64)e_cur / e_s;
+                    u64 room = (u64)e_cur >> e_sh;
                     e_cnt = room < 8 ? (int)room : 8;
                     req_block(e_cur - (idx_t)e_s, -(long long)e_s, e_cnt, e_L);
                 }
@@ -492,12 +493,12 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
                     if (c == 8) {
                         u64 gone = e_dir > 0 ? (u64)(e_cur - e_from) : (u64)(e_from - e_cur);
                         if (gone >= e_limit) { e_edge = e_cur; e_nb = e_L; goto e_done; }
-                        if (e_up && e_s < (1ull << 40)) e_s *= 8;
+                        if (e_up && e_s < (1ull << 40)) { e_s *= 8; e_sh += 3; }
                         goto e_probe;
                     }
                     if (e_s == 1) { e_nb = c < e_cnt ? RL(c) : 0; e_edge = e_cur; goto e_done; }
                     e_up = false;
-                    e_s /= 8;
+                    e_s >>= 3; e_sh -= 3;
                     goto e_probe;
                 }
             e_done:
@@ -515,21 +516,19 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
         u64 buf[8];
         const int req = mreq;
         if (req == M_BLOCK) {
+            idx_t idx = m_base;
+            const idx_t step = (idx_t)m_stride;
+            u64 h = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
-                    idx_t idx = m_base + (idx_t)((long long)j * m_stride);
                     buf[j] = has_keys ? __ldg(ix.keys + idx) : 0;
                     pp[j] = __ldg(ix.pos_lo + idx);
+                    if (WIDE) h |= (u64)__ldg(ix.pos_hi + idx) << (8 * j);
                 }
+                idx += step;
             }
-            if (WIDE) {
-                u64 h = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (j < m_count) h |= (u64)__ldg(ix.pos_hi + (m_base + (idx_t)((long long)j * m_stride))) << (8 * j);
-                pphi = h;
-            }
+            if (WIDE) pphi = h;
         } else if (req == M_PAC) {
             u32 v = pp[0];
 #pragma unroll
@@ -572,9 +571,15 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
-                    u64 p = (u64)pp[j] | (WIDE ? ((pphi >> (8 * j)) & 0xff) << 32 : 0);
-                    u64 ref_len = ix.sa_num - p;
-                    int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
+                    int cap;
+                    if (WIDE) {
+                        u64 p = (u64)pp[j] | (((pphi >> (8 * j)) & 0xff) << 32);
+                        u64 ref_len = ix.sa_num - p;
+                        cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
+                    } else {
+                        u32 ref_len = (u32)n - pp[j];
+                        cap = (int)min(ref_len, (u32)m_cap);
+                    }
                     int l;
                     if (!has_keys) { und |= 1u << j; l = 0; }
                     else {
@@ -602,23 +607,23 @@ __global__ void __launch_bounds__(TPR_THREADS, 2) k_flat(IndexView ix, Args A)
             const int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
             const int sh = (int)(p & 31) * 2;
             int res = -1; bool less = false;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (res < 0) {
-                    int k = pac_k0 + j;
-                    if (32 * k >= cap) res = cap;
-                    else {
-                        u64 rr = sh ? (buf[j] >> sh) | (buf[j + 1] << (64 - sh)) : buf[j];
-                        u64 qq = k == 0 ? q0 : qword(k);
-                        u64 x = rr ^ qq;
-                        if (x) {
-                            int b = (__ffsll((long long)x) - 1) >> 1;
-                            int l = 32 * k + b;
-                            if (l >= cap) res = cap;
-                            else { res = l; less = ((rr >> (2 * b)) & 3) < ((qq >> (2 * b)) & 3); }
-                        }
+            u64 w0 = buf[0], w1 = buf[1], w2 = buf[2], w3 = buf[3], w4 = buf[4];
+#pragma unroll 1
+            for (int j = 0; j < 4 && res < 0; j++) {
+                int k = pac_k0 + j;
+                if (32 * k >= cap) res = cap;
+                else {
+                    u64 rr = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+                    u64 qq = k == 0 ? q0 : qword(k);
+                    u64 x = rr ^ qq;
+                    if (x) {
+                        int b = (__ffsll((long long)x) - 1) >> 1;
+                        int l = 32 * k + b;
+                        if (l >= cap) res = cap;
+                        else { res = l; less = ((rr >> (2 * b)) & 3) < ((qq >> (2 * b)) & 3); }
                     }
                 }
+                w0 = w1; w1 = w2; w2 = w3; w3 = w4;
             }
             if (res < 0) pac_k0 += 4;                      // four more words of the same entry
             else {

@@ -896,8 +896,11 @@ static int launch_tpr(meme_index_t *ix, const Args &A)
 {
     if (A.n_tasks <= 0) return MEME_OK;
     if (tpr_variant() == 1) return launch_kernel(ix, A, k_tpr<KIND>);
-    if (ix->v.pos_wide) return launch_kernel(ix, A, k_flat<KIND, true>);
-    return launch_kernel(ix, A, k_flat<KIND, false>);
+    static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 2;
+    if (ix->v.pos_wide) return launch_kernel(ix, A, k_flat<KIND, true, 2>);
+    if (minb == 3) return launch_kernel(ix, A, k_flat<KIND, false, 3>);
+    if (minb == 4) return launch_kernel(ix, A, k_flat<KIND, false, 4>);
+    return launch_kernel(ix, A, k_flat<KIND, false, 2>);
 }
 
 int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
