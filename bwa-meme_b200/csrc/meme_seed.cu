@@ -846,7 +846,8 @@ extern "C" int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
     int rc;
     ix->last_opt = *opt;
     if (n == 0) { ix->ran = 1; return MEME_OK; }
-    {   // MEME_SEED_IMPL=coop selects the cooperative (group-per-read) kernel; default is thread-per-task
+    {   // MEME_SEED_IMPL=coop selects the cooperative (group-per-read) kernel; default is the thread-per-task
+        // flat state machine (meme_seed_flat.cuh); "tpr" is its coroutine formulation
         static int impl = -1;
         if (impl < 0) { const char *e = getenv("MEME_SEED_IMPL"); impl = (e && !strcmp(e, "coop")) ? 0 : 1; }
         if (impl == 1) return tpr_seed_run(ix, opt);

@@ -1,0 +1,170 @@
+// meme_glue.cpp -- see meme_glue.h.  Compiled together with the (patched) reference sources; binds
+// libmeme_b200.so with dlopen so that the aligner has no link-time CUDA dependency.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <chrono>
+#include "meme_glue.h"
+#include "../../include/meme_b200.h"
+
+namespace {
+
+struct Api {
+    void *so = nullptr;
+    decltype(&meme_index_load) index_load = nullptr;
+    decltype(&meme_seed_batch) seed_batch = nullptr;
+    decltype(&meme_bsw_create) bsw_create = nullptr;
+    decltype(&meme_bsw_batch) bsw_batch = nullptr;
+    decltype(&meme_last_error) last_error = nullptr;
+    bool ok = false;
+};
+
+Api &api()
+{
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *path = getenv("MEME_B200_LIB");
+        a.so = dlopen(path ? path : "libmeme_b200.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.so) { fprintf(stderr, "[meme_b200] cannot load the CUDA library: %s\n", dlerror()); exit(EXIT_FAILURE); }
+        a.index_load = (decltype(a.index_load))dlsym(a.so, "meme_index_load");
+        a.seed_batch = (decltype(a.seed_batch))dlsym(a.so, "meme_seed_batch");
+        a.bsw_create = (decltype(a.bsw_create))dlsym(a.so, "meme_bsw_create");
+        a.bsw_batch = (decltype(a.bsw_batch))dlsym(a.so, "meme_bsw_batch");
+        a.last_error = (decltype(a.last_error))dlsym(a.so, "meme_last_error");
+        a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error;
+        if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
+    });
+    return a;
+}
+
+bool env_on(const char *name)
+{
+    const char *e = getenv(name);
+    return e && e[0] == '1';
+}
+
+std::string g_prefix;
+meme_index_t *g_index = nullptr;
+// results of the chunk being processed (valid until the next meme_glue_seed_chunk)
+const bseq1_t *g_base = nullptr;
+int g_n = 0;
+meme_seed_result_t g_res;
+bool g_have = false;
+double g_seed_s = 0;
+long g_seed_reads = 0;
+
+[[noreturn]] void die(const char *what, int rc)
+{
+    fprintf(stderr, "[meme_b200] %s failed (%d): %s\n", what, rc, api().last_error());
+    exit(EXIT_FAILURE);      // the reference's own error protocol
+}
+
+}  // namespace
+
+void meme_glue_set_prefix(const char *idx_prefix) { g_prefix = idx_prefix ? idx_prefix : ""; }
+
+// One GPU seeding call for the whole chunk (the reference seeds 512 reads at a time per thread).
+void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_learned)
+{
+    g_have = false;
+    if (!use_learned || !env_on("MEME_B200") || n <= 0) return;
+    Api &a = api();
+    if (!g_index) {
+        int mode = getenv("MEME_B200_MODE") ? atoi(getenv("MEME_B200_MODE")) : MODE;
+        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+        int rc = a.index_load(g_prefix.c_str(), mode, dev, &g_index);
+        if (rc) die("meme_index_load", rc);
+        fprintf(stderr, "[meme_b200] index %s resident on GPU %d (mode %d)\n", g_prefix.c_str(), dev, mode);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    // base codes: nst_nt4_table of the ASCII read; worker_bwt converts seqs[i].seq in place later
+    // (src/bwamem.cpp:L1277-1280) and later stages rely on that, so the reads are not touched here
+    static std::vector<uint8_t> codes;
+    static std::vector<int64_t> off;
+    off.resize((size_t)n + 1);
+    size_t tot = 0;
+    for (int i = 0; i < n; i++) { off[i] = (int64_t)tot; tot += (size_t)seqs[i].l_seq; }
+    off[n] = (int64_t)tot;
+    codes.resize(tot + 1);
+    for (int i = 0; i < n; i++) {
+        const unsigned char *s = (const unsigned char *)seqs[i].seq;
+        uint8_t *d = codes.data() + off[i];
+        for (int k = 0; k < seqs[i].l_seq; k++) d[k] = s[k] < 4 ? s[k] : nst_nt4_table[s[k]];
+    }
+    meme_seed_opt_t so;
+    so.min_seed_len = opt->min_seed_len;
+    so.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+    so.split_width = opt->split_width;
+    so.max_mem_intv = (int32_t)opt->max_mem_intv;
+    so.rounds = 3;
+    so.max_occ = 0;                 // mem_chain_Learned computes l_rep from hitcount and indexes hits with a stride
+    int rc = a.seed_batch(g_index, codes.data(), off.data(), n, &so, &g_res);
+    if (rc) die("meme_seed_batch", rc);
+    g_base = seqs; g_n = n; g_have = true;
+    g_seed_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_seed_reads += n;
+    fprintf(stderr, "[meme_b200] seeded %d reads on the GPU: %ld SMEMs, %ld hits (cumulative %.3f s for %ld reads)\n", n,
+            (long)g_res.n_smems, (long)g_res.n_hits, g_seed_s, g_seed_reads);
+}
+
+// Fill the per-thread kvecs exactly as the reference's seeding + ks_introsort would leave them.
+bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits)
+{
+    if (!g_have) return false;
+    long idx = (long)(s - g_base);
+    if (idx < 0 || idx >= g_n) return false;
+    int64_t s0 = g_res.smem_off[idx], s1 = g_res.smem_off[idx + 1];
+    int64_t h0 = g_res.hit_off[idx], h1 = g_res.hit_off[idx + 1];
+    size_t ns = (size_t)(s1 - s0), nh = (size_t)(h1 - h0);
+    if (smems->m < ns) kv_resize(mem_tl, *smems, ns + 16);
+    if (hits->m < nh) kv_resize(uint64_t, *hits, nh + 16);
+    static_assert(sizeof(mem_tl) == sizeof(meme_smem_t), "mem_tl layout");
+    memcpy(smems->a, g_res.smems + s0, ns * sizeof(mem_tl));
+    memcpy(hits->a, g_res.hits + h0, nh * sizeof(uint64_t));
+    smems->n = ns;
+    hits->n = nh;
+    return true;
+}
+
+// Seed extension through the GPU: same contract as getScores8/16 / scalarBandedSWAWrapper (fills the six
+// result fields of every pair in place).  One handle per host thread (kt_for worker).
+bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
+                   int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b)
+{
+    if (!env_on("MEME_B200_BSW")) return false;
+    if (n_pairs <= 0) return true;
+    Api &A = api();
+    static thread_local meme_bsw_t *h = nullptr;
+    static thread_local std::vector<meme_seqpair_t> tmp;
+    if (!h) {
+        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+        int rc = A.bsw_create(dev, &h);
+        if (rc) die("meme_bsw_create", rc);
+    }
+    static_assert(sizeof(SeqPair) == sizeof(meme_seqpair_t), "SeqPair layout");
+    // the pairs address slices of per-thread sequence buffers: rebase to the touched range
+    int64_t r0 = INT64_MAX, r1 = 0, q0 = INT64_MAX, q1 = 0;
+    for (int i = 0; i < n_pairs; i++) {
+        const SeqPair &p = pairs[i];
+        if (p.idr < r0) r0 = p.idr;
+        if ((int64_t)p.idr + p.len1 > r1) r1 = (int64_t)p.idr + p.len1;
+        if (p.idq < q0) q0 = p.idq;
+        if ((int64_t)p.idq + p.len2 > q1) q1 = (int64_t)p.idq + p.len2;
+    }
+    tmp.resize((size_t)n_pairs);
+    memcpy(tmp.data(), pairs, (size_t)n_pairs * sizeof(SeqPair));
+    for (int i = 0; i < n_pairs; i++) { tmp[i].idr -= (int32_t)r0; tmp[i].idq -= (int32_t)q0; }
+    meme_bsw_opt_t o = {o_del, e_del, o_ins, e_ins, zdrop, end_bonus, a, b};
+    int rc = A.bsw_batch(h, tmp.data(), n_pairs, seq_buf_ref + r0, r1 - r0, seq_buf_qer + q0, q1 - q0, w, &o);
+    if (rc) die("meme_bsw_batch", rc);
+    for (int i = 0; i < n_pairs; i++) {
+        pairs[i].score = tmp[i].score; pairs[i].tle = tmp[i].tle; pairs[i].gtle = tmp[i].gtle;
+        pairs[i].qle = tmp[i].qle; pairs[i].gscore = tmp[i].gscore; pairs[i].max_off = tmp[i].max_off;
+    }
+    return true;
+}

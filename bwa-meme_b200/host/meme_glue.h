@@ -1,0 +1,24 @@
+// meme_glue.h -- host-side C++ mirror of the reference's hot-path interface over the C ABI.
+//
+// These are the four calls a maintainer of kaist-ina/BWA-MEME adds to route `bwa-meme mem -7` through
+// libmeme_b200.so (INTEGRATION.md shows the diff; integration/apply_patch.py applies it to a scratch copy):
+//
+//   meme_glue_set_prefix   in memoryAllocLearned()            src/fastmap.cpp:L351   (index prefix)
+//   meme_glue_seed_chunk   in mem_process_seqs(), before kt_for(worker_bwt)  src/bwamem.cpp:L1941
+//   meme_glue_take         in mem_kernel1_core_Learned(), around the seeding calls  src/bwamem.cpp:L1366-1397
+//   meme_glue_bsw          first line of BandedPairWiseSW::getScores8/16 and scalarBandedSWAWrapper
+//                                                             src/bandedSWA.cpp:L242, L412, L1117, L1970, L2664, L3469, L4198
+//
+// Everything is off unless the environment says MEME_B200=1 (seeding) / MEME_B200_BSW=1 (extension), so the
+// patched binary is byte-for-byte the reference's behaviour by default.
+#pragma once
+#include <stdint.h>
+#include "bwamem.h"
+#include "bandedSWA.h"
+#include "LearnedIndex_seeding.h"
+
+void meme_glue_set_prefix(const char *idx_prefix);
+void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_learned);
+bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits);
+bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
+                   int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b);

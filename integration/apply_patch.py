@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Write patched copies of three reference files (never touching the reference tree).
+
+usage: apply_patch.py <reference root> <out dir>
+
+The patch is the one shown in INTEGRATION.md: one include + four call sites of bwa-meme_b200/host/meme_glue.h.
+It is applied by anchor text (not by line number) and fails loudly if an anchor is missing or ambiguous.
+"""
+import os
+import re
+import sys
+
+HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, "
+            "w_match, -w_mismatch)) return;\n")
+
+
+def patch_bwamem(src: str) -> str:
+    out, n_seed, n_close, n_chunk, n_inc = [], 0, 0, 0, 0
+    for line in src.splitlines(keepends=True):
+        if line.startswith('#include "bwamem.h"') and not n_inc:
+            out.append(line)
+            out.append('#include "meme_glue.h"\n')
+            n_inc += 1
+            continue
+        if "Learned_getSMEMsAllPosOneThread(&iaux, &raux, smems, hits, hasN, split_len,opt->split_width);" in line and not line.lstrip().startswith("//"):
+            out.append("        if (!meme_glue_take(&seq_[l], smems, hits)) {   // meme_b200: GPU seeds for this read, if any\n")
+            out.append(line)
+            n_seed += 1
+            continue
+        if "ks_introsort(mem_smem_sort_lt_learned, smems->n, smems->a);" in line:
+            out.append("        }   // meme_b200\n")
+            out.append(line)
+            n_close += 1
+            continue
+        if re.match(r"\s*kt_for\(worker_bwt, &w, n_\);", line):
+            out.append("    meme_glue_seed_chunk(opt, seqs, n_, w.useLearned);   // meme_b200: whole-chunk GPU seeding\n")
+            out.append(line)
+            n_chunk += 1
+            continue
+        out.append(line)
+    assert (n_inc, n_seed, n_close, n_chunk) == (1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk)
+    return "".join(out)
+
+
+def patch_banded(src: str) -> str:
+    lines = src.splitlines(keepends=True)
+    out, i, n = [], 0, 0
+    while i < len(lines):
+        line = lines[i]
+        m = re.match(r"void BandedPairWiseSW::(getScores8|getScores16|scalarBandedSWAWrapper)\(SeqPair \*(\w+),", line)
+        out.append(line)
+        i += 1
+        if m:
+            arr = m.group(2)
+            # copy the rest of the signature up to and including the line that opens the body
+            while True:
+                l2 = lines[i]
+                out.append(l2)
+                i += 1
+                if "{" in l2:
+                    break
+            out.append(HOOK_BSW.format(arr=arr))
+            n += 1
+    assert n == 7, n
+    return '#include "meme_glue.h"\n' + "".join(out)
+
+
+def patch_fastmap(src: str) -> str:
+    out, n, armed = [], 0, False
+    for line in src.splitlines(keepends=True):
+        out.append(line)
+        if line.startswith("void memoryAllocLearned("):
+            armed = True
+        if armed and line.strip() == "{":
+            out.append("    meme_glue_set_prefix(idx_prefix);   // meme_b200\n")
+            armed = False
+            n += 1
+    assert n == 1, n
+    return '#include "meme_glue.h"\n' + "".join(out)
+
+
+def main():
+    ref, out = sys.argv[1], sys.argv[2]
+    os.makedirs(out, exist_ok=True)
+    for name, fn in (("bwamem.cpp", patch_bwamem), ("bandedSWA.cpp", patch_banded), ("fastmap.cpp", patch_fastmap)):
+        src = open(os.path.join(ref, "src", name), newline="", encoding="latin-1").read()
+        open(os.path.join(out, name), "w", newline="", encoding="latin-1").write(fn(src))
+    print("patched bwamem.cpp, bandedSWA.cpp, fastmap.cpp ->", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@ The fixtures are small and committed; the GPU box only reads them.
   smem_len*_s{1,2}.json per-read SMEM counts with steps=1 / steps=2 (rounds 1 and 1+2 only)
   bsw_*.npy             {score,tle,gtle,qle,gscore,max_off} of BandedPairWiseSW::scalarBandedSWAWrapper
   mem7.sam              `bwa-meme mem -7` SAM (minus @PG) for the len150 reads  (end-to-end reference)
+  pe_reads.npy, mem7_pe.sam   250 read pairs (codes) and the reference's paired-end SAM for them
 """
 import hashlib
 import json
@@ -72,6 +73,28 @@ def main():
             sam = subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "mem", "-7", "-t", "1", fa, fq],
                                  capture_output=True, text=True, check=True).stdout
             open(os.path.join(HERE, "mem7.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
+    # paired-end: 250 pairs, insert ~ N(400, 50), FR orientation  (exercises mem_pestat + mate rescue downstream)
+    rng = np.random.default_rng(77)
+    n_pairs, rl = 250, 150
+    r1, r2 = [], []
+    for _ in range(n_pairs):
+        ins = int(np.clip(rng.normal(400, 50), 2 * rl // 2 + 20, 700))
+        st = int(rng.integers(0, GENOME_LEN - ins))
+        frag = g[st:st + ins].copy()
+        a, b = frag[:rl].copy(), synth.revcomp(frag[-rl:])
+        for rd in (a, b):
+            m = rng.random(rl) < 0.01
+            rd[m] = (rd[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+        if rng.random() < 0.5:
+            a, b = b, a
+        r1.append(a); r2.append(b)
+    offs = np.arange(n_pairs + 1, dtype=np.int64) * rl
+    synth.write_fastq(os.path.join(work, "pe_1.fq"), np.concatenate(r1), offs, prefix="p")
+    synth.write_fastq(os.path.join(work, "pe_2.fq"), np.concatenate(r2), offs, prefix="p")
+    np.save(os.path.join(HERE, "pe_reads.npy"), np.stack([np.concatenate(r1), np.concatenate(r2)]))
+    sam = subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "mem", "-7", "-t", "1", fa, os.path.join(work, "pe_1.fq"),
+                          os.path.join(work, "pe_2.fq")], capture_output=True, text=True, check=True).stdout
+    open(os.path.join(HERE, "mem7_pe.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
     shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
     for seed, n, mq, mx, h0m in BSW_SETS:
         pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)

@@ -1,0 +1,62 @@
+"""End-to-end drop-in check: the reference aligner with the 13-line integration patch, seeding (and seed
+extension) routed through libmeme_b200.so, must print the same SAM as the unmodified reference CPU run
+(golden files written by tests/golden/make_golden.py).  Needs oracle/_ref (built where the reference is
+mounted; travels to the GPU box)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _binary():
+    flags = open("/proc/cpuinfo").read()
+    for isa in (["avx512bw"] if " avx512bw" in flags else []) + ["avx2"]:
+        p = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme-b200_mode3.{isa}")
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def _run(exe, args, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    env["MEME_B200_LIB"] = os.path.join(ROOT, "bwa-meme_b200", "libmeme_b200.so")
+    p = subprocess.run([exe, "mem", "-7", "-t", "4", *args], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    sam = "".join(l + "\n" for l in p.stdout.splitlines() if not l.startswith("@PG"))
+    return sam, p.stderr
+
+
+@pytest.mark.parametrize("hooks", [{"MEME_B200": "1"}, {"MEME_B200": "1", "MEME_B200_BSW": "1"}])
+def test_single_end_sam_identical(pkg, golden_index, golden_reads, tmp_path, hooks):
+    from bwa_meme_b200 import synth
+    exe = _binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/bwa-meme-b200_* not built (needs the reference sources)")
+    codes, offs = golden_reads[150]
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, codes, offs)
+    sam, err = _run(exe, [golden_index, fq], hooks)
+    assert "seeded 300 reads on the GPU" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7.sam")).read()
+
+
+def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
+    from bwa_meme_b200 import synth
+    exe = _binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/bwa-meme-b200_* not built (needs the reference sources)")
+    pe = np.load(os.path.join(GOLDEN, "pe_reads.npy"))
+    n = pe.shape[1] // 150
+    offs = np.arange(n + 1, dtype=np.int64) * 150
+    f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+    synth.write_fastq(f1, pe[0], offs, prefix="p")
+    synth.write_fastq(f2, pe[1], offs, prefix="p")
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1"})
+    assert "on the GPU" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
