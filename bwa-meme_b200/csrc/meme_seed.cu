@@ -926,6 +926,7 @@ extern "C" int meme_seed_counters(meme_index_t *ix, uint64_t counters[8])
     counters[0] = ix->h_ctrl[CT_SEARCH]; counters[1] = ix->h_ctrl[CT_BLOCK]; counters[2] = ix->h_ctrl[CT_KARY];
     counters[3] = ix->h_ctrl[CT_EXT]; counters[4] = ix->h_ctrl[CT_OVF]; counters[5] = ix->launches;
     counters[6] = ix->h_ctrl[CT_REDO]; counters[7] = (u64)seed_group();
+    if (ix->h_ctrl[41]) { counters[4] = ix->h_ctrl[40]; counters[7] = ix->h_ctrl[41]; }   // flat/tpr: PAC rounds, total round trips
     return MEME_OK;
 }
 

@@ -1012,6 +1012,7 @@ int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
     ix->h_ctrl[11] = ix->h_ctrl[C_EXT];
     ix->h_ctrl[2] = 0;                 // no per-read SMEM limit in this path
     ix->h_ctrl[4] = n_t2;              // reseed tasks (reported in the "redo" counter slot)
+    ix->h_ctrl[40] = ix->h_ctrl[C_PAC]; ix->h_ctrl[41] = ix->h_ctrl[C_ITER];
     ix->ran = 1;
     return MEME_OK;
 }
