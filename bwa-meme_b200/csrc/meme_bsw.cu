@@ -20,6 +20,7 @@
 #include "meme_common.cuh"
 
 #define BSW_WARPS 4
+#define BSW_NCLASS 10
 #define FULL 0xffffffffu
 #define NEG_BIG (-(1 << 28))
 
@@ -31,6 +32,8 @@ struct meme_bsw {
     uint8_t *d_qer; size_t cap_qer;
     int32_t *d_scratch; size_t cap_scratch;     // H/E rows of the generic (very long query) path
     int64_t *d_scratch_off; size_t cap_scratch_off;
+    u32 *d_order; size_t cap_order;
+    int64_t cls_off[BSW_NCLASS + 1];
     u64 *d_ctrl; u64 *h_ctrl;
     int64_t n_pairs, n_ref, n_qer;
     u64 launches;
@@ -276,9 +279,12 @@ __device__ void bsw_thread(const BswConst &P, const uint8_t *__restrict__ query,
 
 #define BSW_MAX_REG_QLEN (32 * 12 - 1)
 
+// One kernel instantiation per column count C: registers (and therefore resident warps) follow the class
+// instead of the worst case.  `order` lists the pairs of this class (built at upload, counting sort by C).
+template <int C>
 __global__ void __launch_bounds__(BSW_WARPS * 32)
-k_bsw(BswConst P, meme_seqpair_t *__restrict__ pairs, int64_t n_pairs, const uint8_t *__restrict__ ref,
-      const uint8_t *__restrict__ qer, u64 *__restrict__ ctrl)
+k_bsw(BswConst P, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order, int64_t n_work,
+      const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer, u64 *__restrict__ ctrl)
 {
     const int lane = threadIdx.x & 31;
     u64 cells = 0;
@@ -286,25 +292,23 @@ k_bsw(BswConst P, meme_seqpair_t *__restrict__ pairs, int64_t n_pairs, const uin
         u64 r = 0;
         if (lane == 0) r = atomicAdd((unsigned long long *)&ctrl[0], 1ull);
         r = __shfl_sync(FULL, r, 0);
-        if (r >= (u64)n_pairs) break;
-        meme_seqpair_t *p = pairs + r;
-        const int qlen = p->len2, tlen = p->len1, h0 = p->h0;
-        const uint8_t *q = qer + p->idq, *t = ref + p->idr;
-        if (qlen > BSW_MAX_REG_QLEN) continue;       // handled by k_bsw_long
-        const int C = (qlen + 1 + 31) / 32;
-        switch (C) {
-        case 0: case 1: bsw_warp<1>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 2: bsw_warp<2>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 3: bsw_warp<3>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 4: bsw_warp<4>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 5: bsw_warp<5>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 6: bsw_warp<6>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 7: case 8: bsw_warp<8>(P, q, qlen, t, tlen, h0, p, cells); break;
-        case 9: case 10: bsw_warp<10>(P, q, qlen, t, tlen, h0, p, cells); break;
-        default: bsw_warp<12>(P, q, qlen, t, tlen, h0, p, cells); break;
-        }
+        if (r >= (u64)n_work) break;
+        meme_seqpair_t *p = pairs + order[r];
+        bsw_warp<C>(P, qer + p->idq, p->len2, ref + p->idr, p->len1, p->h0, p, cells);
     }
     if (lane == 0 && cells) atomicAdd((unsigned long long *)&ctrl[1], (unsigned long long)cells);
+}
+
+// classes: C = 1,2,3,4,5,6,8,10,12 and "long" (generic kernel)
+static inline int bsw_class_of(int qlen)
+{
+    if (qlen > BSW_MAX_REG_QLEN) return 9;
+    int C = (qlen + 1 + 31) / 32;
+    if (C <= 1) return 0;
+    if (C <= 6) return C - 1;
+    if (C <= 8) return 6;
+    if (C <= 10) return 7;
+    return 8;
 }
 
 __global__ void k_bsw_long_offsets(const meme_seqpair_t *__restrict__ pairs, int64_t n_pairs, int64_t *__restrict__ off)
@@ -320,7 +324,7 @@ __global__ void k_bsw_long(BswConst P, meme_seqpair_t *__restrict__ pairs, int64
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     meme_seqpair_t *p = pairs + i;
-    if (p->len2 <= BSW_MAX_REG_QLEN) return;
+    if (p->len2 <= BSW_MAX_REG_QLEN) return;      // (pairs of the register classes are done by k_bsw<C>)
     u64 cells = 0;
     int32_t *H = scratch + off[i], *E = H + p->len2 + 2;
     bsw_thread(P, qer + p->idq, p->len2, ref + p->idr, p->len1, p->h0, H, E, p, cells);
@@ -355,7 +359,7 @@ extern "C" void meme_bsw_free(meme_bsw_t *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
-    void *dev[] = {b->d_pairs, b->d_ref, b->d_qer, b->d_scratch, b->d_scratch_off, b->d_ctrl};
+    void *dev[] = {b->d_pairs, b->d_ref, b->d_qer, b->d_scratch, b->d_scratch_off, b->d_ctrl, b->d_order};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_ctrl) cudaFreeHost(b->h_ctrl);
     cudaStreamDestroy(b->own_stream);
@@ -397,9 +401,24 @@ extern "C" int meme_bsw_upload(meme_bsw_t *b, const meme_seqpair_t *pairs, int64
         CUDA_TRY(cudaMemcpyAsync(b->d_qer, qer, (size_t)n_qer, cudaMemcpyHostToDevice, st));
     }
     b->n_pairs = n_pairs; b->n_ref = n_ref; b->n_qer = n_qer;
-    // does any pair need the long-query path?
-    b->h_ctrl[4] = 0;
-    for (int64_t i = 0; i < n_pairs; i++) if (pairs[i].len2 > BSW_MAX_REG_QLEN) { b->h_ctrl[4] = 1; break; }
+    // counting sort of the pair indices by register class (columns per lane); within a class longer
+    // references first, so that the dynamic scheduler does not end on a long pair
+    {
+        int64_t cnt[BSW_NCLASS] = {0};
+        for (int64_t i = 0; i < n_pairs; i++) cnt[bsw_class_of(pairs[i].len2)]++;
+        b->cls_off[0] = 0;
+        for (int c = 0; c < BSW_NCLASS; c++) b->cls_off[c + 1] = b->cls_off[c] + cnt[c];
+        std::vector<u32> order((size_t)n_pairs + 1);
+        int64_t cur[BSW_NCLASS];
+        for (int c = 0; c < BSW_NCLASS; c++) cur[c] = b->cls_off[c];
+        for (int64_t i = 0; i < n_pairs; i++) order[(size_t)cur[bsw_class_of(pairs[i].len2)]++] = (u32)i;
+        if ((rc = meme_grow_device((void **)&b->d_order, &b->cap_order, (size_t)n_pairs + 1, 4, st))) return rc;
+        if (n_pairs) {
+            CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));       // `order` is a temporary
+        }
+    }
+    b->h_ctrl[4] = b->cls_off[BSW_NCLASS] > b->cls_off[BSW_NCLASS - 1];   // any pair for the long-query path?
     return MEME_OK;
 }
 
@@ -413,15 +432,27 @@ extern "C" int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt)
     CUDA_TRY(cudaMemsetAsync(b->d_ctrl, 0, 8 * 8, st));
     if (n == 0) return MEME_OK;
     BswConst P = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->end_bonus, opt->a, opt->b, w};
-    int sms = 0, per_sm = 0;
+    int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bsw, BSW_WARPS * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = (int64_t)sms * per_sm, need = (n + BSW_WARPS - 1) / BSW_WARPS;
-    if (grid > need) grid = need;
-    k_bsw<<<(unsigned)grid, BSW_WARPS * 32, 0, st>>>(P, b->d_pairs, n, b->d_ref, b->d_qer, b->d_ctrl);
-    CUDA_TRY(cudaGetLastError());
-    b->launches++;
+#define LAUNCH_CLASS(ci, CC)                                                                                          \
+    do {                                                                                                              \
+        int64_t cn = b->cls_off[(ci) + 1] - b->cls_off[ci];                                                           \
+        if (cn > 0) {                                                                                                 \
+            int per_sm = 0;                                                                                           \
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bsw<CC>, BSW_WARPS * 32, 0));           \
+            if (per_sm < 1) per_sm = 1;                                                                               \
+            int64_t grid = (int64_t)sms * per_sm, need = (cn + BSW_WARPS - 1) / BSW_WARPS;                            \
+            if (grid > need) grid = need;                                                                             \
+            CUDA_TRY(cudaMemsetAsync(b->d_ctrl, 0, 8, st));                                                           \
+            k_bsw<CC><<<(unsigned)grid, BSW_WARPS * 32, 0, st>>>(P, b->d_pairs, b->d_order + b->cls_off[ci], cn, b->d_ref, \
+                                                                b->d_qer, b->d_ctrl);                                 \
+            CUDA_TRY(cudaGetLastError());                                                                             \
+            b->launches++;                                                                                            \
+        }                                                                                                             \
+    } while (0)
+    LAUNCH_CLASS(0, 1); LAUNCH_CLASS(1, 2); LAUNCH_CLASS(2, 3); LAUNCH_CLASS(3, 4); LAUNCH_CLASS(4, 5);
+    LAUNCH_CLASS(5, 6); LAUNCH_CLASS(6, 8); LAUNCH_CLASS(7, 10); LAUNCH_CLASS(8, 12);
+#undef LAUNCH_CLASS
     if (b->h_ctrl[4]) {
         int rc;
         if ((rc = meme_grow_device((void **)&b->d_scratch_off, &b->cap_scratch_off, (size_t)n + 1, 8, st))) return rc;
