@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
 
             // ------------------------------------------------ T1: zig-zag (reference L913-972, L1691-1894)
             d1_loop:
+                if (KIND != 1) { state = P_TASK; break; }
                 while (pivot < L && is_n(pivot)) pivot = (L - pivot < min_seed_len) ? L : pivot + 1;
                 if (pivot >= L) {
                     if (A.rd_full) { A.rd_full[rid] = full_match ? 1 : 0; A.rd_maxref[rid] = max_refpos; }
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 s_stepwise = false; d_ret = P_D1_F;
                 goto s_begin;
             case P_D1_F:
+                if (KIND != 1) { state = P_TASK; break; }
                 if (ix.mode == 3 && lev == L) {              // whole read matched (L1870-1875)
                     mreq = M_LD; m_ldk = LD_POS; m_base = lo;
                     state = P_D1_M;
@@ -202,10 +204,12 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 pivot += lev;
                 goto d1_loop;
             case P_D1_M:
+                if (KIND != 1) { state = P_TASK; break; }
                 full_match = true; max_refpos = (idx_t)ld_val;
                 pivot += lev;
                 goto d1_loop;
             d1_zz:
+                if (KIND != 1) { state = P_TASK; break; }
                 if (sp >= L) { pivot = L; goto d1_loop; }
                 if (is_n(sp)) {
                     if (L - sp < min_seed_len) { pivot = L; sp = L; }
@@ -215,39 +219,46 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D1_L;
                 goto auto_start;
             case P_D1_L:
+                if (KIND != 1) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
                 if (L - pivot < min_seed_len) { pivot = L; goto d1_loop; }
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D1_R;
                 goto auto_start;
             case P_D1_R:
+                if (KIND != 1) { state = P_TASK; break; }
                 sp = pivot + lev;
                 pivot = sp;
                 goto d1_zz;
 
             // ------------------------------------------------ T2: reseeding (reference L1897-2126)
             case P_D2_C:
+                if (KIND != 2) { state = P_TASK; break; }
                 cache_refpos = (idx_t)ld_val;
             d2_first:
                 as_pv = pivot; as_right = true; as_emit = false; as_ret = P_D2_F;
                 goto auto_start;
             case P_D2_F:
+                if (KIND != 2) { state = P_TASK; break; }
                 next = pivot + lev; sp = pivot;
             d2_loop:
                 if (sp >= next) { state = P_TASK; break; }
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D2_L;
                 goto auto_start;
             case P_D2_L:
+                if (KIND != 2) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
                 if (next - pivot < min_seed_len) { state = P_TASK; break; }
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D2_R;
                 goto auto_start;
             case P_D2_R:
+                if (KIND != 2) { state = P_TASK; break; }
                 sp = pivot + lev;
                 pivot = sp;
                 goto d2_loop;
 
             // ------------------------------------------------ T3: third round (reference L974-1466)
             d3_loop:
+                if (KIND != 3) { state = P_TASK; break; }
                 for (;;) {
                     if (pivot >= L - min_seed_len + 1) break;
                     if (is_n(pivot)) { pivot++; continue; }
@@ -262,9 +273,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 else { s_mode = ST_RMI; s_isa = false; }
                 goto s_begin;
             case P_D3_S:
+                if (KIND != 3) { state = P_TASK; break; }
                 if (lev < min_seed_len) { pivot += min_seed_len; goto d3_loop; }
                 r3_last_lo = lo; r3_last_cnt = 0; it = 0;
             d3_levels:
+                if (KIND != 3) { state = P_TASK; break; }
                 {
                     u64 cnt = (u64)(hi - lo) + 1;
                     if (cnt >= (u64)min_intv) {                                  // L1243-1251
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                     lv_ret = 0;
                     goto lv_begin;
                 }
-                if (s_emit && lev >= s_msl) push(s_pivot, s_pivot + lev, lo, (u64)(hi - lo) + 1);
+                if (KIND != 3 && s_emit && lev >= s_msl) push(s_pivot, s_pivot + lev, lo, (u64)(hi - lo) + 1);
             search_done:
                 switch (d_ret) {
                 case P_D1_F: state = P_D1_F; break;
@@ -583,11 +596,17 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                     int l;
                     if (!has_keys) { und |= 1u << j; l = 0; }
                     else {
-                        u64 x = buf[j] ^ q0;
-                        if (x) {
-                            int b = (__ffsll((long long)x) - 1) >> 1;
+                        const u32 xl = (u32)buf[j] ^ (u32)q0, xh = (u32)(buf[j] >> 32) ^ (u32)(q0 >> 32);
+                        if (xl | xh) {
+                            // first differing base, in 32-bit halves (16 bases each)
+                            const bool hi_half = xl == 0;
+                            const u32 xx = hi_half ? xh : xl;
+                            const u32 rr = hi_half ? (u32)(buf[j] >> 32) : (u32)buf[j];
+                            const u32 qq = hi_half ? (u32)(q0 >> 32) : (u32)q0;
+                            const int sh = (__ffs((int)xx) - 1) & ~1;
+                            const int b = (sh >> 1) + (hi_half ? 16 : 0);
                             if (b >= cap) l = cap;
-                            else { l = b; if (((buf[j] >> (2 * b)) & 3) < ((q0 >> (2 * b)) & 3)) less |= 1u << j; }
+                            else { l = b; if (((rr >> sh) & 3) < ((qq >> sh) & 3)) less |= 1u << j; }
                         } else if (32 >= cap) l = cap;
                         else { und |= 1u << j; l = 32; }
                     }
