@@ -23,6 +23,81 @@ enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 template <bool WIDE> struct IdxT { typedef u32 type; };
 template <> struct IdxT<true> { typedef u64 type; };
 
+// Cold paths are kept out of the hot loop's instruction footprint (and their state out of registers):
+// emitting an SMEM record happens ~8 times per read, loading a task ~2 times, against ~135 round trips.
+struct OutState { u64 pslot, pend, tslot, tend, n_hit; u32 n_emit; };
+
+template <int KIND>
+__device__ __noinline__ void emit_record(const Args &A, OutState &o, u32 rid, int start, int end, u64 lo_, u64 cnt,
+                                         bool full_match, u64 max_refpos)
+{
+    if (o.pslot == o.pend) { o.pslot = atomicAdd((unsigned long long *)&A.ctrl[C_POOL], 16ull); o.pend = o.pslot + 16; }
+    u64 k = o.pslot++;
+    u32 c32 = cnt > 0xffffffffull ? 0xffffffffu : (u32)cnt;
+    if (k < A.pool_cap) {
+        A.pool_keys[k] = ((u64)rid << 32) | ((u64)start << 16) | (u64)end;
+        PoolRec v; v.lo = lo_; v.cnt = c32; v.pad = 0;
+        A.pool_vals[k] = v;
+    } else atomicExch((unsigned long long *)&A.ctrl[C_POOL_OVF], 1ull);
+    o.n_emit++;
+    u32 c = c32;
+    if (A.opt.max_occ > 0) {
+        u32 mo = (u32)A.opt.max_occ;
+        u32 step = c > mo ? c / mo : 1;
+        u32 t = (c - 1) / step + 1;
+        c = c == 0 ? 0 : (t < mo ? t : mo);
+    }
+    o.n_hit += c;
+    // T1: long and rare SMEMs become reseed tasks (reference L923-947)
+    if (KIND == 1 && A.opt.rounds >= 2 && end - start >= A.opt.split_len && c32 <= (u32)A.opt.split_width) {
+        if (o.tslot == o.tend) { o.tslot = atomicAdd((unsigned long long *)&A.ctrl[C_T2], 8ull); o.tend = o.tslot + 8; }
+        u64 t = o.tslot++;
+        if (t < A.t2_cap) {
+            Task2 x; x.read = rid; x.se = (u32)start | ((u32)end << 16); x.cnt = c32;
+            x.full = full_match ? 1u : 0u; x.lo = full_match ? max_refpos : lo_; x.pad = 0;
+            A.t2_out[t] = x;
+        } else atomicExch((unsigned long long *)&A.ctrl[C_T2_OVF], 1ull);
+    }
+}
+
+__device__ __noinline__ void flush_counts(const Args &A, OutState &o, u32 rid)
+{
+    if (o.n_emit) {
+        atomicAdd(&A.rd_nsmem[rid], o.n_emit);
+        atomicAdd((unsigned long long *)&A.rd_nhit[rid], (unsigned long long)o.n_hit);
+        o.n_emit = 0; o.n_hit = 0;
+    }
+}
+
+__device__ __noinline__ void load_task_words(const Args &A, u32 rid, u32 *sm)
+{
+    const u64 *src = A.packed + (u64)rid * TPR_RW;
+    const u32 *nsrc = A.nmask + (u64)rid * TPR_RW;
+#pragma unroll
+    for (int w = 0; w < TPR_RW; w++) {
+        u64 v = __ldg(src + w);
+        sm[2 * w] = (u32)v; sm[2 * w + 1] = (u32)(v >> 32);
+        sm[20 + w] = __ldg(nsrc + w);
+    }
+}
+
+template <int KIND>
+__device__ __noinline__ void finish_thread(const Args &A, OutState &o, u32 st_search, u32 st_block, u32 st_kary, u32 st_ext,
+                                           u32 st_pac, u32 st_iter)
+{
+    // reserved but unused slots must not look like records
+    for (; o.pslot < o.pend; o.pslot++) if (o.pslot < A.pool_cap) A.pool_keys[o.pslot] = ~0ull;
+    if (KIND == 1)
+        for (; o.tslot < o.tend; o.tslot++)
+            if (o.tslot < A.t2_cap) { Task2 x; x.read = 0xffffffffu; x.se = 0; x.cnt = 0; x.full = 0; x.lo = 0; x.pad = 0; A.t2_out[o.tslot] = x; }
+    atomicAdd((unsigned long long *)&A.ctrl[C_SEARCH], (unsigned long long)st_search);
+    atomicAdd((unsigned long long *)&A.ctrl[C_BLOCK], (unsigned long long)st_block);
+    atomicAdd((unsigned long long *)&A.ctrl[C_KARY], (unsigned long long)st_kary);
+    atomicAdd((unsigned long long *)&A.ctrl[C_EXT], (unsigned long long)st_ext);
+    atomicAdd((unsigned long long *)&A.ctrl[C_PAC], (unsigned long long)st_pac);
+    atomicAdd((unsigned long long *)&A.ctrl[C_ITER], (unsigned long long)st_iter);
+}
+
 template <int KIND, bool WIDE, int MINB>
 __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A)
 {
@@ -64,7 +139,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     // auto-start scratch
     int as_pv = 0, as_ret = 0; bool as_right = false, as_emit = false;
     // ---- output ----
-    u64 pslot = 0, pend = 0, tslot = 0, tend = 0; u32 n_emit = 0; u64 n_hit = 0;
+    OutState out; out.pslot = out.pend = out.tslot = out.tend = out.n_hit = 0; out.n_emit = 0;
     u32 st_search = 0, st_block = 0, st_kary = 0, st_ext = 0, st_pac = 0, st_iter = 0;
 
     // ------------------------------------------------------------------ helpers (lambdas: inlined once per use)
@@ -110,32 +185,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         st_block++;
     };
     auto push = [&](int start, int end, idx_t lo_, u64 cnt) {
-        if (pslot == pend) { pslot = atomicAdd((unsigned long long *)&A.ctrl[C_POOL], 16ull); pend = pslot + 16; }
-        u64 k = pslot++;
-        u32 c32 = cnt > 0xffffffffull ? 0xffffffffu : (u32)cnt;
-        if (k < A.pool_cap) {
-            A.pool_keys[k] = ((u64)rid << 32) | ((u64)start << 16) | (u64)end;
-            PoolRec v; v.lo = lo_; v.cnt = c32; v.pad = 0;
-            A.pool_vals[k] = v;
-        } else atomicExch((unsigned long long *)&A.ctrl[C_POOL_OVF], 1ull);
-        n_emit++;
-        u32 c = c32;
-        if (A.opt.max_occ > 0) {
-            u32 mo = (u32)A.opt.max_occ;
-            u32 step = c > mo ? c / mo : 1;
-            u32 t = (c - 1) / step + 1;
-            c = c == 0 ? 0 : (t < mo ? t : mo);
-        }
-        n_hit += c;
-        if (KIND == 1 && A.opt.rounds >= 2 && end - start >= A.opt.split_len && c32 <= (u32)A.opt.split_width) {
-            if (tslot == tend) { tslot = atomicAdd((unsigned long long *)&A.ctrl[C_T2], 8ull); tend = tslot + 8; }
-            u64 t = tslot++;
-            if (t < A.t2_cap) {
-                Task2 x; x.read = rid; x.se = (u32)start | ((u32)end << 16); x.cnt = c32;
-                x.full = full_match ? 1u : 0u; x.lo = full_match ? (u64)max_refpos : (u64)lo_; x.pad = 0;
-                A.t2_out[t] = x;
-            } else atomicExch((unsigned long long *)&A.ctrl[C_T2_OVF], 1ull);
-        }
+        emit_record<KIND>(A, out, rid, start, end, (u64)lo_, cnt, full_match, (u64)max_refpos);
     };
 
     for (;;) {
@@ -143,11 +193,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             // =========================== control: one flat state machine ===========================
             switch (state) {
             case P_TASK:
-                if (n_emit) {
-                    atomicAdd(&A.rd_nsmem[rid], n_emit);
-                    atomicAdd((unsigned long long *)&A.rd_nhit[rid], (unsigned long long)n_hit);
-                    n_emit = 0; n_hit = 0;
-                }
+                flush_counts(A, out, rid);
                 task = atomicAdd((unsigned long long *)&A.ctrl[C_WORK], 1ull);
                 if (task >= (u64)A.n_tasks) goto finished;
                 if (KIND == 2) { mreq = M_T2REC; }
@@ -301,11 +347,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             auto_start:
                 s_pivot = as_pv; q_strand = as_right ? 0 : 1; s_emit = as_emit; s_need = min_intv; s_msl = min_seed_len;
                 s_stepwise = false; d_ret = as_ret; s_mode = ST_RMI; s_isa = false;
-                if (ix.mode == 3) {
+                if (KIND != 1 && ix.mode == 3) {
                     if (full_match) {
                         s_mode = ST_EXACT; s_isa = true;
                         s_hint = as_right ? max_refpos + as_pv : n - max_refpos - as_pv - 1;
-                    } else if (use_cached) {
+                    } else if (KIND == 2 && use_cached) {
                         if (as_right && cache_pivot_end >= as_pv + 18 && as_pv >= cache_pivot) {
                             s_mode = ST_NEAR; s_isa = true; s_hint = cache_refpos + as_pv - cache_pivot;
                         } else if (!as_right && as_pv < cache_pivot_end && cache_pivot + 18 <= as_pv) {
@@ -320,9 +366,10 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 if (q_strand == 0) { q_from = s_pivot; q_V = next_n(s_pivot) - s_pivot; }
                 else { q_from = L - 1 - s_pivot; q_V = s_pivot - prev_n(s_pivot); }
                 q0 = qword(0);
-                if (s_isa) { mreq = M_LD; m_ldk = LD_ISA; m_base = s_hint; state = P_S_ISA; break; }
+                if (KIND != 1 && s_isa) { mreq = M_LD; m_ldk = LD_ISA; m_base = s_hint; state = P_S_ISA; break; }
                 goto s_rmi;
             case P_S_ISA:
+                if (KIND == 1) { state = P_TASK; break; }
                 s_hint = (idx_t)ld_val;
                 if (s_mode == ST_EXACT) { req_contig(s_hint > 3 ? s_hint - 3 : 0, q_V); state = P_S_EXACT; break; }
                 center = s_hint; rad_lo = rad_hi = 2;
@@ -433,10 +480,10 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             init_right:
                 if (nbr < 0) { e_dir = +1; e_from = hi; e_L = lev; e_limit = lv_limit; e_ret = R_INIT_R; goto e_begin; }
             leveled:
-                if (s_stepwise) goto search_done;
+                if (KIND == 3 && s_stepwise) goto search_done;
                 it = 0;
             level_loop:
-                if ((u64)(hi - lo) + 1 < (u64)s_need && it++ < 400) {
+                if (KIND != 1 && (u64)(hi - lo) + 1 < (u64)s_need && it++ < 400) {
                     lv_limit = (s_emit && max(nbl, nbr) >= s_msl) ? ~0ull : (u64)s_need;
                     lv_ret = 0;
                     goto lv_begin;
@@ -456,6 +503,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
 
             // ------------------------------------------------ one level drop (reference L2569-2574)
             lv_begin:
+                if (KIND == 1) { state = P_TASK; break; }
                 lev = nbl > nbr ? nbl : nbr;
                 if (lev <= 0) { lev = 0; lo = 0; hi = n - 1; nbl = nbr = 0; goto lv_done; }
                 if (nbl >= lev) {
@@ -569,14 +617,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             ulonglong2 a = __ldg(t2), b = __ldg(t2 + 1);
             buf[0] = a.x; buf[1] = a.y; buf[2] = b.x;
         } else if (req == M_TASK) {
-            const u64 *src = A.packed + (u64)rid * TPR_RW;
-            const u32 *nsrc = A.nmask + (u64)rid * TPR_RW;
-#pragma unroll
-            for (int w = 0; w < TPR_RW; w++) {
-                u64 v = __ldg(src + w);
-                sm[2 * w] = (u32)v; sm[2 * w + 1] = (u32)(v >> 32);
-                sm[20 + w] = __ldg(nsrc + w);
-            }
+            load_task_words(A, rid, sm);
         }
         // =========================== compare phase ===========================
         if (req == M_BLOCK) {
@@ -677,17 +718,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         }
     }
 finished:
-    // reserved but unused slots must not look like records
-    for (; pslot < pend; pslot++) if (pslot < A.pool_cap) A.pool_keys[pslot] = ~0ull;
-    if (KIND == 1)
-        for (; tslot < tend; tslot++)
-            if (tslot < A.t2_cap) { Task2 x; x.read = 0xffffffffu; x.se = 0; x.cnt = 0; x.full = 0; x.lo = 0; x.pad = 0; A.t2_out[tslot] = x; }
-    atomicAdd((unsigned long long *)&A.ctrl[C_SEARCH], (unsigned long long)st_search);
-    atomicAdd((unsigned long long *)&A.ctrl[C_BLOCK], (unsigned long long)st_block);
-    atomicAdd((unsigned long long *)&A.ctrl[C_KARY], (unsigned long long)st_kary);
-    atomicAdd((unsigned long long *)&A.ctrl[C_EXT], (unsigned long long)st_ext);
-    atomicAdd((unsigned long long *)&A.ctrl[C_PAC], (unsigned long long)st_pac);
-    atomicAdd((unsigned long long *)&A.ctrl[C_ITER], (unsigned long long)st_iter);
+    finish_thread<KIND>(A, out, st_search, st_block, st_kary, st_ext, st_pac, st_iter);
 #undef RL
 #undef BL
 }
