@@ -396,14 +396,15 @@ def main_ours(a):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_seed_dram_bytes_per_read")
+                traffic = json.load(open(tp)).get("seed_kernels_dram_bytes_per_read")
                 traffic = traffic * n if traffic else None
             except Exception:
                 traffic = None
         if bytes_per_read:
             achieved = bytes_per_read * n / (kseed_ms / 1e3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": traffic, "kernel": "k_seed", "algorithmic_bytes_per_read": bytes_per_read,
+                                "traffic": traffic, "kernel": "seeding kernels k_flat<1|2|3> (T1 zig-zag, T2 reseed, T3 third round) + k_pack_reads",
+                                "algorithmic_bytes_per_read": bytes_per_read,
                                 "peak_source": peak_src,
                                 "note": "algorithmic bytes = SURVEY §8d formula with counters from oracle/seed_oracle.c on a "
                                         "sample of this workload; accesses are 8-24 B random reads, so the sector-granular DRAM "
