@@ -58,7 +58,7 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------------
 def workload_key(a) -> str:
-    s = f"g{a.genome_len}-b{a.bits}-v3"
+    s = f"g{a.genome_len}-b{a.bits}-v5"
     return hashlib.sha1(s.encode()).hexdigest()[:12]
 
 

@@ -947,14 +947,28 @@ int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
         CUDA_TRY(cudaStreamSynchronize(st));
         n_t2 = ix->h_ctrl[C_T2];
         bool ovf = ix->h_ctrl[C_T2_OVF] != 0;
+        static const bool dbg = getenv("MEME_SEED_DEBUG") != nullptr;   // per-kernel counters + times on stderr
+        auto dump = [&](const char *name, cudaEvent_t e0, cudaEvent_t e1, int64_t tasks) {
+            u64 c[16]; float ms = 0;
+            cudaMemcpyAsync(c, ix->d_ctrl, sizeof c, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[meme_seed] %s: %lld tasks, %.2f ms (cumulative counters) searches %llu blocks %llu kary %llu ext %llu pac %llu "
+                    "round-trips %llu\n", name, (long long)tasks, ms, c[C_SEARCH], c[C_BLOCK], c[C_KARY], c[C_EXT], c[C_PAC], c[C_ITER]);
+        };
+        cudaEvent_t de[4];
+        if (dbg) { for (auto &e : de) cudaEventCreate(&e); cudaEventRecord(de[1], st); dump("T1", ix->ev[0], de[1], n); }
         if (!ovf && opt->rounds >= 2 && n_t2) {
             A.kind = 2; A.n_tasks = (int64_t)n_t2; A.t2_in = (const Task2 *)ix->d_t2; A.t2_out = nullptr; A.t2_cap = 0;
             if ((rc = launch_tpr<2>(ix, A))) return rc;
+            if (dbg) { cudaEventRecord(de[2], st); dump("T2", de[1], de[2], (int64_t)n_t2); }
         }
         if (!ovf && opt->rounds >= 3 && opt->max_mem_intv > 0) {
             A.kind = 3; A.n_tasks = n; A.t2_in = nullptr;
             if ((rc = launch_tpr<3>(ix, A))) return rc;
+            if (dbg) { cudaEventRecord(de[3], st); dump("T3", de[2], de[3], n); }
         }
+        if (dbg) for (auto &e : de) cudaEventDestroy(e);
         CUDA_TRY(cudaEventRecord(ix->ev[1], st));
         CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

@@ -23,7 +23,7 @@ import torch
 
 PARTIAL_MIN = 1000  # leaves with more keys get a third layer (two_layer.rs:L373)
 PARTIAL_DIV = 20
-SLACK = 2           # added to both error bounds (covers fma-vs-mul/add rounding and unseen keys)
+SLACK = 1           # added to both error bounds (the reference's window code underflows with a zero window at position 0, L2262-2264)
 TWO32 = 4294967296.0
 
 

@@ -240,7 +240,7 @@ static uint64_t locate_window(rd_t *r, const uint8_t *q, int V, uint64_t est, ui
     uint64_t cerr = (enc_err >> 32) & 0x3fffffff, err = enc_err & 0x7fffffff;
     uint64_t ub = est + err >= n_sa - 1 ? n_sa - 2 : est + err;
     uint64_t lb = est > cerr ? est - cerr : 1;
-    if (lb >= ub) lb = ub - 1;
+    if (lb >= ub) lb = ub > 0 ? ub - 1 : 0;   /* (the reference underflows here when ub == 0: degenerate parameter files) */
     uint64_t n = ub - lb + 1, mid = est, half;
     int less, exact = 0, ml = 0, last;
     while ((half = n >> 1)) {
