@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmeme_b200.so")
+LIB_PATH = os.environ.get("MEME_B200_LIB") or os.path.join(HERE, "libmeme_b200.so")   # same override as the C++ glue
 
 SMEM_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("hitbeg", "<i4"), ("hitcount", "<i4"), ("cache_refpos", "<u8")])
 SEQPAIR_DTYPE = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1", "<i4"), ("len2", "<i4"),

@@ -20,6 +20,24 @@ enum {
 };
 enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 
+// per-thread shared words: [0,2) zero pair (read word -1), [2,22) packed read words 0..9, [22,24) zero pair
+// (read word 10), [24,34) N-mask words, 1 pad (odd stride: conflict-free)
+// Block-probe load/compare loops: fully unrolled (8) keeps buf[]/pp[] in registers; rolled (1) puts them in local
+// memory but takes 440 instructions out of the hot loop.  The reseeding kernel (T2) walks the level/extension code
+// as well and only fits the 32 KB instruction cache rolled ("no instruction" stalls 3.8 -> 0.55 per issue, ncu);
+// T1 and T3 fit either way and are faster unrolled (profiles/r1/experiments).
+#ifndef FLAT_VOTE
+#define FLAT_VOTE 1                       // 1: lanes re-enter the control switch together (vote-controlled loop)
+#endif
+#ifdef FLAT_BLK_UNROLL
+#define FLAT_BU(KIND) (FLAT_BLK_UNROLL)
+#else
+#define FLAT_BU(KIND) ((KIND) == 2 ? 1 : 8)
+#endif
+#define FLAT_SW 35
+#define FLAT_RD 2
+#define FLAT_NM 24
+
 template <bool WIDE> struct IdxT { typedef u32 type; };
 template <> struct IdxT<true> { typedef u64 type; };
 
@@ -76,8 +94,8 @@ __device__ __noinline__ void load_task_words(const Args &A, u32 rid, u32 *sm)
 #pragma unroll
     for (int w = 0; w < TPR_RW; w++) {
         u64 v = __ldg(src + w);
-        sm[2 * w] = (u32)v; sm[2 * w + 1] = (u32)(v >> 32);
-        sm[20 + w] = __ldg(nsrc + w);
+        sm[FLAT_RD + 2 * w] = (u32)v; sm[FLAT_RD + 2 * w + 1] = (u32)(v >> 32);
+        sm[FLAT_NM + w] = __ldg(nsrc + w);
     }
 }
 
@@ -98,12 +116,14 @@ __device__ __noinline__ void finish_thread(const Args &A, OutState &o, u32 st_se
     atomicAdd((unsigned long long *)&A.ctrl[C_ITER], (unsigned long long)st_iter);
 }
 
-template <int KIND, bool WIDE, int MINB>
+template <int KIND, bool WIDE, int MINB, bool SYNC, bool STATS>
 __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A)
 {
     typedef typename IdxT<WIDE>::type idx_t;
-    __shared__ u32 smem[TPR_THREADS * TPR_SW];
-    u32 *const sm = &smem[threadIdx.x * TPR_SW];
+    constexpr int BU = FLAT_BU(KIND);
+    __shared__ u32 smem[TPR_THREADS * FLAT_SW];
+    u32 *const sm = &smem[threadIdx.x * FLAT_SW];
+    sm[0] = sm[1] = sm[FLAT_RD + 2 * TPR_RW] = sm[FLAT_RD + 2 * TPR_RW + 1] = 0;
     const idx_t n = (idx_t)ix.sa_num;
     const bool has_keys = ix.keys != nullptr;
     const int opt_msl = A.opt.min_seed_len;
@@ -143,30 +163,33 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     u32 st_search = 0, st_block = 0, st_kary = 0, st_ext = 0, st_pac = 0, st_iter = 0;
 
     // ------------------------------------------------------------------ helpers (lambdas: inlined once per use)
-    auto rdw = [&](int w) -> u64 { return (w < 0 || w >= TPR_RW) ? 0 : ((u64)sm[2 * w] | ((u64)sm[2 * w + 1] << 32)); };
+    // 32 bases of the forward read from `start` (any integer: bases outside the read are 0); read words -1 and
+    // TPR_RW are zero pads, so the window needs no per-word bounds checks
     auto fwwin = [&](int start) -> u64 {
-        if (start < 0) return start <= -32 ? 0 : rdw(0) << (2 * (-start));
-        int w = start >> 5, sh = (start & 31) * 2;
-        u64 a = rdw(w);
-        return sh == 0 ? a : ((a >> sh) | (rdw(w + 1) << (64 - sh)));
+        if (start < -32 || start >= 32 * TPR_RW) return 0;
+        const int w = start >> 5, sh = (start & 31) * 2;
+        const u32 *p = sm + FLAT_RD + 2 * w;
+        const u64 a = (u64)p[0] | ((u64)p[1] << 32), b = (u64)p[2] | ((u64)p[3] << 32);
+        return sh == 0 ? a : ((a >> sh) | (b << (64 - sh)));
     };
     auto qword = [&](int k) -> u64 {
-        int f = q_from + 32 * k;
-        return q_strand == 0 ? fwwin(f) : revcomp32(fwwin(L - 32 - f));
+        const int f = q_from + 32 * k;
+        const u64 v = fwwin(q_strand == 0 ? f : L - 32 - f);
+        return q_strand == 0 ? v : revcomp32(v);
     };
-    auto is_n = [&](int p) -> bool { return (sm[20 + (p >> 5)] >> (p & 31)) & 1; };
+    auto is_n = [&](int p) -> bool { return (sm[FLAT_NM + (p >> 5)] >> (p & 31)) & 1; };
     auto next_n = [&](int from) -> int {
         int w = from >> 5;
-        u32 m = sm[20 + w] >> (from & 31);
+        u32 m = sm[FLAT_NM + w] >> (from & 31);
         if (m) { int p = from + __ffs(m) - 1; return p < L ? p : L; }
-        for (w++; w * 32 < L; w++) { u32 x = sm[20 + w]; if (x) { int p = w * 32 + __ffs(x) - 1; return p < L ? p : L; } }
+        for (w++; w * 32 < L; w++) { u32 x = sm[FLAT_NM + w]; if (x) { int p = w * 32 + __ffs(x) - 1; return p < L ? p : L; } }
         return L;
     };
     auto prev_n = [&](int p) -> int {
         int w = p >> 5;
-        u32 m = sm[20 + w] & (0xffffffffu >> (31 - (p & 31)));
+        u32 m = sm[FLAT_NM + w] & (0xffffffffu >> (31 - (p & 31)));
         if (m) return w * 32 + 31 - __clz(m);
-        for (w--; w >= 0; w--) { u32 x = sm[20 + w]; if (x) return w * 32 + 31 - __clz(x); }
+        for (w--; w >= 0; w--) { u32 x = sm[FLAT_NM + w]; if (x) return w * 32 + 31 - __clz(x); }
         return -1;
     };
     auto get16 = [](u64 a, u64 b, int j) -> int { return (int)(((j < 4 ? a : b) >> (16 * (j & 3))) & 0xffff); };
@@ -182,20 +205,33 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         int c = n - b < 8 ? (int)(n - b) : 8;
         base = b; nvalid = c;
         req_block(b, 1, c, cap);
-        st_block++;
+        if (STATS) st_block++;
     };
     auto push = [&](int start, int end, idx_t lo_, u64 cnt) {
         emit_record<KIND>(A, out, rid, start, end, (u64)lo_, cnt, full_match, (u64)max_refpos);
     };
 
+    // SYNC: the warp reconverges at the head of every iteration (lanes that ran out of tasks idle in the loop
+    // until the whole warp is done), so that the memory and compare phases run with every lane of a request
+    // kind together.  Without it the irreducible control flow below leaves the warp split in independently
+    // looping fragments (ncu: 3 active lanes per instruction even in the block-probe loads, profiles/r1).
+    bool done = false;
     for (;;) {
-        if (mreq == M_NONE) {
+        if (SYNC) {
+            __syncwarp();
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+#if FLAT_VOTE
+        while (__any_sync(0xffffffffu, !done && mreq == M_NONE)) if (!done && mreq == M_NONE) {
+#else
+        while (!done && mreq == M_NONE) {
+#endif
             // =========================== control: one flat state machine ===========================
             switch (state) {
             case P_TASK:
                 flush_counts(A, out, rid);
                 task = atomicAdd((unsigned long long *)&A.ctrl[C_WORK], 1ull);
-                if (task >= (u64)A.n_tasks) goto finished;
+                if (task >= (u64)A.n_tasks) { done = true; break; }
                 if (KIND == 2) { mreq = M_T2REC; }
                 else { rid = (u32)task; mreq = M_TASK; }
                 state = P_TASK_LOADED;
@@ -362,7 +398,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 // fall through
             // ------------------------------------------------ search (right_smem_search / mem_search / *_tradeoff)
             s_begin:
-                st_search++;
+                if (STATS) st_search++;
                 if (q_strand == 0) { q_from = s_pivot; q_V = next_n(s_pivot) - s_pivot; }
                 else { q_from = L - 1 - s_pivot; q_V = s_pivot - prev_n(s_pivot); }
                 q0 = qword(0);
@@ -439,7 +475,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                         int cnt = 0;
                         if (first < pb) { idx_t c = (pb - 1 - first) / k_stride + 1; cnt = c < 8 ? (int)c : 8; }
                         req_block(first, (long long)k_stride, cnt, q_V);
-                        st_kary++;
+                        if (STATS) st_kary++;
                     }
                     state = P_S_LOC;
                 }
@@ -543,7 +579,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                     e_cnt = room < 8 ? (int)room : 8;
                     req_block(e_cur - (idx_t)e_s, -(long long)e_s, e_cnt, e_L);
                 }
-                st_ext++;
+                if (STATS) st_ext++;
                 state = P_E;
                 break;
             case P_E:
@@ -571,16 +607,17 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 }
             }
         }
-        if (mreq == M_NONE) continue;
-        st_iter++;
+        if (!SYNC && done) break;
+        if (SYNC) __syncwarp();
         // =========================== memory phase: every lane issues the loads of its own request ===========================
         u64 buf[8];
-        const int req = mreq;
+        const int req = done ? (int)M_NONE : mreq;
+        if (STATS && req != M_NONE) st_iter++;
         if (req == M_BLOCK) {
             idx_t idx = m_base;
             const idx_t step = (idx_t)m_stride;
             u64 h = 0;
-#pragma unroll
+#pragma unroll BU
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
                     buf[j] = has_keys ? __ldg(ix.keys + idx) : 0;
@@ -591,9 +628,12 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             }
             if (WIDE) pphi = h;
         } else if (req == M_PAC) {
-            u32 v = pp[0];
+            u32 v;
+            if (BU == 8) {
+                v = pp[0];
 #pragma unroll
-            for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
+                for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
+            } else v = pp[pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
@@ -619,10 +659,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         } else if (req == M_TASK) {
             load_task_words(A, rid, sm);
         }
+        if (SYNC) __syncwarp();
         // =========================== compare phase ===========================
         if (req == M_BLOCK) {
             u64 lo16 = 0, hi16 = 0; u32 less = 0, und = 0;
-#pragma unroll
+#pragma unroll BU
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
                     int cap;
@@ -658,10 +699,13 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             if (und) { pac_e = __ffs(und) - 1; pac_k0 = has_keys ? 1 : 0; mreq = M_PAC; }
             else mreq = M_NONE;
         } else if (req == M_PAC) {
-            st_pac++;
-            u32 v = pp[0];
+            if (STATS) st_pac++;
+            u32 v;
+            if (BU == 8) {
+                v = pp[0];
 #pragma unroll
-            for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
+                for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
+            } else v = pp[pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             const int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
@@ -717,7 +761,6 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             mreq = M_NONE;
         }
     }
-finished:
     finish_thread<KIND>(A, out, st_search, st_block, st_kary, st_ext, st_pac, st_iter);
 #undef RL
 #undef BL

@@ -897,10 +897,16 @@ static int launch_tpr(meme_index_t *ix, const Args &A)
     if (A.n_tasks <= 0) return MEME_OK;
     if (tpr_variant() == 1) return launch_kernel(ix, A, k_tpr<KIND>);
     static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 2;
-    if (ix->v.pos_wide) return launch_kernel(ix, A, k_flat<KIND, true, 2>);
-    if (minb == 3) return launch_kernel(ix, A, k_flat<KIND, false, 3>);
-    if (minb == 4) return launch_kernel(ix, A, k_flat<KIND, false, 4>);
-    return launch_kernel(ix, A, k_flat<KIND, false, 2>);
+    static int sync = getenv("MEME_SEED_SYNC") ? atoi(getenv("MEME_SEED_SYNC")) : 1;   // warp reconvergence per iteration
+    // work counters (meme_seed_counters [0..3]) cost registers and code in the hot loop: off unless asked for
+    const char *se = getenv("MEME_SEED_STATS");
+    const bool stats = se && atoi(se) != 0;
+    if (ix->v.pos_wide)
+        return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>);
+    if (!sync) return launch_kernel(ix, A, k_flat<KIND, false, 2, false, false>);
+    if (minb == 3)
+        return stats ? launch_kernel(ix, A, k_flat<KIND, false, 3, true, true>) : launch_kernel(ix, A, k_flat<KIND, false, 3, true, false>);
+    return stats ? launch_kernel(ix, A, k_flat<KIND, false, 2, true, true>) : launch_kernel(ix, A, k_flat<KIND, false, 2, true, false>);
 }
 
 int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)

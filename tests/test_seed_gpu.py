@@ -50,13 +50,14 @@ def test_cuda_matches_oracle_rounds(oracle, pkg, gidx, golden_index, golden_read
     assert (got["hits"] == want["hits"]).all()
 
 
-def test_wide_windows_repeats_and_all_lengths(oracle, pkg, mid_index):
+def test_wide_windows_repeats_and_all_lengths(oracle, pkg, mid_index, monkeypatch):
     """400 kb genome, 2^12 leaves (RMI windows of hundreds of entries -> 32-ary narrowing), 60-copy repeat
     families (intervals larger than one 32-entry block -> galloping), ragged read lengths 20..320."""
     from bwa_meme_b200 import capi, synth
     prefix, g = mid_index
     codes, offs = synth.make_reads(g, 3000, 320, seed=5, n_frac=0.05, len_jitter=300)
     n = len(offs) - 1
+    monkeypatch.setenv("MEME_SEED_STATS", "1")          # the work counters are off by default (they cost registers)
     for mode in (3, 1):
         ix = capi.MemeIndex(prefix, mode=mode)
         got = ix.seed(codes, offs)
