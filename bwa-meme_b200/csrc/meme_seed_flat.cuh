@@ -16,27 +16,37 @@ namespace tpr {
 
 enum {
     P_TASK = 0, P_TASK_LOADED, P_S_ISA, P_S_EXACT, P_S_RMI1, P_S_RMI2, P_S_CENTER, P_S_LOC, P_E,
-    P_D1_L, P_D1_R, P_D1_F, P_D1_M, P_D2_C, P_D2_F, P_D2_L, P_D2_R, P_D3_S, P_D3_LV
+    P_D1_L, P_D1_R, P_D1_F, P_D1_M, P_D2_C, P_D2_F, P_D2_L, P_D2_R, P_D3_S, P_D3_LV, P_AUTO, P_SBEGIN, P_LOCATED
 };
 enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 
 // per-thread shared words: [0,2) zero pair (read word -1), [2,22) packed read words 0..9, [22,24) zero pair
-// (read word 10), [24,34) N-mask words, 1 pad (odd stride: conflict-free)
-// Block-probe load/compare loops: fully unrolled (8) keeps buf[]/pp[] in registers; rolled (1) puts them in local
-// memory but takes 440 instructions out of the hot loop.  The reseeding kernel (T2) walks the level/extension code
-// as well and only fits the 32 KB instruction cache rolled ("no instruction" stalls 3.8 -> 0.55 per issue, ncu);
-// T1 and T3 fit either way and are faster unrolled (profiles/r1/experiments).
-#ifndef FLAT_VOTE
-#define FLAT_VOTE 1                       // 1: lanes re-enter the control switch together (vote-controlled loop)
-#endif
-#ifdef FLAT_BLK_UNROLL
-#define FLAT_BU(KIND) (FLAT_BLK_UNROLL)
-#else
-#define FLAT_BU(KIND) ((KIND) == 2 ? 1 : 8)
-#endif
+// (read word 10), [24,34) N-mask words, 1 pad (odd stride: conflict-free), then FLAT_STG staging words (rolled kinds)
 #define FLAT_SW 35
 #define FLAT_RD 2
 #define FLAT_NM 24
+#define FLAT_STG 24                       // staging words per thread: key low halves, key high halves, positions
+
+// Tuning switches (profiles/r1/experiments has the measurements behind the defaults).
+#ifndef FLAT_VOTE
+#define FLAT_VOTE 1                       // 1: lanes re-enter the control switch together (vote-controlled loop)
+#endif
+// Shared control code (start selection, search begin, located) entered as a state of its own, so that lanes arriving
+// from different states run it together.  Costs ~300 instructions of code; pays for the third-round kernel only.
+#ifndef FLAT_MERGE
+#define FLAT_MERGE(KIND) ((KIND) == 3)
+#endif
+#define FLAT_GOTO(label, st) do { if (FLAT_MERGE(KIND)) { state = st; goto next_state; } else goto label; } while (0)
+// Block-probe compare loop: fully unrolled (8) keeps the 8 keys/positions in registers; rolled (< 8) stages them in
+// FLAT_STG more shared words per thread and takes ~250 instructions out of the hot loop (the loads stay unrolled so
+// that all 16 are in flight).  The kernels that walk the level/extension code as well (T2, T3) only fit the 32 KB
+// instruction cache rolled ("no instruction" stalls 3.8 -> 0.55 per issue, ncu).
+#ifdef FLAT_BLK_UNROLL
+#define FLAT_BU(KIND) (FLAT_BLK_UNROLL)
+#else
+#define FLAT_BU(KIND) 1
+#endif
+template <int KIND> __host__ __device__ constexpr int flat_sw() { return FLAT_SW + (FLAT_BU(KIND) == 8 ? 0 : FLAT_STG); }
 
 template <bool WIDE> struct IdxT { typedef u32 type; };
 template <> struct IdxT<true> { typedef u64 type; };
@@ -121,8 +131,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
 {
     typedef typename IdxT<WIDE>::type idx_t;
     constexpr int BU = FLAT_BU(KIND);
-    __shared__ u32 smem[TPR_THREADS * FLAT_SW];
-    u32 *const sm = &smem[threadIdx.x * FLAT_SW];
+    constexpr bool STG = BU != 8;
+    constexpr int SW = flat_sw<KIND>();
+    extern __shared__ u32 smem[];
+    u32 *const sm = &smem[threadIdx.x * SW];
+    u32 *const stg = sm + FLAT_SW;
     sm[0] = sm[1] = sm[FLAT_RD + 2 * TPR_RW] = sm[FLAT_RD + 2 * TPR_RW + 1] = 0;
     const idx_t n = (idx_t)ix.sa_num;
     const bool has_keys = ix.keys != nullptr;
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 // first search of a segment: always through the RMI
                 s_pivot = pivot; q_strand = 0; s_emit = true; s_need = 1; s_msl = min_seed_len; s_mode = ST_RMI; s_isa = false;
                 s_stepwise = false; d_ret = P_D1_F;
-                goto s_begin;
+                FLAT_GOTO(s_begin, P_SBEGIN);
             case P_D1_F:
                 if (KIND != 1) { state = P_TASK; break; }
                 if (ix.mode == 3 && lev == L) {              // whole read matched (L1870-1875)
@@ -299,13 +312,13 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                     goto d1_zz;
                 }
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D1_L;
-                goto auto_start;
+                FLAT_GOTO(auto_start, P_AUTO);
             case P_D1_L:
                 if (KIND != 1) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
                 if (L - pivot < min_seed_len) { pivot = L; goto d1_loop; }
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D1_R;
-                goto auto_start;
+                FLAT_GOTO(auto_start, P_AUTO);
             case P_D1_R:
                 if (KIND != 1) { state = P_TASK; break; }
                 sp = pivot + lev;
@@ -318,20 +331,20 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 cache_refpos = (idx_t)ld_val;
             d2_first:
                 as_pv = pivot; as_right = true; as_emit = false; as_ret = P_D2_F;
-                goto auto_start;
+                FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_F:
                 if (KIND != 2) { state = P_TASK; break; }
                 next = pivot + lev; sp = pivot;
             d2_loop:
                 if (sp >= next) { state = P_TASK; break; }
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D2_L;
-                goto auto_start;
+                FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_L:
                 if (KIND != 2) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
                 if (next - pivot < min_seed_len) { state = P_TASK; break; }
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D2_R;
-                goto auto_start;
+                FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_R:
                 if (KIND != 2) { state = P_TASK; break; }
                 sp = pivot + lev;
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 d_ret = P_D3_S;
                 if (full_match) { s_mode = ST_EXACT; s_hint = max_refpos + pivot; s_isa = true; }
                 else { s_mode = ST_RMI; s_isa = false; }
-                goto s_begin;
+                FLAT_GOTO(s_begin, P_SBEGIN);
             case P_D3_S:
                 if (KIND != 3) { state = P_TASK; break; }
                 if (lev < min_seed_len) { pivot += min_seed_len; goto d3_loop; }
@@ -380,6 +393,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 goto d3_levels;
 
             // ------------------------------------------------ start selection (reference L1741-1816 / L1926-2040)
+            case P_AUTO:
             auto_start:
                 s_pivot = as_pv; q_strand = as_right ? 0 : 1; s_emit = as_emit; s_need = min_intv; s_msl = min_seed_len;
                 s_stepwise = false; d_ret = as_ret; s_mode = ST_RMI; s_isa = false;
@@ -395,8 +409,9 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                         }
                     }
                 }
-                // fall through
+                FLAT_GOTO(s_begin, P_SBEGIN);
             // ------------------------------------------------ search (right_smem_search / mem_search / *_tradeoff)
+            case P_SBEGIN:
             s_begin:
                 if (STATS) st_search++;
                 if (q_strand == 0) { q_from = s_pivot; q_V = next_n(s_pivot) - s_pivot; }
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 center = s_hint; rad_lo = rad_hi = 2;
                 goto loc_init;
             case P_S_EXACT:
-                goto located;
+                FLAT_GOTO(located, P_LOCATED);
             s_rmi:
                 {
                     u64 k = q0;                             // RMI key = Tokenization (L795-901)
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 {
                     int c = lead_less();
                     bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + nvalid == n;
-                    if (left_ok && right_ok) goto located;
+                    if (left_ok && right_ok) FLAT_GOTO(located, P_LOCATED);
                     if (!left_ok) hi_b = base; else lo_b = base + nvalid;
                 }
             loc_next:
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 if (k_contig) {
                     int c = lead_less();
                     bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + nvalid == n;
-                    if (left_ok && right_ok) goto located;
+                    if (left_ok && right_ok) FLAT_GOTO(located, P_LOCATED);
                     if (!left_ok) hi_b = base; else lo_b = base + nvalid;
                 } else {
                     int c = lead_less();
@@ -495,6 +510,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 rad_hi = rad_hi * 8 + 8;
                 if (++it < 64) goto loc_next;
                 // not reached for a sorted suffix array: use the last block
+            case P_LOCATED:
             located:
                 // ---- first level = maximal lcp in the block, [lo,hi] = its interval ----
                 b_lo = r_lo; b_hi = r_hi;
@@ -606,6 +622,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 default: hi = e_edge; nbr = e_nb; goto lv_done;
                 }
             }
+        next_state:;
         }
         if (!SYNC && done) break;
         if (SYNC) __syncwarp();
@@ -613,11 +630,32 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         u64 buf[8];
         const int req = done ? (int)M_NONE : mreq;
         if (STATS && req != M_NONE) st_iter++;
-        if (req == M_BLOCK) {
+        if (req == M_BLOCK && STG) {
+            // asynchronous copies straight into the staging words: a rolled loop with every load in flight
+            u32 dst = (u32)__cvta_generic_to_shared(stg);
+            const char *kp = reinterpret_cast<const char *>(ix.keys + m_base);
+            const char *pq = reinterpret_cast<const char *>(ix.pos_lo + m_base);
+#pragma unroll 1
+            for (int j = 0; j < m_count; j++) {
+                if (has_keys) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(kp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32), "l"(kp + 4) : "memory");
+                }
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 64), "l"(pq) : "memory");
+                dst += 4; kp += m_stride * 8; pq += m_stride * 4;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (WIDE) {
+                u64 h = 0; idx_t idx = m_base;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { if (j < m_count) h |= (u64)__ldg(ix.pos_hi + idx) << (8 * j); idx += (idx_t)m_stride; }
+                pphi = h;
+            }
+        } else if (req == M_BLOCK) {
             idx_t idx = m_base;
             const idx_t step = (idx_t)m_stride;
             u64 h = 0;
-#pragma unroll BU
+#pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
                     buf[j] = has_keys ? __ldg(ix.keys + idx) : 0;
@@ -629,11 +667,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             if (WIDE) pphi = h;
         } else if (req == M_PAC) {
             u32 v;
-            if (BU == 8) {
+            if (!STG) {
                 v = pp[0];
 #pragma unroll
                 for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
-            } else v = pp[pac_e];
+            } else v = stg[16 + pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
@@ -663,27 +701,31 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         // =========================== compare phase ===========================
         if (req == M_BLOCK) {
             u64 lo16 = 0, hi16 = 0; u32 less = 0, und = 0;
+            if (STG) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll BU
             for (int j = 0; j < 8; j++) {
                 if (j < m_count) {
+                    const u32 klo = STG ? stg[j] : (u32)buf[j], khi = STG ? stg[8 + j] : (u32)(buf[j] >> 32);
+                    const u32 pj = STG ? stg[16 + j] : pp[j];
+                    (void)0;
                     int cap;
                     if (WIDE) {
-                        u64 p = (u64)pp[j] | (((pphi >> (8 * j)) & 0xff) << 32);
+                        u64 p = (u64)pj | (((pphi >> (8 * j)) & 0xff) << 32);
                         u64 ref_len = ix.sa_num - p;
                         cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
                     } else {
-                        u32 ref_len = (u32)n - pp[j];
+                        u32 ref_len = (u32)n - pj;
                         cap = (int)min(ref_len, (u32)m_cap);
                     }
                     int l;
                     if (!has_keys) { und |= 1u << j; l = 0; }
                     else {
-                        const u32 xl = (u32)buf[j] ^ (u32)q0, xh = (u32)(buf[j] >> 32) ^ (u32)(q0 >> 32);
+                        const u32 xl = klo ^ (u32)q0, xh = khi ^ (u32)(q0 >> 32);
                         if (xl | xh) {
                             // first differing base, in 32-bit halves (16 bases each)
                             const bool hi_half = xl == 0;
                             const u32 xx = hi_half ? xh : xl;
-                            const u32 rr = hi_half ? (u32)(buf[j] >> 32) : (u32)buf[j];
+                            const u32 rr = hi_half ? khi : klo;
                             const u32 qq = hi_half ? (u32)(q0 >> 32) : (u32)q0;
                             const int sh = (__ffs((int)xx) - 1) & ~1;
                             const int b = (sh >> 1) + (hi_half ? 16 : 0);
@@ -701,11 +743,11 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         } else if (req == M_PAC) {
             if (STATS) st_pac++;
             u32 v;
-            if (BU == 8) {
+            if (!STG) {
                 v = pp[0];
 #pragma unroll
                 for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
-            } else v = pp[pac_e];
+            } else v = stg[16 + pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             const int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;

@@ -876,16 +876,17 @@ static int tpr_variant()
 }
 
 template <class K>
-static int launch_kernel(meme_index_t *ix, const Args &A, K kernel)
+static int launch_kernel(meme_index_t *ix, const Args &A, K kernel, size_t dyn_smem = 0)
 {
     int sms = 0, per_sm = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPR_THREADS, 0));
+    if (dyn_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPR_THREADS, dyn_smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sms * per_sm, need = (A.n_tasks + TPR_THREADS - 1) / TPR_THREADS;
     if (grid > need) grid = need;
     CUDA_TRY(cudaMemsetAsync(ix->d_ctrl + C_WORK, 0, 8, ix->stream));
-    kernel<<<(unsigned)grid, TPR_THREADS, 0, ix->stream>>>(ix->v, A);
+    kernel<<<(unsigned)grid, TPR_THREADS, dyn_smem, ix->stream>>>(ix->v, A);
     CUDA_TRY(cudaGetLastError());
     ix->launches++;
     return MEME_OK;
@@ -896,17 +897,15 @@ static int launch_tpr(meme_index_t *ix, const Args &A)
 {
     if (A.n_tasks <= 0) return MEME_OK;
     if (tpr_variant() == 1) return launch_kernel(ix, A, k_tpr<KIND>);
-    static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 2;
     static int sync = getenv("MEME_SEED_SYNC") ? atoi(getenv("MEME_SEED_SYNC")) : 1;   // warp reconvergence per iteration
     // work counters (meme_seed_counters [0..3]) cost registers and code in the hot loop: off unless asked for
     const char *se = getenv("MEME_SEED_STATS");
     const bool stats = se && atoi(se) != 0;
+    const size_t sm = (size_t)TPR_THREADS * flat_sw<KIND>() * sizeof(u32);
     if (ix->v.pos_wide)
-        return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>);
-    if (!sync) return launch_kernel(ix, A, k_flat<KIND, false, 2, false, false>);
-    if (minb == 3)
-        return stats ? launch_kernel(ix, A, k_flat<KIND, false, 3, true, true>) : launch_kernel(ix, A, k_flat<KIND, false, 3, true, false>);
-    return stats ? launch_kernel(ix, A, k_flat<KIND, false, 2, true, true>) : launch_kernel(ix, A, k_flat<KIND, false, 2, true, false>);
+        return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>, sm);
+    if (!sync) return launch_kernel(ix, A, k_flat<KIND, false, 2, false, false>, sm);
+    return stats ? launch_kernel(ix, A, k_flat<KIND, false, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, false, 2, true, false>, sm);
 }
 
 int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
