@@ -114,7 +114,7 @@ __device__ void bsw_warp(const BswConst &P, const uint8_t *__restrict__ query, i
                 int M = d ? d + score_of(tc, qc[c], P.a, P.b) : 0;
                 Mv[c] = M;
                 fv[c] = lf;
-                if (in) { int t = M - oe_ins; t = t > 0 ? t : 0; lf = max(lf - e_ins, t); }
+                if (in) lf = __viaddmax_s32(lf, -e_ins, __viaddmax_s32(M, -oe_ins, 0));     // DPX: max(lf - e_ins, max(M - oe_ins, 0))
             }
             // ---- stitch F across lanes: exclusive prefix max of G = F_out + e_ins * (next column) ----
             int endcol = min(end, j0 + C);
@@ -141,13 +141,10 @@ __device__ void bsw_warp(const BswConst &P, const uint8_t *__restrict__ query, i
                 if (j == beg) f = 0;
                 else { f = max(fv[c], pg - e_ins * j); }
                 int e = E[c], M = Mv[c];
-                int h = max(max(M, e), f);
-                if (h < 0) h = 0;                  // f may be a large negative placeholder outside the chain
+                int h = __vimax3_s32_relu(M, e, f);   // DPX; relu: f may be a large negative placeholder outside the chain
                 newH[c] = hprev;                   // H(i, j-1); fixed up below for c == 0 and j == beg
                 if (in) {
-                    int t = M - oe_del; t = t > 0 ? t : 0;
-                    e -= e_del; e = e > t ? e : t;
-                    E[c] = e;
+                    E[c] = __viaddmax_s32(e, -e_del, __viaddmax_s32(M, -oe_del, 0));
                     int key = (h << 12) | j;
                     lkey = max(lkey, key);
                     hprev = h;
@@ -174,9 +171,7 @@ __device__ void bsw_warp(const BswConst &P, const uint8_t *__restrict__ query, i
                 int owner = (end - 1) / C;
                 h1_end = __shfl_sync(FULL, hlast, owner);
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) lkey = max(lkey, __shfl_xor_sync(FULL, lkey, o));
-            rowkey = lkey;
+            rowkey = __reduce_max_sync(FULL, lkey);
             cells += (u64)(end - beg);
         } else {
             // empty band: the reference still writes eh[end] = {h1, 0} (L199)
@@ -212,11 +207,8 @@ __device__ void bsw_warp(const BswConst &P, const uint8_t *__restrict__ query, i
                 llast = j;
             }
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            lfirst = min(lfirst, __shfl_xor_sync(FULL, lfirst, o));
-            llast = max(llast, __shfl_xor_sync(FULL, llast, o));
-        }
+        lfirst = __reduce_min_sync(FULL, lfirst);
+        llast = __reduce_max_sync(FULL, llast);
         int nbeg = lfirst < end ? lfirst : end;
         int jl = llast >= nbeg ? llast : nbeg - 1;
         beg = nbeg;

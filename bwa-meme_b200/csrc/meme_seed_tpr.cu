@@ -31,7 +31,12 @@
 
 namespace tpr {
 
+#ifndef TPR_THREADS
 #define TPR_THREADS 256
+#endif
+#ifndef FLAT_MINB
+#define FLAT_MINB 2                     // resident CTAs per SM the flat kernel is compiled for (registers = 64 K / threads)
+#endif
 #define TPR_RW 10                       // 64-bit words of a packed read (MEME_MAX_READ_LEN / 32)
 #define TPR_SW 31                       // shared 32-bit words per thread: 20 read + 10 N mask + 1 pad (odd stride)
 
@@ -905,7 +910,9 @@ static int launch_tpr(meme_index_t *ix, const Args &A)
     if (ix->v.pos_wide)
         return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>, sm);
     if (!sync) return launch_kernel(ix, A, k_flat<KIND, false, 2, false, false>, sm);
-    return stats ? launch_kernel(ix, A, k_flat<KIND, false, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, false, 2, true, false>, sm);
+    static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 2;   // resident CTAs per SM asked of the compiler
+    if (minb == 3 && !stats) return launch_kernel(ix, A, k_flat<KIND, false, 3, true, false>, sm);
+    return stats ? launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, false>, sm);
 }
 
 int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt)
