@@ -312,9 +312,8 @@ def main_ours(a):
 
     # ---- end-to-end through the C ABI with host buffers: `e2e` ----
     def e2e_step():
-        ix.seed_upload_ptr(host.data_ptr(), offs_pinned.data_ptr(), n)
-        ix.seed_run(opt)
-        return ix.seed_download(copy=False)
+        # one meme_seed_batch call on host buffers: sub-batches pipeline H2D / kernels / D2H inside the library
+        return ix.seed_batch_ptr(host.data_ptr(), offs_pinned.data_ptr(), n, opt)
 
     e2e_step()
     sync_all()

@@ -172,6 +172,16 @@ class MemeIndex:
                                      C.byref(res)), "meme_seed_batch")
         return self._wrap(res)
 
+    def seed_batch_ptr(self, codes_ptr: int, offsets_ptr: int, n_reads: int, opt: SeedOpt) -> dict:
+        """meme_seed_batch on raw host pointers; the lists stay in the handle's pinned arrays (no numpy copy)."""
+        res = SeedResult()
+        _check(lib().meme_seed_batch(self.h, C.c_void_p(codes_ptr), C.c_void_p(offsets_ptr), n_reads, C.byref(opt), C.byref(res)),
+               "meme_seed_batch")
+        return {"n_reads": int(res.n_reads), "n_smems": int(res.n_smems), "n_hits": int(res.n_hits), "_res": res}
+
+    def wrap_result(self, r: dict) -> dict:
+        return self._wrap(r["_res"])
+
     def seed_upload(self, codes: np.ndarray, offsets: np.ndarray):
         _check(lib().meme_seed_upload(self.h, codes.ctypes.data, offsets.ctypes.data, len(offsets) - 1), "meme_seed_upload")
 

@@ -45,6 +45,14 @@ struct IndexView {
     int bit_shift;         // 64 - bits
 };
 
+// second set of input/output buffers of the pipelined batch path (meme_seed.cu: seed_batch_pipelined)
+struct SeedAlt {
+    uint8_t *d_codes; size_t cap_codes;
+    int64_t *d_read_off, *d_smem_off, *d_hit_off; size_t cap_reads;
+    meme_smem_t *d_smems; size_t cap_smems;
+    u64 *d_hits; size_t cap_hits;
+};
+
 struct meme_index {
     int device;
     IndexView v;
@@ -82,6 +90,11 @@ struct meme_index {
     void *d_t2; size_t cap_t2;
     cudaEvent_t ev[6];                    // k_seed start/stop, offsets start/stop, k_gather start/stop
     int ev_ready;
+    // ---- pipelined batch ----
+    SeedAlt alt;
+    cudaStream_t copy_stream;
+    cudaEvent_t pe[6];                    // per buffer set: input arrived [0,1], run finished [2,3], lists drained [4,5]
+    int piped; int64_t piped_reads;
 };
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);

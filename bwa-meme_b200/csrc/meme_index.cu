@@ -303,6 +303,9 @@ extern "C" void meme_index_free(meme_index_t *ix)
                    ix->d_packed, ix->d_nmask, ix->d_rd_full, ix->d_rd_maxref, ix->d_pool_keys, ix->d_pool_vals, ix->d_pool_keys2,
                    ix->d_pool_vals2, ix->d_t2};
     for (void *p : dev) if (p) cudaFree(p);
+    void *alt[] = {ix->alt.d_codes, ix->alt.d_read_off, ix->alt.d_smem_off, ix->alt.d_hit_off, ix->alt.d_smems, ix->alt.d_hits};
+    for (void *p : alt) if (p) cudaFree(p);
+    if (ix->copy_stream) { cudaStreamDestroy(ix->copy_stream); for (int k = 0; k < 6; k++) cudaEventDestroy(ix->pe[k]); }
     void *host[] = {ix->h_smems, ix->h_hits, ix->h_smem_off, ix->h_hit_off, ix->h_ctrl};
     for (void *p : host) if (p) cudaFreeHost(p);
     for (int k = 0; k < 6; k++) if (ix->ev[k]) cudaEventDestroy(ix->ev[k]);

@@ -24,6 +24,8 @@
 //   * results are canonical (they depend on the suffix array only), which is what makes this
 //     cooperative formulation bit-exact with the reference's sequential one.
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <utility>
 #include "meme_common.cuh"
 
 #define BLOCK_THREADS 256
@@ -728,19 +730,9 @@ __global__ void k_gather(IndexView ix, const RawSmem *__restrict__ pool, const u
 // ---------------------------------------------------------------------------------------------
 // host API
 // ---------------------------------------------------------------------------------------------
-extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads)
+// input buffers and the per-read arrays of a batch of up to n_reads reads / n_codes bases
+static int seed_alloc_inputs(meme_index_t *ix, int64_t n_reads, int64_t n_codes)
 {
-    if (!ix || !read_off || n_reads < 0 || (n_reads > 0 && !codes)) { meme_set_error("bad argument"); return MEME_E_ARG; }
-    CUDA_TRY(cudaSetDevice(ix->device));
-    int64_t n_codes = n_reads ? read_off[n_reads] - read_off[0] : 0;
-    if (n_reads && read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
-    for (int64_t i = 0; i < n_reads; i++) {
-        int64_t len = read_off[i + 1] - read_off[i];
-        if (len < 0 || len > MEME_MAX_READ_LEN) {
-            meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
-            return MEME_E_ARG;
-        }
-    }
     int rc;
     cudaStream_t st = ix->stream;
     if ((rc = meme_grow_device((void **)&ix->d_codes, &ix->cap_codes, (size_t)n_codes + 64, 1, st))) return rc;
@@ -757,6 +749,26 @@ extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const in
             if ((rc = meme_grow_device(bufs[k], &dummy, c, el[k], st))) return rc;
         }
     }
+    return MEME_OK;
+}
+
+extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads)
+{
+    if (!ix || !read_off || n_reads < 0 || (n_reads > 0 && !codes)) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    int64_t n_codes = n_reads ? read_off[n_reads] - read_off[0] : 0;
+    if (n_reads && read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
+    for (int64_t i = 0; i < n_reads; i++) {
+        int64_t len = read_off[i + 1] - read_off[i];
+        if (len < 0 || len > MEME_MAX_READ_LEN) {
+            meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
+            return MEME_E_ARG;
+        }
+    }
+    int rc;
+    cudaStream_t st = ix->stream;
+    if ((rc = seed_alloc_inputs(ix, n_reads, n_codes))) return rc;
+    ix->piped = 0;
     if (n_codes) CUDA_TRY(cudaMemcpyAsync(ix->d_codes, codes, (size_t)n_codes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ix->d_read_off, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     ix->n_reads = n_reads;
@@ -938,6 +950,11 @@ extern "C" int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out)
     int64_t n = ix->n_reads;
     int64_t ns = n ? (int64_t)ix->h_ctrl[32] : 0, nh = n ? (int64_t)ix->h_ctrl[33] : 0;
     int rc;
+    if (ix->piped) {                       // the pipelined batch already assembled the lists on the host
+        out->n_reads = ix->piped_reads; out->n_smems = ns; out->n_hits = nh;
+        out->smems = ix->h_smems; out->smem_off = ix->h_smem_off; out->hit_off = ix->h_hit_off; out->hits = (const uint64_t *)ix->h_hits;
+        return MEME_OK;
+    }
     if ((rc = meme_grow_pinned((void **)&ix->h_smems, &ix->hcap_smems, (size_t)ns + 1, sizeof(meme_smem_t)))) return rc;
     if ((rc = meme_grow_pinned((void **)&ix->h_hits, &ix->hcap_hits, (size_t)nh + 1, 8))) return rc;
     size_t c0 = ix->hcap_off;
@@ -959,10 +976,174 @@ extern "C" int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out)
     return MEME_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined batch: the chunk (the reference's -K batch, src/fastmap.cpp:L743) is cut into sub-batches of
+// MEME_SEED_CHUNK reads; while sub-batch c runs, the lists of c-1 drain to the host and the reads of c+1 arrive,
+// on a second stream with a second set of input/output buffers.  Results land in one set of pinned arrays,
+// exactly as the one-shot path delivers them.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_add_base(int64_t *__restrict__ a, int64_t n, int64_t base)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += base;
+}
+
+static void seed_swap_sets(meme_index_t *ix)
+{
+    SeedAlt &a = ix->alt;
+    std::swap(ix->d_codes, a.d_codes); std::swap(ix->cap_codes, a.cap_codes);
+    std::swap(ix->d_read_off, a.d_read_off); std::swap(ix->d_smem_off, a.d_smem_off); std::swap(ix->d_hit_off, a.d_hit_off);
+    std::swap(ix->d_smems, a.d_smems); std::swap(ix->cap_smems, a.cap_smems);
+    std::swap(ix->d_hits, a.d_hits); std::swap(ix->cap_hits, a.cap_hits);
+}
+
+// grow a pinned array, keeping its first `keep` elements
+static int grow_pinned_keep(void **p, size_t *cap, size_t need, size_t elem, size_t keep)
+{
+    if (need <= *cap && *p) return MEME_OK;
+    size_t ncap = need + need / 4 + 64;
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, ncap * elem);
+    if (e != cudaSuccess) { meme_set_error("cudaMallocHost(%zu bytes): %s", ncap * elem, cudaGetErrorString(e)); return MEME_E_NOMEM; }
+    if (*p) { if (keep) memcpy(q, *p, keep * elem); cudaFreeHost(*p); }
+    *p = q; *cap = ncap;
+    return MEME_OK;
+}
+
+static int64_t seed_chunk_reads()
+{
+    const char *e = getenv("MEME_SEED_CHUNK");
+    long long v = e ? atoll(e) : (1ll << 20);
+    return v < 1024 ? 1024 : (int64_t)v;
+}
+
+static int seed_batch_pipelined(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n,
+                                const meme_seed_opt_t *opt, meme_seed_result_t *out, int64_t chunk)
+{
+    CUDA_TRY(cudaSetDevice(ix->device));
+    if (read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
+    for (int64_t i = 0; i < n; i++) {
+        int64_t len = read_off[i + 1] - read_off[i];
+        if (len < 0 || len > MEME_MAX_READ_LEN) {
+            meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
+            return MEME_E_ARG;
+        }
+    }
+    const int64_t K = (n + chunk - 1) / chunk;
+    int64_t max_codes = 0;
+    for (int64_t c = 0; c < K; c++) {
+        int64_t r0 = c * chunk, r1 = r0 + chunk < n ? r0 + chunk : n;
+        max_codes = std::max(max_codes, read_off[r1] - read_off[r0]);
+    }
+    int rc;
+    cudaStream_t st = ix->stream;
+    if ((rc = seed_alloc_inputs(ix, chunk, max_codes))) return rc;
+    SeedAlt &A = ix->alt;
+    if (A.cap_reads != ix->cap_reads) {                 // second set of per-read offset arrays, same capacity as the first
+        CUDA_TRY(cudaDeviceSynchronize());
+        void **bufs[] = {(void **)&A.d_read_off, (void **)&A.d_smem_off, (void **)&A.d_hit_off};
+        for (void **b : bufs) {
+            if (*b) { CUDA_TRY(cudaFree(*b)); *b = nullptr; }
+            size_t dummy = 0;
+            if ((rc = meme_grow_device(b, &dummy, ix->cap_reads, 8, st))) return rc;
+        }
+        A.cap_reads = ix->cap_reads;
+    }
+    if ((rc = meme_grow_device((void **)&A.d_codes, &A.cap_codes, (size_t)max_codes + 64, 1, st))) return rc;
+    if (!ix->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 6; k++) CUDA_TRY(cudaEventCreateWithFlags(&ix->pe[k], cudaEventDisableTiming));
+    }
+    cudaStream_t cs = ix->copy_stream;
+    cudaEvent_t *e_h2d = ix->pe, *e_run = ix->pe + 2, *e_d2h = ix->pe + 4;      // indexed by set (chunk & 1)
+    {
+        size_t c0 = ix->hcap_off;
+        if ((rc = meme_grow_pinned((void **)&ix->h_smem_off, &c0, (size_t)n + 1, 8))) return rc;
+        c0 = ix->hcap_off;
+        if ((rc = meme_grow_pinned((void **)&ix->h_hit_off, &c0, (size_t)n + 1, 8))) return rc;
+        ix->hcap_off = c0;
+    }
+    struct Part { int64_t r0, n, tot_s, tot_h, base_s, base_h; } part[2] = {};
+    int64_t base_s = 0, base_h = 0;
+    u64 acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    // input of sub-batch c -> the buffers named by the arguments (the set that is NOT installed while c-1 runs)
+    auto h2d = [&](int64_t c, uint8_t *d_codes, int64_t *d_read_off) -> int {
+        int64_t r0 = c * chunk, r1 = r0 + chunk < n ? r0 + chunk : n, nr = r1 - r0;
+        int64_t nc = read_off[r1] - read_off[r0];
+        if (nc) CUDA_TRY(cudaMemcpyAsync(d_codes, codes + read_off[r0], (size_t)nc, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(d_read_off, read_off + r0, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, cs));
+        if (read_off[r0]) k_add_base<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, cs>>>(d_read_off, nr + 1, -read_off[r0]);
+        CUDA_TRY(cudaEventRecord(e_h2d[c & 1], cs));
+        return MEME_OK;
+    };
+    // lists of a finished sub-batch -> the pinned arrays, offsets rebased to the whole batch
+    auto d2h = [&](const Part &p, int set, const meme_smem_t *d_smems, const u64 *d_hits, int64_t *d_smem_off, int64_t *d_hit_off) -> int {
+        int r;
+        if ((size_t)(p.base_s + p.tot_s) + 1 > ix->hcap_smems || (size_t)(p.base_h + p.tot_h) + 1 > ix->hcap_hits || !ix->h_smems || !ix->h_hits) {
+            CUDA_TRY(cudaStreamSynchronize(cs));        // earlier copies target the old arrays
+            // first call: size for the whole batch from the density seen so far
+            double scale = (double)n / (double)(p.r0 + p.n) * 1.1;
+            size_t want_s = (size_t)((double)(p.base_s + p.tot_s) * scale) + 1024, want_h = (size_t)((double)(p.base_h + p.tot_h) * scale) + 1024;
+            if ((r = grow_pinned_keep((void **)&ix->h_smems, &ix->hcap_smems, want_s, sizeof(meme_smem_t), (size_t)p.base_s))) return r;
+            if ((r = grow_pinned_keep((void **)&ix->h_hits, &ix->hcap_hits, want_h, 8, (size_t)p.base_h))) return r;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(cs, e_run[set], 0));
+        unsigned g = (unsigned)((p.n + 1 + 255) / 256);
+        if (p.base_s) k_add_base<<<g, 256, 0, cs>>>(d_smem_off, p.n + 1, p.base_s);
+        if (p.base_h) k_add_base<<<g, 256, 0, cs>>>(d_hit_off, p.n + 1, p.base_h);
+        if (p.tot_s) CUDA_TRY(cudaMemcpyAsync(ix->h_smems + p.base_s, d_smems, (size_t)p.tot_s * sizeof(meme_smem_t), cudaMemcpyDeviceToHost, cs));
+        if (p.tot_h) CUDA_TRY(cudaMemcpyAsync(ix->h_hits + p.base_h, d_hits, (size_t)p.tot_h * 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_smem_off + p.r0, d_smem_off, (size_t)(p.n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_hit_off + p.r0, d_hit_off, (size_t)(p.n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaEventRecord(e_d2h[set], cs));
+        return MEME_OK;
+    };
+    CUDA_TRY(cudaStreamSynchronize(st));                // the handle's buffers are idle from here on
+    if ((rc = h2d(0, ix->d_codes, ix->d_read_off))) return rc;
+    for (int64_t c = 0; c < K; c++) {
+        const int set = (int)(c & 1);
+        if (c >= 1) {
+            seed_swap_sets(ix);                          // installed: set of c; ix->alt: set of c-1 (= set of c+1)
+            if ((rc = d2h(part[set ^ 1], set ^ 1, A.d_smems, A.d_hits, A.d_smem_off, A.d_hit_off))) return rc;
+        }
+        if (c + 1 < K && (rc = h2d(c + 1, A.d_codes, A.d_read_off))) return rc;   // after the d2h wait on e_run[c-1]
+        int64_t r0 = c * chunk, r1 = r0 + chunk < n ? r0 + chunk : n;
+        CUDA_TRY(cudaStreamWaitEvent(st, e_h2d[set], 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, e_d2h[set], 0));             // the lists of c-2 have left this set
+        ix->n_reads = r1 - r0; ix->n_codes = read_off[r1] - read_off[r0]; ix->ran = 0;
+        if ((rc = meme_seed_run(ix, opt))) return rc;
+        CUDA_TRY(cudaEventRecord(e_run[set], st));
+        Part &p = part[set];
+        p.r0 = r0; p.n = r1 - r0; p.tot_s = (int64_t)ix->h_ctrl[32]; p.tot_h = (int64_t)ix->h_ctrl[33];
+        p.base_s = base_s; p.base_h = base_h;
+        base_s += p.tot_s; base_h += p.tot_h;
+        const int slot[7] = {8, 9, 10, 11, 4, 40, 41};
+        for (int k = 0; k < 7; k++) acc[k] += ix->h_ctrl[slot[k]];
+    }
+    {
+        const int set = (int)((K - 1) & 1);
+        if ((rc = d2h(part[set], set, ix->d_smems, ix->d_hits, ix->d_smem_off, ix->d_hit_off))) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    {
+        const int slot[7] = {8, 9, 10, 11, 4, 40, 41};
+        for (int k = 0; k < 7; k++) ix->h_ctrl[slot[k]] = acc[k];
+    }
+    ix->h_ctrl[32] = (u64)base_s; ix->h_ctrl[33] = (u64)base_h;
+    ix->piped = 1; ix->piped_reads = n; ix->ran = 1;
+    out->n_reads = n; out->n_smems = base_s; out->n_hits = base_h;
+    out->smems = ix->h_smems; out->smem_off = ix->h_smem_off; out->hit_off = ix->h_hit_off; out->hits = (const uint64_t *)ix->h_hits;
+    return MEME_OK;
+}
+
 extern "C" int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
                                const meme_seed_opt_t *opt, meme_seed_result_t *out)
 {
     int rc;
+    if (!ix || !out || !opt || !read_off || n_reads < 0 || (n_reads > 0 && !codes)) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    const int64_t chunk = seed_chunk_reads();
+    if (n_reads > chunk + chunk / 2) return seed_batch_pipelined(ix, codes, read_off, n_reads, opt, out, chunk);
     if ((rc = meme_seed_upload(ix, codes, read_off, n_reads))) return rc;
     if ((rc = meme_seed_run(ix, opt))) return rc;
     return meme_seed_download(ix, out);

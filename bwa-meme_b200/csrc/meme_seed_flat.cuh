@@ -25,6 +25,7 @@ enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 #define FLAT_SW 35
 #define FLAT_RD 2
 #define FLAT_NM 24
+#define FLAT_ANYN 34                      // OR of the N-mask words (the pad word)
 #define FLAT_STG 24                       // staging words per thread: key low halves, key high halves, positions
 
 // Tuning switches (profiles/r1/experiments has the measurements behind the defaults).
@@ -101,12 +102,16 @@ __device__ __noinline__ void load_task_words(const Args &A, u32 rid, u32 *sm)
 {
     const u64 *src = A.packed + (u64)rid * TPR_RW;
     const u32 *nsrc = A.nmask + (u64)rid * TPR_RW;
+    u32 any = 0;
 #pragma unroll
     for (int w = 0; w < TPR_RW; w++) {
         u64 v = __ldg(src + w);
         sm[FLAT_RD + 2 * w] = (u32)v; sm[FLAT_RD + 2 * w + 1] = (u32)(v >> 32);
-        sm[FLAT_NM + w] = __ldg(nsrc + w);
+        u32 m = __ldg(nsrc + w);
+        sm[FLAT_NM + w] = m;
+        any |= m;
     }
+    sm[FLAT_ANYN] = any;                   // most reads have no N: next_n / prev_n answer without scanning
 }
 
 template <int KIND>
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     };
     auto is_n = [&](int p) -> bool { return (sm[FLAT_NM + (p >> 5)] >> (p & 31)) & 1; };
     auto next_n = [&](int from) -> int {
+        if (!sm[FLAT_ANYN]) return L;
         int w = from >> 5;
         u32 m = sm[FLAT_NM + w] >> (from & 31);
         if (m) { int p = from + __ffs(m) - 1; return p < L ? p : L; }
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         return L;
     };
     auto prev_n = [&](int p) -> int {
+        if (!sm[FLAT_ANYN]) return -1;
         int w = p >> 5;
         u32 m = sm[FLAT_NM + w] & (0xffffffffu >> (31 - (p & 31)));
         if (m) return w * 32 + 31 - __clz(m);

@@ -169,3 +169,26 @@ def test_invariants_at_scale(oracle, pkg, mid_index):
     assert (got_cnt == np.diff(want["smem_off"])).all()
     got_hits = np.array([a["hit_off"][i + 1] - a["hit_off"][i] for i in sel])
     assert (got_hits == np.diff(want["hit_off"])).all()
+
+
+def test_pipelined_batch_equals_one_shot(oracle, pkg, gidx, golden_index, golden_genome, monkeypatch):
+    """meme_seed_batch cuts large batches into sub-batches that overlap copies and kernels (MEME_SEED_CHUNK reads
+    each): the assembled lists must equal the one-shot result and the oracle, including a ragged last sub-batch."""
+    from bwa_meme_b200 import synth
+    codes, offs = synth.make_reads(golden_genome, 5300, 150, seed=77, n_frac=0.05, len_jitter=60)
+    n = len(offs) - 1
+    monkeypatch.setenv("MEME_SEED_CHUNK", "100000000")
+    one = gidx[3].seed(codes, offs)
+    monkeypatch.setenv("MEME_SEED_CHUNK", "1024")
+    for _ in range(2):                                   # second call reuses the pinned arrays and both buffer sets
+        got = gidx[3].seed(codes, offs)
+        for k in ("smem_off", "hit_off", "hits"):
+            assert (got[k] == one[k]).all(), k
+        assert (got["smems"] == one["smems"]).all()
+    oix = oracle.OracleIndex(golden_index, 3)
+    want = oix.seed(codes, offs)
+    oix.close()
+    assert _canon(oracle, got, n) == _canon(oracle, want, n)
+    monkeypatch.setenv("MEME_SEED_CHUNK", "100000000")
+    again = gidx[3].seed(codes[: offs[700]], offs[:701])   # back to the one-shot path on the same handle
+    assert (again["hits"] == one["hits"][: one["hit_off"][700]]).all()
