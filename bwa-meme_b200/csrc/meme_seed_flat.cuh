@@ -21,14 +21,19 @@ enum {
 enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 
 // per-thread shared words: [0,2) zero pair (read word -1), [2,22) packed read words 0..9, [22,24) zero pair
-// (read word 10), [24,34) N-mask words, 1 pad (odd stride: conflict-free), then FLAT_STG staging words (rolled kinds)
+// (read word 10), [24,34) N-mask words, the OR of the N masks, then FLAT_STG staging words (stride 75: odd, conflict-free)
 #define FLAT_SW 35
 #define FLAT_RD 2
 #define FLAT_NM 24
 #define FLAT_ANYN 34                      // OR of the N-mask words (the pad word)
-#define FLAT_STG 24                       // staging words per thread: key low halves, key high halves, positions
 
 // Tuning switches (profiles/r1/experiments has the measurements behind the defaults).
+// Control rounds per iteration: a lane that needs more than this many passes through the switch before its next
+// memory request sits the memory phase out and joins the first round of the next iteration, where more lanes share
+// its state (the late rounds run with 1-3 lanes).
+#ifndef FLAT_MAXROUNDS
+#define FLAT_MAXROUNDS 1000
+#endif
 #ifndef FLAT_VOTE
 #define FLAT_VOTE 1                       // 1: lanes re-enter the control switch together (vote-controlled loop)
 #endif
@@ -38,16 +43,19 @@ enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 #define FLAT_MERGE(KIND) ((KIND) == 3)
 #endif
 #define FLAT_GOTO(label, st) do { if (FLAT_MERGE(KIND)) { state = st; goto next_state; } else goto label; } while (0)
-// Block-probe compare loop: fully unrolled (8) keeps the 8 keys/positions in registers; rolled (< 8) stages them in
-// FLAT_STG more shared words per thread and takes ~250 instructions out of the hot loop (the loads stay unrolled so
-// that all 16 are in flight).  The kernels that walk the level/extension code as well (T2, T3) only fit the 32 KB
-// instruction cache rolled ("no instruction" stalls 3.8 -> 0.55 per issue, ncu).
-#ifdef FLAT_BLK_UNROLL
-#define FLAT_BU(KIND) (FLAT_BLK_UNROLL)
-#else
-#define FLAT_BU(KIND) 1
+// Block probes are staged in shared memory: cp.async copies the 8 keys (two halves) and positions straight into the
+// thread's staging words (a rolled loop with every load in flight and no register staging), the rolled compare loop
+// reads them back and leaves the 8 LCPs in one of two LCP buffers (the block a search is located in keeps its LCPs
+// while extension probes use the other buffer).  Against fully unrolled register code this took ~600 instructions
+// out of the hot loop, which is what lets the level/extension code of T2 and T3 stay inside the 32 KB instruction
+// cache ("no instruction" stalls 3.8 -> 0.6 per issue, ncu; profiles/r1/experiments).
+#ifndef FLAT_BLK_UNROLL
+#define FLAT_BLK_UNROLL 1
 #endif
-template <int KIND> __host__ __device__ constexpr int flat_sw() { return FLAT_SW + (FLAT_BU(KIND) == 8 ? 0 : FLAT_STG); }
+#define FLAT_STG 40                       // key low halves [0,8), key high halves [8,16), positions [16,24), LCPs [24,32) [32,40)
+#define FLAT_LCP0 24
+#define FLAT_LCP1 32
+template <int KIND> __host__ __device__ constexpr int flat_sw() { return FLAT_SW + FLAT_STG; }
 
 template <bool WIDE> struct IdxT { typedef u32 type; };
 template <> struct IdxT<true> { typedef u64 type; };
@@ -135,8 +143,7 @@ template <int KIND, bool WIDE, int MINB, bool SYNC, bool STATS>
 __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A)
 {
     typedef typename IdxT<WIDE>::type idx_t;
-    constexpr int BU = FLAT_BU(KIND);
-    constexpr bool STG = BU != 8;
+    constexpr int BU = FLAT_BLK_UNROLL;
     constexpr int SW = flat_sw<KIND>();
     extern __shared__ u32 smem[];
     u32 *const sm = &smem[threadIdx.x * SW];
@@ -152,11 +159,10 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     // ---- request + probe results ----
     int mreq = M_NONE, m_count = 0, m_cap = 0, m_ldk = 0;
     idx_t m_base = 0; long long m_stride = 1; const RmiRec *m_rec = nullptr;
-    u64 r_lo = 0, r_hi = 0; u32 r_less = 0, undet = 0; int r_count = 0;
-    u32 pp[8]; u64 pphi = 0; int pac_e = 0, pac_k0 = 0;
+    u32 r_less = 0, undet = 0; int r_count = 0;
+    int rl_off = FLAT_LCP0, bl_off = FLAT_LCP1;          // LCP buffers of the latest probe / of the located block
+    u64 pphi = 0; int pac_e = 0, pac_k0 = 0;
     u64 ld_val = 0; double rmi_a = 0, rmi_b = 0; u64 rmi_e = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) pp[j] = 0;
     // ---- query ----
     int q_strand = 0, q_from = 0, q_V = 0; u64 q0 = 0;
     // ---- search ----
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     int s_pivot = 0, s_need = 1, s_msl = 19, s_mode = ST_RMI, d_ret = 0, it = 0;
     idx_t s_hint = 0, center = 0, lo_b = 0, hi_b = 0, k_stride = 0, k_pa = 0, base = 0;
     u64 rad_lo = 0, rad_hi = 0;
-    int nvalid = 0; u64 b_lo = 0, b_hi = 0;
+    int nvalid = 0;
     idx_t lo = 0, hi = 0; int nbl = 0, nbr = 0, lev = 0;
     u64 lv_limit = 0; int lv_ret = 0;
     // ---- extension ----
@@ -212,13 +218,12 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         for (w--; w >= 0; w--) { u32 x = sm[FLAT_NM + w]; if (x) return w * 32 + 31 - __clz(x); }
         return -1;
     };
-    auto get16 = [](u64 a, u64 b, int j) -> int { return (int)(((j < 4 ? a : b) >> (16 * (j & 3))) & 0xffff); };
-#define RL(j) get16(r_lo, r_hi, (j))
-#define BL(j) get16(b_lo, b_hi, (j))
+#define RL(j) ((int)stg[rl_off + (j)])
+#define BL(j) ((int)stg[bl_off + (j)])
     auto lead_less = [&]() -> int { int c = __ffs(~r_less) - 1; return c > r_count ? r_count : c; };
     auto req_block = [&](idx_t b, long long stride, int count, int cap) {
         m_base = b; m_stride = stride; m_count = count; m_cap = cap; r_count = count;
-        if (count > 0) mreq = M_BLOCK; else { mreq = M_NONE; r_lo = r_hi = 0; r_less = 0; }
+        if (count > 0) mreq = M_BLOCK; else { mreq = M_NONE; r_less = 0; }
     };
     auto req_contig = [&](idx_t b, int cap) {
         if (n >= 8 && b > n - 8) b = n - 8;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             if (__all_sync(0xffffffffu, done)) break;
         }
 #if FLAT_VOTE
-        while (__any_sync(0xffffffffu, !done && mreq == M_NONE)) if (!done && mreq == M_NONE) {
+        for (int round = 0; round < FLAT_MAXROUNDS && __any_sync(0xffffffffu, !done && mreq == M_NONE); round++) if (!done && mreq == M_NONE) {
 #else
         while (!done && mreq == M_NONE) {
 #endif
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             case P_LOCATED:
             located:
                 // ---- first level = maximal lcp in the block, [lo,hi] = its interval ----
-                b_lo = r_lo; b_hi = r_hi;
+                bl_off = rl_off; rl_off ^= FLAT_LCP0 ^ FLAT_LCP1;       // keep this block's LCPs; later probes use the other buffer
                 {
                     int m = -1, first = 0;
 #pragma unroll
@@ -637,7 +642,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         u64 buf[8];
         const int req = done ? (int)M_NONE : mreq;
         if (STATS && req != M_NONE) st_iter++;
-        if (req == M_BLOCK && STG) {
+        if (req == M_BLOCK) {
             // asynchronous copies straight into the staging words: a rolled loop with every load in flight
             u32 dst = (u32)__cvta_generic_to_shared(stg);
             const char *kp = reinterpret_cast<const char *>(ix.keys + m_base);
@@ -658,27 +663,8 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 for (int j = 0; j < 8; j++) { if (j < m_count) h |= (u64)__ldg(ix.pos_hi + idx) << (8 * j); idx += (idx_t)m_stride; }
                 pphi = h;
             }
-        } else if (req == M_BLOCK) {
-            idx_t idx = m_base;
-            const idx_t step = (idx_t)m_stride;
-            u64 h = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (j < m_count) {
-                    buf[j] = has_keys ? __ldg(ix.keys + idx) : 0;
-                    pp[j] = __ldg(ix.pos_lo + idx);
-                    if (WIDE) h |= (u64)__ldg(ix.pos_hi + idx) << (8 * j);
-                }
-                idx += step;
-            }
-            if (WIDE) pphi = h;
         } else if (req == M_PAC) {
-            u32 v;
-            if (!STG) {
-                v = pp[0];
-#pragma unroll
-                for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
-            } else v = stg[16 + pac_e];
+            const u32 v = stg[16 + pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
@@ -707,54 +693,43 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         if (SYNC) __syncwarp();
         // =========================== compare phase ===========================
         if (req == M_BLOCK) {
-            u64 lo16 = 0, hi16 = 0; u32 less = 0, und = 0;
-            if (STG) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            u32 less = 0, und = 0;
+            const u32 qlo = (u32)q0, qhi = (u32)(q0 >> 32);
+            u32 *const rl = stg + rl_off;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll BU
-            for (int j = 0; j < 8; j++) {
-                if (j < m_count) {
-                    const u32 klo = STG ? stg[j] : (u32)buf[j], khi = STG ? stg[8 + j] : (u32)(buf[j] >> 32);
-                    const u32 pj = STG ? stg[16 + j] : pp[j];
-                    (void)0;
-                    int cap;
-                    if (WIDE) {
-                        u64 p = (u64)pj | (((pphi >> (8 * j)) & 0xff) << 32);
-                        u64 ref_len = ix.sa_num - p;
-                        cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
-                    } else {
-                        u32 ref_len = (u32)n - pj;
-                        cap = (int)min(ref_len, (u32)m_cap);
-                    }
-                    int l;
-                    if (!has_keys) { und |= 1u << j; l = 0; }
-                    else {
-                        const u32 xl = klo ^ (u32)q0, xh = khi ^ (u32)(q0 >> 32);
-                        if (xl | xh) {
-                            // first differing base, in 32-bit halves (16 bases each)
-                            const bool hi_half = xl == 0;
-                            const u32 xx = hi_half ? xh : xl;
-                            const u32 rr = hi_half ? khi : klo;
-                            const u32 qq = hi_half ? (u32)(q0 >> 32) : (u32)q0;
-                            const int sh = (__ffs((int)xx) - 1) & ~1;
-                            const int b = (sh >> 1) + (hi_half ? 16 : 0);
-                            if (b >= cap) l = cap;
-                            else { l = b; if (((rr >> sh) & 3) < ((qq >> sh) & 3)) less |= 1u << j; }
-                        } else if (32 >= cap) l = cap;
-                        else { und |= 1u << j; l = 32; }
-                    }
-                    if (j < 4) lo16 |= (u64)l << (16 * j); else hi16 |= (u64)l << (16 * (j - 4));
+            for (int j = 0; j < m_count; j++) {
+                const u32 klo = stg[j], khi = stg[8 + j], pj = stg[16 + j];
+                int cap;
+                if (WIDE) {
+                    u64 p = (u64)pj | (((pphi >> (8 * j)) & 0xff) << 32);
+                    u64 ref_len = ix.sa_num - p;
+                    cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
+                } else {
+                    u32 ref_len = (u32)n - pj;
+                    cap = (int)min(ref_len, (u32)m_cap);
                 }
+                int l = 0;
+                if (!has_keys) und |= 1u << j;
+                else {
+                    // first differing base in 32-bit halves (16 bases each), branch-free; xx == 0: all 32 bases equal
+                    const u32 xl = klo ^ qlo, xh = khi ^ qhi;
+                    const bool hi_half = xl == 0;
+                    const u32 xx = hi_half ? xh : xl, rr = hi_half ? khi : klo, qq = hi_half ? qhi : qlo;
+                    const int sh = (__ffs((int)xx) - 1) & 30;
+                    const int b = xx ? (sh >> 1) + (hi_half ? 16 : 0) : 32;
+                    l = min(b, cap);
+                    if (xx != 0 && b < cap && ((rr >> sh) & 3) < ((qq >> sh) & 3)) less |= 1u << j;
+                    if (xx == 0 && cap > 32) und |= 1u << j;
+                }
+                rl[j] = (u32)l;
             }
-            r_lo = lo16; r_hi = hi16; r_less = less; undet = und;
+            r_less = less; undet = und;
             if (und) { pac_e = __ffs(und) - 1; pac_k0 = has_keys ? 1 : 0; mreq = M_PAC; }
             else mreq = M_NONE;
         } else if (req == M_PAC) {
             if (STATS) st_pac++;
-            u32 v;
-            if (!STG) {
-                v = pp[0];
-#pragma unroll
-                for (int k = 1; k < 8; k++) v = pac_e == k ? pp[k] : v;
-            } else v = stg[16 + pac_e];
+            const u32 v = stg[16 + pac_e];
             u64 p = (u64)v | (WIDE ? ((pphi >> (8 * pac_e)) & 0xff) << 32 : 0);
             u64 ref_len = ix.sa_num - p;
             const int cap = ref_len < (u64)m_cap ? (int)ref_len : m_cap;
@@ -780,8 +755,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             }
             if (res < 0) pac_k0 += 4;                      // four more words of the same entry
             else {
-                u64 msk = 0xffffull << (16 * (pac_e & 3)), x = (u64)(res & 0xffff) << (16 * (pac_e & 3));
-                if (pac_e < 4) r_lo = (r_lo & ~msk) | x; else r_hi = (r_hi & ~msk) | x;
+                stg[rl_off + pac_e] = (u32)res;
                 if (less) r_less |= 1u << pac_e;
                 undet &= ~(1u << pac_e);
                 if (undet) { pac_e = __ffs(undet) - 1; pac_k0 = has_keys ? 1 : 0; }

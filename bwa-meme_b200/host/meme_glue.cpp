@@ -66,7 +66,26 @@ long g_seed_reads = 0;
 
 }  // namespace
 
-void meme_glue_set_prefix(const char *idx_prefix) { g_prefix = idx_prefix ? idx_prefix : ""; }
+static void ensure_index()
+{
+    if (g_index) return;
+    Api &a = api();
+    int mode = getenv("MEME_B200_MODE") ? atoi(getenv("MEME_B200_MODE")) : MODE;
+    int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = a.index_load(g_prefix.c_str(), mode, dev, &g_index);
+    if (rc) die("meme_index_load", rc);
+    fprintf(stderr, "[meme_b200] index %s resident on GPU %d (mode %d) in %.2f s\n", g_prefix.c_str(), dev, mode,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+
+// Called from memoryAllocLearned(): the index goes to HBM where the reference loads its own copy, i.e. outside
+// the per-chunk timers of mem_process_seqs ("Processed N reads in ... real sec", src/bwamem.cpp:L1968).
+void meme_glue_set_prefix(const char *idx_prefix)
+{
+    g_prefix = idx_prefix ? idx_prefix : "";
+    if (env_on("MEME_B200")) ensure_index();
+}
 
 // One GPU seeding call for the whole chunk (the reference seeds 512 reads at a time per thread).
 void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_learned)
@@ -74,13 +93,7 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     g_have = false;
     if (!use_learned || !env_on("MEME_B200") || n <= 0) return;
     Api &a = api();
-    if (!g_index) {
-        int mode = getenv("MEME_B200_MODE") ? atoi(getenv("MEME_B200_MODE")) : MODE;
-        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
-        int rc = a.index_load(g_prefix.c_str(), mode, dev, &g_index);
-        if (rc) die("meme_index_load", rc);
-        fprintf(stderr, "[meme_b200] index %s resident on GPU %d (mode %d)\n", g_prefix.c_str(), dev, mode);
-    }
+    ensure_index();
     auto t0 = std::chrono::steady_clock::now();
     // base codes: nst_nt4_table of the ASCII read; worker_bwt converts seqs[i].seq in place later
     // (src/bwamem.cpp:L1277-1280) and later stages rely on that, so the reads are not touched here
@@ -91,6 +104,7 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     for (int i = 0; i < n; i++) { off[i] = (int64_t)tot; tot += (size_t)seqs[i].l_seq; }
     off[n] = (int64_t)tot;
     codes.resize(tot + 1);
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++) {
         const unsigned char *s = (const unsigned char *)seqs[i].seq;
         uint8_t *d = codes.data() + off[i];
