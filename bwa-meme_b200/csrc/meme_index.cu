@@ -200,7 +200,9 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
     IndexView &v = ix->v;
     v.sa_num = n;
     v.mode = mode;
-    v.pos_wide = n >= (1ull << 32);
+    // MEME_FORCE_WIDE=1 (tests): treat a small index as a >= 2^32-entry one, so that the 5-byte position arrays and
+    // the 64-bit-index kernel instantiations (GRCh38 scale) run on fixtures that fit a test
+    v.pos_wide = n >= (1ull << 32) || (getenv("MEME_FORCE_WIDE") && atoi(getenv("MEME_FORCE_WIDE")) != 0);
     u64 n_words = (n + 31) / 32 + 2;
     CUDA_TRY(cudaMalloc((void **)&ix->d_pac, n_words * 8));
     CUDA_TRY(cudaMemsetAsync(ix->d_pac, 0, n_words * 8, st));

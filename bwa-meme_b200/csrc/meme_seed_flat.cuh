@@ -37,10 +37,12 @@ enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 #ifndef FLAT_VOTE
 #define FLAT_VOTE 1                       // 1: lanes re-enter the control switch together (vote-controlled loop)
 #endif
-// Shared control code (start selection, search begin, located) entered as a state of its own, so that lanes arriving
-// from different states run it together.  Costs ~300 instructions of code; pays for the third-round kernel only.
+// Shared control code (start selection, search begin, located) can be entered as a state of its own, so that lanes
+// arriving from different states run it together.  Measured: more active lanes per instruction, but ~300 more
+// instructions of code and more passes through the switch; no gain for any kind once the kernels fit the instruction
+// cache (profiles/r1/experiments), so it is off.
 #ifndef FLAT_MERGE
-#define FLAT_MERGE(KIND) ((KIND) == 3)
+#define FLAT_MERGE(KIND) 0
 #endif
 #define FLAT_GOTO(label, st) do { if (FLAT_MERGE(KIND)) { state = st; goto next_state; } else goto label; } while (0)
 // Block probes are staged in shared memory: cp.async copies the 8 keys (two halves) and positions straight into the

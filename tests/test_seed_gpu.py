@@ -192,3 +192,30 @@ def test_pipelined_batch_equals_one_shot(oracle, pkg, gidx, golden_index, golden
     monkeypatch.setenv("MEME_SEED_CHUNK", "100000000")
     again = gidx[3].seed(codes[: offs[700]], offs[:701])   # back to the one-shot path on the same handle
     assert (again["hits"] == one["hits"][: one["hit_off"][700]]).all()
+
+
+@pytest.mark.parametrize("mode", [3, 1])
+def test_wide_index_kernels_on_golden_fixtures(oracle, pkg, golden_index, golden_reads, mid_index, mode, monkeypatch):
+    """GRCh38-scale indexes (sa_num >= 2^32) use 5-byte positions and the 64-bit-index kernel instantiations.
+    MEME_FORCE_WIDE runs exactly that code on the golden fixtures: results must equal the reference dumps / oracle."""
+    from bwa_meme_b200 import capi, synth
+    monkeypatch.setenv("MEME_FORCE_WIDE", "1")
+    ix = capi.MemeIndex(golden_index, mode=mode)
+    try:
+        for rl in (150, 250):
+            codes, offs = golden_reads[rl]
+            n = len(offs) - 1
+            want = oracle.parse_ref_dump(os.path.join(GOLDEN, f"smem_len{rl}.txt"), n)
+            assert _canon(oracle, ix.seed(codes, offs), n) == want
+    finally:
+        ix.close()
+    prefix, g = mid_index                                  # wide RMI windows + repeats: k-ary narrowing and galloping
+    codes, offs = synth.make_reads(g, 1500, 320, seed=9, n_frac=0.05, len_jitter=300)
+    n = len(offs) - 1
+    ix = capi.MemeIndex(prefix, mode=mode)
+    got = ix.seed(codes, offs)
+    ix.close()
+    oix = oracle.OracleIndex(prefix, mode)
+    want = oix.seed(codes, offs)
+    oix.close()
+    assert _canon(oracle, got, n) == _canon(oracle, want, n)
