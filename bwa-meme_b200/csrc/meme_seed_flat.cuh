@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             // =========================== control: one flat state machine ===========================
             switch (state) {
             case P_TASK:
+            c_task:                                         // task ends jump here: no extra pass through the switch
                 flush_counts(A, out, rid);
                 task = atomicAdd((unsigned long long *)&A.ctrl[C_WORK], 1ull);
                 if (task >= (u64)A.n_tasks) { done = true; break; }
@@ -295,8 +296,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 while (pivot < L && is_n(pivot)) pivot = (L - pivot < min_seed_len) ? L : pivot + 1;
                 if (pivot >= L) {
                     if (A.rd_full) { A.rd_full[rid] = full_match ? 1 : 0; A.rd_maxref[rid] = max_refpos; }
-                    state = P_TASK;
-                    break;
+                    goto c_task;
                 }
                 if (pivot != 0 && !is_n(pivot - 1)) { sp = pivot; goto d1_zz; }
                 // first search of a segment: always through the RMI
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 s_stepwise = false; d_ret = P_D1_F;
                 FLAT_GOTO(s_begin, P_SBEGIN);
             case P_D1_F:
+            c_d1_f:
                 if (KIND != 1) { state = P_TASK; break; }
                 if (ix.mode == 3 && lev == L) {              // whole read matched (L1870-1875)
                     mreq = M_LD; m_ldk = LD_POS; m_base = lo;
@@ -328,12 +329,14 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D1_L;
                 FLAT_GOTO(auto_start, P_AUTO);
             case P_D1_L:
+            c_d1_l:
                 if (KIND != 1) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
                 if (L - pivot < min_seed_len) { pivot = L; goto d1_loop; }
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D1_R;
                 FLAT_GOTO(auto_start, P_AUTO);
             case P_D1_R:
+            c_d1_r:
                 if (KIND != 1) { state = P_TASK; break; }
                 sp = pivot + lev;
                 pivot = sp;
@@ -347,19 +350,22 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 as_pv = pivot; as_right = true; as_emit = false; as_ret = P_D2_F;
                 FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_F:
+            c_d2_f:
                 if (KIND != 2) { state = P_TASK; break; }
                 next = pivot + lev; sp = pivot;
             d2_loop:
-                if (sp >= next) { state = P_TASK; break; }
+                if (sp >= next) goto c_task;
                 as_pv = pivot; as_right = false; as_emit = false; as_ret = P_D2_L;
                 FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_L:
+            c_d2_l:
                 if (KIND != 2) { state = P_TASK; break; }
                 pivot = pivot - lev + 1;
-                if (next - pivot < min_seed_len) { state = P_TASK; break; }
+                if (next - pivot < min_seed_len) goto c_task;
                 as_pv = pivot; as_right = true; as_emit = true; as_ret = P_D2_R;
                 FLAT_GOTO(auto_start, P_AUTO);
             case P_D2_R:
+            c_d2_r:
                 if (KIND != 2) { state = P_TASK; break; }
                 sp = pivot + lev;
                 pivot = sp;
@@ -375,13 +381,14 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                     if (V < min_seed_len) { pivot += V; continue; }
                     break;
                 }
-                if (pivot >= L - min_seed_len + 1) { state = P_TASK; break; }
+                if (pivot >= L - min_seed_len + 1) goto c_task;
                 s_pivot = pivot; q_strand = 0; s_emit = false; s_need = min_intv; s_msl = min_seed_len; s_stepwise = true;
                 d_ret = P_D3_S;
                 if (full_match) { s_mode = ST_EXACT; s_hint = max_refpos + pivot; s_isa = true; }
                 else { s_mode = ST_RMI; s_isa = false; }
                 FLAT_GOTO(s_begin, P_SBEGIN);
             case P_D3_S:
+            c_d3_s:
                 if (KIND != 3) { state = P_TASK; break; }
                 if (lev < min_seed_len) { pivot += min_seed_len; goto d3_loop; }
                 r3_last_lo = lo; r3_last_cnt = 0; it = 0;
@@ -556,16 +563,10 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
                 }
                 if (KIND != 3 && s_emit && lev >= s_msl) push(s_pivot, s_pivot + lev, lo, (u64)(hi - lo) + 1);
             search_done:
-                switch (d_ret) {
-                case P_D1_F: state = P_D1_F; break;
-                case P_D1_L: state = P_D1_L; break;
-                case P_D1_R: state = P_D1_R; break;
-                case P_D2_F: state = P_D2_F; break;
-                case P_D2_L: state = P_D2_L; break;
-                case P_D2_R: state = P_D2_R; break;
-                default: state = P_D3_S; break;
-                }
-                break;                                       // re-enter the switch at the driver continuation
+                // straight to the driver continuation of this kind (no extra pass through the state switch)
+                if (KIND == 1) { if (d_ret == P_D1_F) goto c_d1_f; if (d_ret == P_D1_L) goto c_d1_l; goto c_d1_r; }
+                if (KIND == 2) { if (d_ret == P_D2_F) goto c_d2_f; if (d_ret == P_D2_L) goto c_d2_l; goto c_d2_r; }
+                goto c_d3_s;
 
             // ------------------------------------------------ one level drop (reference L2569-2574)
             lv_begin:
