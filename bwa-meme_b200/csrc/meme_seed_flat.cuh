@@ -142,7 +142,11 @@ __device__ __noinline__ void finish_thread(const Args &A, OutState &o, u32 st_se
 }
 
 template <int KIND, bool WIDE, int MINB, bool SYNC, bool STATS>
+#ifdef FLAT_MAXNREG                                    // experiment: register cap independent of the CTA shape
+__global__ void __maxnreg__(FLAT_MAXNREG) k_flat(IndexView ix, Args A)
+#else
 __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A)
+#endif
 {
     typedef typename IdxT<WIDE>::type idx_t;
     constexpr int BU = FLAT_BLK_UNROLL;

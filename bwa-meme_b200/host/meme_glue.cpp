@@ -110,6 +110,7 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
         uint8_t *d = codes.data() + off[i];
         for (int k = 0; k < seqs[i].l_seq; k++) d[k] = s[k] < 4 ? s[k] : nst_nt4_table[s[k]];
     }
+    auto t1 = std::chrono::steady_clock::now();
     meme_seed_opt_t so;
     so.min_seed_len = opt->min_seed_len;
     so.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
@@ -122,8 +123,10 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     g_base = seqs; g_n = n; g_have = true;
     g_seed_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     g_seed_reads += n;
-    fprintf(stderr, "[meme_b200] seeded %d reads on the GPU: %ld SMEMs, %ld hits (cumulative %.3f s for %ld reads)\n", n,
-            (long)g_res.n_smems, (long)g_res.n_hits, g_seed_s, g_seed_reads);
+    auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[meme_b200] seeded %d reads on the GPU: %ld SMEMs, %ld hits (cumulative %.3f s for %ld reads; this chunk: "
+            "codes %.1f ms, meme_seed_batch %.1f ms)\n", n, (long)g_res.n_smems, (long)g_res.n_hits, g_seed_s, g_seed_reads,
+            std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3);
 }
 
 // Fill the per-thread kvecs exactly as the reference's seeding + ks_introsort would leave them.

@@ -40,4 +40,6 @@ for name, exe, env in (("reference_cpu", ref, {}), ("gpu_seed", b200, {"MEME_B20
            "Mbases_per_s": N * 150 / real / 1e6, "sam_identical_to_reference": sams[name] == sams["reference_cpu"]}
     gpu_lines = [l for l in p.stderr.splitlines() if "[meme_b200] seeded" in l]
     if gpu_lines: out["gpu_seed_log"] = gpu_lines[-1]
+    if os.environ.get("E2E_VERBOSE"):
+        print("\n".join(l for l in p.stderr.splitlines() if "[meme" in l), file=sys.stderr)
     print(json.dumps(out), flush=True)
