@@ -236,7 +236,7 @@ def main_reference(a):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main_ours(a):
@@ -416,7 +416,7 @@ def main_ours(a):
             line["roofline"] = None
         if a.bsw:
             line["bsw"] = bench_bsw(a, local)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ix.close()
     if world > 1:
         dist.destroy_process_group()
@@ -444,8 +444,18 @@ def bench_bsw(a, device: int) -> dict:
     return {"pairs_per_s": len(big) / dt, "gcups": cells / dt / 1e9, "pairs": len(big), "ms": dt * 1e3}
 
 
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     args = parse()
+    # Libraries print to stdout too (NCCL announces its version there): keep fd 1 for the JSON line alone and send
+    # everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         main_reference(args)
     else:
