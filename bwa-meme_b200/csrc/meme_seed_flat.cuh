@@ -1,14 +1,19 @@
-// meme_seed_flat.cuh -- the thread-per-task seeding kernel as ONE flat state machine.
+// meme_seed_flat.cuh -- the thread-per-task seeding kernel as ONE flat state machine (the default kernel A).
 //
-// Same algorithm and the same request/compare phases as the coroutine formulation in meme_seed_tpr.cu
-// (kept as a readable reference and selectable with MEME_SEED_IMPL=tpr), but every piece of control code
-// exists exactly once and all task state lives in registers:
-//   * nested coroutines (driver -> search -> level -> extend) are flattened into one `switch (state)` with
-//     continuation codes, so the extension / level code is not duplicated at each call site and the kernel
-//     (~1.6 k instructions) fits the 32 KB L1.5 instruction cache -- "no instruction" stalls were 40 % of
-//     the samples of the coroutine version (profiles/r1);
+// One lane owns one task (T1: zig-zag pass of a read, T2: one reseed, T3: third round of a read) and alternates
+// between a control phase -- its own path through `switch (state)` until it needs memory -- and a memory phase the
+// whole warp runs together.  What shapes the code (profiles/r1/experiments):
+//   * the warp is reconverged explicitly at the head of every iteration, between the load and the compare phase
+//     and at every pass through the switch; the goto-based control flow has no reconvergence point of its own and
+//     left warps in independently looping fragments (3 active lanes per instruction even in the loads);
+//   * a block probe (8 suffix-array entries) is staged with cp.async into per-lane shared words and compared by a
+//     rolled, branch-free loop; LCPs stay in shared memory;
+//   * code size is budgeted against the 32 KB instruction cache: every piece of control code exists once
+//     (continuation codes instead of call sites), cold paths are __noinline__, the work counters are compiled out
+//     unless STATS, loops over the 8 entries are rolled;
 //   * suffix-array indices and positions are 32-bit unless the index is wide (sa_num >= 2^32), a template
 //     parameter, which halves the integer work of the control code.
+// The same algorithm as nested coroutines is in meme_seed_tpr.cu (MEME_SEED_IMPL=tpr), kept as a readable reference.
 // Included by meme_seed_tpr.cu (shares Args / PoolRec / Task2 / request enums).
 #pragma once
 
