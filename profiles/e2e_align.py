@@ -22,8 +22,9 @@ if not os.path.exists(fq):
     reads = synth.make_reads_torch(torch.from_numpy(g).cuda(), N, 150, seed=3).cpu().numpy()
     synth.write_fastq(fq, reads.reshape(-1), np.arange(N + 1, dtype=np.int64) * 150)
 isa = "avx512bw" if " avx512bw" in open("/proc/cpuinfo").read() else "avx2"
-ref = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme_mode3.{isa}")
-b200 = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme-b200_mode3.{isa}")
+MODE = os.environ.get("MODE", "3")          # index layout the binaries are compiled for (1: positions only, 3: keys + ISA)
+ref = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme_mode{MODE}.{isa}")
+b200 = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme-b200_mode{MODE}.{isa}")
 lib = os.path.join(ROOT, "bwa-meme_b200", "libmeme_b200.so")
 sams = {}
 for name, exe, env in (("reference_cpu", ref, {}), ("gpu_seed", b200, {"MEME_B200": "1"}),
@@ -36,7 +37,7 @@ for name, exe, env in (("reference_cpu", ref, {}), ("gpu_seed", b200, {"MEME_B20
     proc = [l for l in p.stderr.splitlines() if "Processed" in l and "real sec" in l]
     real = sum(float(l.split("CPU sec,")[1].split("real sec")[0]) for l in proc)
     sams[name] = "".join(l for l in open(f"{d}/{name}.sam") if not l.startswith("@PG"))
-    out = {"arm": name, "threads": int(T), "reads": N, "mem_process_seqs_real_s": real, "wall_s": wall,
+    out = {"arm": name, "mode": int(MODE), "genome_bp": G, "threads": int(T), "reads": N, "mem_process_seqs_real_s": real, "wall_s": wall,
            "Mbases_per_s": N * 150 / real / 1e6, "sam_identical_to_reference": sams[name] == sams["reference_cpu"]}
     gpu_lines = [l for l in p.stderr.splitlines() if "[meme_b200] seeded" in l]
     if gpu_lines: out["gpu_seed_log"] = gpu_lines[-1]
