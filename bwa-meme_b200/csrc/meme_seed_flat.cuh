@@ -16,6 +16,18 @@
 // The same algorithm as nested coroutines is in meme_seed_tpr.cu (MEME_SEED_IMPL=tpr), kept as a readable reference.
 // Included by meme_seed_tpr.cu (shares Args / PoolRec / Task2 / request enums).
 #pragma once
+#include "meme_seed_task.cuh"
+
+// The few device-only constructs go through these macros so that tests/host_sim can compile this file with g++ and
+// run the same control code one lane at a time against the oracle (no GPU needed to check a logic change).
+#ifndef MEME_HOST_SIM
+#define FLAT_SMEM_DECL extern __shared__ u32 smem[]
+typedef u32 flat_stage_t;                                   // shared-window byte address
+#define FLAT_STAGE_BASE(p) ((u32)__cvta_generic_to_shared(p))
+#define FLAT_CP4(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory")
+#define FLAT_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define FLAT_CP_WAIT() asm volatile("cp.async.wait_group 0;" ::: "memory")
+#endif
 
 namespace tpr {
 
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
     typedef typename IdxT<WIDE>::type idx_t;
     constexpr int BU = FLAT_BLK_UNROLL;
     constexpr int SW = flat_sw<KIND>();
-    extern __shared__ u32 smem[];
+    FLAT_SMEM_DECL;
     u32 *const sm = &smem[threadIdx.x * SW];
     u32 *const stg = sm + FLAT_SW;
     sm[0] = sm[1] = sm[FLAT_RD + 2 * TPR_RW] = sm[FLAT_RD + 2 * TPR_RW + 1] = 0;
@@ -656,19 +668,19 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
         if (STATS && req != M_NONE) st_iter++;
         if (req == M_BLOCK) {
             // asynchronous copies straight into the staging words: a rolled loop with every load in flight
-            u32 dst = (u32)__cvta_generic_to_shared(stg);
+            flat_stage_t dst = FLAT_STAGE_BASE(stg);
             const char *kp = reinterpret_cast<const char *>(ix.keys + m_base);
             const char *pq = reinterpret_cast<const char *>(ix.pos_lo + m_base);
 #pragma unroll 1
             for (int j = 0; j < m_count; j++) {
                 if (has_keys) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(kp) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32), "l"(kp + 4) : "memory");
+                    FLAT_CP4(dst, kp);
+                    FLAT_CP4(dst + 32, kp + 4);
                 }
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 64), "l"(pq) : "memory");
+                FLAT_CP4(dst + 64, pq);
                 dst += 4; kp += m_stride * 8; pq += m_stride * 4;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            FLAT_CP_COMMIT();
             if (WIDE) {
                 u64 h = 0; idx_t idx = m_base;
 #pragma unroll
@@ -708,7 +720,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             u32 less = 0, und = 0;
             const u32 qlo = (u32)q0, qhi = (u32)(q0 >> 32);
             u32 *const rl = stg + rl_off;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            FLAT_CP_WAIT();
 #pragma unroll BU
             for (int j = 0; j < m_count; j++) {
                 const u32 klo = stg[j], khi = stg[8 + j], pj = stg[16 + j];
