@@ -99,4 +99,3 @@ struct meme_index {
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);
 int meme_grow_pinned(void **p, size_t *cap, size_t need, size_t elem);
-int tpr_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);

@@ -13,8 +13,7 @@
 //     unless STATS, loops over the 8 entries are rolled;
 //   * suffix-array indices and positions are 32-bit unless the index is wide (sa_num >= 2^32), a template
 //     parameter, which halves the integer work of the control code.
-// The same algorithm as nested coroutines is in meme_seed_tpr.cu (MEME_SEED_IMPL=tpr), kept as a readable reference.
-// Included by meme_seed_tpr.cu (shares Args / PoolRec / Task2 / request enums).
+// Included by meme_seed.cu (launch sequence, sort, gather) and by tests/host_sim (single-lane CPU run of this source).
 #pragma once
 #include "meme_seed_task.cuh"
 

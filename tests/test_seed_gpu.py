@@ -219,35 +219,3 @@ def test_wide_index_kernels_on_golden_fixtures(oracle, pkg, golden_index, golden
     want = oix.seed(codes, offs)
     oix.close()
     assert _canon(oracle, got, n) == _canon(oracle, want, n)
-
-
-@pytest.mark.parametrize("env", [{"MEME_SEED_IMPL": "coop"}, {"MEME_SEED_IMPL": "tpr"}, {"MEME_SEED_SYNC": "0"}])
-def test_earlier_kernel_generations_still_match(oracle, pkg, golden_index, env):
-    """The cooperative (group-per-read) kernel, the coroutine formulation and the non-reconverging flat kernel stay
-    selectable.  The choice is latched per process, so each runs in its own interpreter."""
-    import subprocess
-    import sys
-    code = f"""
-import sys, os, numpy as np
-sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
-import __graft_entry__ as ge
-ge.load_pkg(); O = ge.load_oracle()
-from bwa_meme_b200 import capi, synth
-from conftest import GOLDEN
-g = synth.make_genome({{}}, seed={{}}, n_families=3, copies=12, rep_len=400)
-"""
-    meta = __import__("json").load(open(os.path.join(GOLDEN, "index_sha.json")))
-    code = code.format(meta["genome_len"], meta["genome_seed"]) + f"""
-codes, offs = synth.make_reads(g, 300, 150, seed=21, n_frac=0.05)
-n = len(offs) - 1
-ix = capi.MemeIndex({golden_index!r}, mode=3)
-got = ix.seed(codes, offs)
-want = O.parse_ref_dump(os.path.join(GOLDEN, "smem_len150.txt"), n)
-assert O.canon_lines(got["smems"], got["smem_off"], got["hit_off"], got["hits"], n) == want
-print("OK")
-"""
-    e = dict(os.environ)
-    e.update(env)
-    e["PYTHONPATH"] = os.path.dirname(os.path.abspath(__file__)) + os.pathsep + e.get("PYTHONPATH", "")
-    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
-    assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-2000:]
