@@ -64,7 +64,7 @@ struct meme_index {
     // ---- seeding workspace (grown on demand) ----
     uint8_t *d_codes; size_t cap_codes;
     int64_t *d_read_off; size_t cap_reads;
-    int64_t n_reads; int64_t n_codes;
+    int64_t n_reads; int64_t n_codes; int max_read_len;
     // per-read: raw pool offset, smem count, hit count (after sampling)
     u64 *d_rd_pool_off; u32 *d_rd_nsmem; u64 *d_rd_nhit; u32 *d_redo;
     int64_t *d_smem_off, *d_hit_off;      // n_reads+1 exclusive scans

@@ -94,6 +94,7 @@ __global__ void k_gather2(IndexView ix, const u64 *__restrict__ keys, const Pool
 }  // namespace tpr
 
 #include "meme_seed_flat.cuh"
+#include "meme_seed_grp.cuh"
 
 using namespace tpr;
 
@@ -114,20 +115,56 @@ static int launch_kernel(meme_index_t *ix, const Args &A, K kernel, size_t dyn_s
     return MEME_OK;
 }
 
+// MEME_SEED_IMPL: "grp" (default) = tasks regrouped by state across the CTA (meme_seed_grp.cuh); "flat" = one task per
+// lane (meme_seed_flat.cuh), kept for comparison
+static int seed_impl()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MEME_SEED_IMPL"); v = (e && !strcmp(e, "flat")) ? 0 : 1; }
+    return v;
+}
+
+template <class K>
+static int launch_grp_kernel(meme_index_t *ix, const Args &A, K kernel, size_t dyn_smem)
+{
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
+    static int warps = getenv("MEME_GRP_WARPS") ? atoi(getenv("MEME_GRP_WARPS")) : 12;
+    int nw = warps < 1 ? 1 : (warps > 16 ? 16 : warps);
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    int64_t grid = sms, need = (A.n_tasks + 63) / 64;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    CUDA_TRY(cudaMemsetAsync(ix->d_ctrl + C_WORK, 0, 8, ix->stream));
+    kernel<<<(unsigned)grid, nw * 32, dyn_smem, ix->stream>>>(ix->v, A);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    return MEME_OK;
+}
+
+template <int KIND, bool WIDE, bool LONG>
+static int launch_grp(meme_index_t *ix, const Args &A, bool stats)
+{
+    const size_t sm = grp::Lay<WIDE, LONG>::BYTES;
+    static_assert(grp::Lay<WIDE, LONG>::BYTES <= 227 * 1024, "task cells exceed the shared memory of an SM");
+    return stats ? launch_grp_kernel(ix, A, grp::k_grp<KIND, WIDE, LONG, true>, sm) : launch_grp_kernel(ix, A, grp::k_grp<KIND, WIDE, LONG, false>, sm);
+}
+
 template <int KIND>
 static int launch_seed(meme_index_t *ix, const Args &A)
 {
     if (A.n_tasks <= 0) return MEME_OK;
-    static int sync = getenv("MEME_SEED_SYNC") ? atoi(getenv("MEME_SEED_SYNC")) : 1;   // warp reconvergence per iteration
-    // work counters (meme_seed_counters [0..3]) cost registers and code in the hot loop: off unless asked for
+    // work counters (meme_seed_counters) cost registers and code in the hot loop: off unless asked for
     const char *se = getenv("MEME_SEED_STATS");
     const bool stats = se && atoi(se) != 0;
+    if (seed_impl() == 1) {
+        const bool lng = ix->max_read_len > 32 * (TPR_RW / 2);
+        if (ix->v.pos_wide) return lng ? launch_grp<KIND, true, true>(ix, A, stats) : launch_grp<KIND, true, false>(ix, A, stats);
+        return lng ? launch_grp<KIND, false, true>(ix, A, stats) : launch_grp<KIND, false, false>(ix, A, stats);
+    }
     const size_t sm = (size_t)TPR_THREADS * flat_sw<KIND>() * sizeof(u32);
     if (ix->v.pos_wide)
         return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>, sm);
-    if (!sync) return launch_kernel(ix, A, k_flat<KIND, false, 2, false, false>, sm);
-    static int minb = getenv("MEME_SEED_MINB") ? atoi(getenv("MEME_SEED_MINB")) : 2;   // resident CTAs per SM asked of the compiler
-    if (minb == 3 && !stats) return launch_kernel(ix, A, k_flat<KIND, false, 3, true, false>, sm);
     return stats ? launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, false>, sm);
 }
 
@@ -159,7 +196,7 @@ static int seed_run_kernels(meme_index_t *ix, const meme_seed_opt_t *opt)
         if ((rc = meme_grow_device((void **)&ix->d_pool_vals, &ix->cap_pool_vals, cap, sizeof(PoolRec), st))) return rc;
         if ((rc = meme_grow_device((void **)&ix->d_pool_keys2, &ix->cap_pool_keys2, cap, 8, st))) return rc;
         if ((rc = meme_grow_device((void **)&ix->d_pool_vals2, &ix->cap_pool_vals2, cap, sizeof(PoolRec), st))) return rc;
-        CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, 16 * 8, st));
+        CUDA_TRY(cudaMemsetAsync(ix->d_ctrl, 0, C_NCTRL * 8, st));
         CUDA_TRY(cudaMemsetAsync(ix->d_rd_nsmem, 0, (size_t)n * 4, st));
         CUDA_TRY(cudaMemsetAsync(ix->d_rd_nhit, 0, (size_t)n * 8, st));
         Args A;
@@ -171,18 +208,21 @@ static int seed_run_kernels(meme_index_t *ix, const meme_seed_opt_t *opt)
         A.ctrl = ix->d_ctrl; A.opt = *opt;
         A.kind = 1; A.n_tasks = n;
         if ((rc = launch_seed<1>(ix, A))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, C_NCTRL * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         n_t2 = ix->h_ctrl[C_T2];
         bool ovf = ix->h_ctrl[C_T2_OVF] != 0;
         static const bool dbg = getenv("MEME_SEED_DEBUG") != nullptr;   // per-kernel counters + times on stderr
         auto dump = [&](const char *name, cudaEvent_t e0, cudaEvent_t e1, int64_t tasks) {
-            u64 c[16]; float ms = 0;
+            u64 c[C_NCTRL]; float ms = 0;
             cudaMemcpyAsync(c, ix->d_ctrl, sizeof c, cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);
             cudaEventElapsedTime(&ms, e0, e1);
             fprintf(stderr, "[meme_seed] %s: %lld tasks, %.2f ms (cumulative counters) searches %llu blocks %llu kary %llu ext %llu pac %llu "
-                    "round-trips %llu\n", name, (long long)tasks, ms, c[C_SEARCH], c[C_BLOCK], c[C_KARY], c[C_EXT], c[C_PAC], c[C_ITER]);
+                    "round-trips %llu; passes ctl %llu (%.1f lanes) mem %llu (%.1f lanes)\n", name, (long long)tasks, ms, c[C_SEARCH],
+                    c[C_BLOCK], c[C_KARY], c[C_EXT], c[C_PAC], c[C_ITER], c[C_PASS_CTL] / 32,
+                    c[C_PASS_CTL] ? 32.0 * c[C_LANES_CTL] / c[C_PASS_CTL] : 0.0, c[C_PASS_MEM] / 32,
+                    c[C_PASS_MEM] ? 32.0 * c[C_LANES_MEM] / c[C_PASS_MEM] : 0.0);
         };
         cudaEvent_t de[4];
         if (dbg) { for (auto &e : de) cudaEventCreate(&e); cudaEventRecord(de[1], st); dump("T1", ix->ev[0], de[1], n); }
@@ -198,7 +238,7 @@ static int seed_run_kernels(meme_index_t *ix, const meme_seed_opt_t *opt)
         }
         if (dbg) for (auto &e : de) cudaEventDestroy(e);
         CUDA_TRY(cudaEventRecord(ix->ev[1], st));
-        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, C_NCTRL * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         n_pool = ix->h_ctrl[C_POOL];
         if (!ovf && !ix->h_ctrl[C_POOL_OVF]) break;
@@ -289,13 +329,16 @@ extern "C" int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const in
     CUDA_TRY(cudaSetDevice(ix->device));
     int64_t n_codes = n_reads ? read_off[n_reads] - read_off[0] : 0;
     if (n_reads && read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
+    int64_t max_len = 0;
     for (int64_t i = 0; i < n_reads; i++) {
         int64_t len = read_off[i + 1] - read_off[i];
         if (len < 0 || len > MEME_MAX_READ_LEN) {
             meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
             return MEME_E_ARG;
         }
+        if (len > max_len) max_len = len;
     }
+    ix->max_read_len = (int)max_len;
     int rc;
     cudaStream_t st = ix->stream;
     if ((rc = seed_alloc_inputs(ix, n_reads, n_codes))) return rc;
@@ -426,13 +469,16 @@ static int seed_batch_pipelined(meme_index_t *ix, const uint8_t *codes, const in
 {
     CUDA_TRY(cudaSetDevice(ix->device));
     if (read_off[0] != 0) { meme_set_error("read_off[0] must be 0"); return MEME_E_ARG; }
+    int64_t max_len = 0;
     for (int64_t i = 0; i < n; i++) {
         int64_t len = read_off[i + 1] - read_off[i];
         if (len < 0 || len > MEME_MAX_READ_LEN) {
             meme_set_error("read %lld has length %lld (limit %d; the reference asserts <= 301)", (long long)i, (long long)len, MEME_MAX_READ_LEN);
             return MEME_E_ARG;
         }
+        if (len > max_len) max_len = len;
     }
+    ix->max_read_len = (int)max_len;
     const int64_t K = (n + chunk - 1) / chunk;
     int64_t max_codes = 0;
     for (int64_t c = 0; c < K; c++) {

@@ -22,7 +22,7 @@ enum { M_NONE = 0, M_BLOCK, M_PAC, M_RMI, M_LD, M_TASK, M_T2REC };
 enum { LD_POS = 0, LD_ISA = 1 };
 enum { ST_RMI = 0, ST_EXACT = 1, ST_NEAR = 2 };
 enum { C_WORK = 0, C_POOL = 1, C_T2 = 2, C_POOL_OVF = 3, C_T2_OVF = 4, C_SEARCH = 8, C_BLOCK = 9, C_KARY = 10, C_EXT = 11,
-       C_PAC = 12, C_ITER = 13 };
+       C_PAC = 12, C_ITER = 13, C_PASS_CTL = 14, C_PASS_MEM = 15, C_LANES_CTL = 16, C_LANES_MEM = 17, C_NCTRL = 24 };
 
 struct Args {
     const u64 *packed; const u32 *nmask; const int64_t *read_off;

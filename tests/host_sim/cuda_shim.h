@@ -44,6 +44,29 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __all_sync(unsigned, int p) { return p; }
 static inline int __any_sync(unsigned, int p) { return p; }
 
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
+static inline unsigned atomicSub(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
+// the device-only constructs of meme_seed_grp.cuh: a CTA of one warp of one lane
+#include <cstdio>
+#include <cstdlib>
+#define GRP_TRACE(...) do { static int on = getenv("GRP_TRACE") != nullptr; static long cnt = 0; if (on && cnt++ < 400) fprintf(stderr, __VA_ARGS__); } while (0)
+#define GRP_SMEM_DECL alignas(16) static unsigned char grp_smem[L::BYTES]
+#define GRP_CP4(dst, src) memcpy((void *)(dst), (const void *)(src), 4)
+#define GRP_CP8(dst, src) memcpy((void *)(dst), (const void *)(src), 8)
+#define GRP_CP16(dst, src) memcpy((void *)(dst), (const void *)(src), 16)
+#define GRP_CP_COMMIT() ((void)0)
+#define GRP_CP_WAIT(n) ((void)0)
+#define GRP_FENCE() ((void)0)
+#define GRP_SLEEP(ns) ((void)0)
+#define GRP_LANE() 0
+#define GRP_WARP() 0
+#define GRP_BALLOT(p) ((p) ? 1u : 0u)
+#define GRP_SHFL(v, l) (v)
+#define GRP_SYNCWARP() ((void)0)
+#define GRP_SYNCTHREADS() ((void)0)
+
 // the device-only constructs of meme_seed_flat.cuh
 #define FLAT_SMEM_DECL static u32 smem[TPR_THREADS * 128]
 typedef char *flat_stage_t;

@@ -5,6 +5,7 @@
 #include <numeric>
 #include <vector>
 #include "../../bwa-meme_b200/csrc/meme_seed_flat.cuh"
+#include "../../bwa-meme_b200/csrc/meme_seed_grp.cuh"
 
 using namespace tpr;
 
@@ -15,22 +16,34 @@ struct Result {
     std::vector<uint64_t> hits;
 } g_res;
 
+int g_impl = 0;       // 0: flat kernel, 1: regrouped kernel (meme_seed_grp.cuh)
+
+template <int KIND, bool WIDE>
+void run_kind(const IndexView &ix, Args &A, bool lng)
+{
+    if (g_impl == 0) k_flat<KIND, WIDE, 2, true, true>(ix, A);
+    else if (lng) grp::k_grp<KIND, WIDE, true, true>(ix, A);
+    else grp::k_grp<KIND, WIDE, false, true>(ix, A);
+}
+
 template <bool WIDE>
-void run_kinds(const IndexView &ix, Args &A, const meme_seed_opt_t &opt, int64_t n, std::vector<Task2> &t2, u64 *ctrl)
+void run_kinds(const IndexView &ix, Args &A, const meme_seed_opt_t &opt, int64_t n, std::vector<Task2> &t2, u64 *ctrl, bool lng)
 {
     A.kind = 1; A.n_tasks = n; ctrl[C_WORK] = 0;
-    k_flat<1, WIDE, 2, true, true>(ix, A);
+    run_kind<1, WIDE>(ix, A, lng);
     const u64 n_t2 = ctrl[C_T2];
     if (opt.rounds >= 2 && n_t2) {
         A.kind = 2; A.n_tasks = (int64_t)n_t2; A.t2_in = t2.data(); A.t2_out = nullptr; A.t2_cap = 0; ctrl[C_WORK] = 0;
-        k_flat<2, WIDE, 2, true, true>(ix, A);
+        run_kind<2, WIDE>(ix, A, lng);
     }
     if (opt.rounds >= 3 && opt.max_mem_intv > 0) {
         A.kind = 3; A.n_tasks = n; A.t2_in = nullptr; ctrl[C_WORK] = 0;
-        k_flat<3, WIDE, 2, true, true>(ix, A);
+        run_kind<3, WIDE>(ix, A, lng);
     }
 }
 }  // namespace
+
+extern "C" void flat_sim_set_impl(int impl) { g_impl = impl; }
 
 extern "C" int flat_sim_seed(const uint8_t *text, uint64_t sa_num, const uint8_t *pos_packed, const void *l1_raw, uint64_t n_l1,
                              const void *l2_raw, uint64_t n_l2, int mode, int wide, const uint8_t *codes, const int64_t *read_off,
@@ -41,7 +54,7 @@ extern "C" int flat_sim_seed(const uint8_t *text, uint64_t sa_num, const uint8_t
     std::vector<u64> pac((n + 31) / 32 + 2, 0);
     for (u64 i = 0; i < n; i++) pac[i >> 5] |= (u64)(text[i] & 3) << (2 * (i & 31));
     std::vector<u32> pos_lo(n), isa_lo(mode == 3 ? n : 0);
-    std::vector<uint8_t> pos_hi(wide ? n : 0), isa_hi(wide && mode == 3 ? n : 0);
+    std::vector<uint8_t> pos_hi(wide ? n + 8 : 0), isa_hi(wide && mode == 3 ? n + 8 : 0);
     std::vector<u64> keys(mode >= 2 ? n : 0);
     for (u64 i = 0; i < n; i++) {
         const uint8_t *p = pos_packed + i * 5;
@@ -78,9 +91,11 @@ extern "C" int flat_sim_seed(const uint8_t *text, uint64_t sa_num, const uint8_t
     const int64_t nr = n_reads;
     std::vector<u64> packed((size_t)nr * TPR_RW + 16, 0);
     std::vector<u32> nmask((size_t)nr * TPR_RW + 16, 0);
+    int max_len = 0;
     for (int64_t r = 0; r < nr; r++) {
         int64_t o = read_off[r]; int L = (int)(read_off[r + 1] - o);
         if (L < 0 || L > MEME_MAX_READ_LEN) return MEME_E_ARG;
+        if (L > max_len) max_len = L;
         for (int p = 0; p < L; p++) {
             u32 c = codes[o + p];
             if (c > 3) nmask[r * TPR_RW + (p >> 5)] |= 1u << (p & 31);
@@ -103,7 +118,8 @@ extern "C" int flat_sim_seed(const uint8_t *text, uint64_t sa_num, const uint8_t
     A.pool_keys = pool_keys.data(); A.pool_vals = pool_vals.data(); A.pool_cap = pool_cap;
     A.rd_nsmem = rd_nsmem.data(); A.rd_nhit = rd_nhit.data(); A.rd_full = rd_full.data(); A.rd_maxref = rd_maxref.data();
     A.ctrl = ctrl; A.opt = *opt;
-    if (nr > 0) { if (wide) run_kinds<true>(ix, A, *opt, nr, t2, ctrl); else run_kinds<false>(ix, A, *opt, nr, t2, ctrl); }
+    const bool lng = max_len > 32 * (TPR_RW / 2);
+    if (nr > 0) { if (wide) run_kinds<true>(ix, A, *opt, nr, t2, ctrl, lng); else run_kinds<false>(ix, A, *opt, nr, t2, ctrl, lng); }
     if (ctrl[C_POOL_OVF] || ctrl[C_T2_OVF]) return MEME_E_OVERFLOW;
     if (counters) { counters[0] = ctrl[C_SEARCH]; counters[1] = ctrl[C_BLOCK]; counters[2] = ctrl[C_KARY]; counters[3] = ctrl[C_EXT];
                     counters[4] = ctrl[C_PAC]; counters[5] = ctrl[C_ITER]; counters[6] = ctrl[C_T2]; counters[7] = ctrl[C_POOL]; }

@@ -26,8 +26,8 @@ def _cuda_include():
     return None
 
 
-@pytest.fixture(scope="module")
-def sim(pkg):
+@pytest.fixture(scope="module", params=["grp", "flat"])
+def sim(pkg, request):
     inc = _cuda_include()
     if not shutil.which("g++") or not inc:
         pytest.skip("g++ or the CUDA headers are missing")
@@ -35,13 +35,14 @@ def sim(pkg):
     os.makedirs(out_dir, exist_ok=True)
     lib = os.path.join(out_dir, "libflat_host.so")
     deps = [os.path.join(SIM_DIR, f) for f in ("flat_host.cpp", "cuda_shim.h")] + \
-           [os.path.join(CSRC, f) for f in ("meme_seed_flat.cuh", "meme_seed_task.cuh", "meme_common.cuh")] + \
+           [os.path.join(CSRC, f) for f in ("meme_seed_flat.cuh", "meme_seed_grp.cuh", "meme_seed_task.cuh", "meme_common.cuh")] + \
            [os.path.join(ROOT, "include", "meme_b200.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-I", inc, "-o", lib,
                         os.path.join(SIM_DIR, "flat_host.cpp")], check=True)
     L = C.CDLL(lib)
     L.flat_sim_seed.restype = C.c_int
+    impl = 1 if request.param == "grp" else 0
     from bwa_meme_b200 import capi
 
     def seed(prefix, mode, codes, offs, opt=None, wide=False):
@@ -54,6 +55,7 @@ def sim(pkg):
         res = capi.SeedResult()
         counters = (C.c_uint64 * 8)()
         vp = lambda a: C.c_void_p(a.ctypes.data)
+        L.flat_sim_set_impl(C.c_int(impl))
         rc = L.flat_sim_seed(vp(text), C.c_uint64(len(text)), vp(pos), vp(l1), C.c_uint64(len(l1) // 24), vp(l2),
                              C.c_uint64(len(l2) // 24), C.c_int(mode), C.c_int(int(wide)), vp(codes), vp(offs),
                              C.c_int64(len(offs) - 1), C.byref(opt), C.byref(res), counters)
