@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--mode", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the 64-bit-index sub-record")
     ap.add_argument("--bsw", action="store_true", help="also time the banded-SW kernel on synthetic extension pairs")
     return ap.parse_args()
 
@@ -268,7 +269,9 @@ def main_ours(a):
     t0 = time.time()
     ix = capi.MemeIndex(prefix, mode=a.mode, device=local)
     log(f"rank {rank}: index resident in HBM: {ix.device_bytes / 1e9:.2f} GB, loaded in {time.time() - t0:.1f}s")
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the library launches on it and the torch events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ix.set_stream(stream.cuda_stream)
 
     # ---- reads: every rank owns its shard of the job (weak scaling: 10 M reads per GPU) ----
@@ -328,6 +331,31 @@ def main_ours(a):
     clocks = sampler.stop()
     h2d = n * L + (n + 1) * 8
     d2h = tot["n_smems"] * 24 + tot["n_hits"] * 8 + 2 * (n + 1) * 8
+
+    # ---- the 64-bit-index kernel instantiations (sa_num >= 2^32: every GRCh38-scale run) on the same workload ----
+    wide = None
+    if rank == 0 and not a.no_wide:
+        os.environ["MEME_FORCE_WIDE"] = "1"
+        wix = capi.MemeIndex(prefix, mode=a.mode, device=local)
+        del os.environ["MEME_FORCE_WIDE"]
+        wix.set_stream(stream.cuda_stream)
+        wix.seed_upload_ptr(host.data_ptr(), offs_pinned.data_ptr(), n)
+        for _ in range(2):
+            wix.seed_run(opt)
+        torch.cuda.synchronize()
+        w0e, w1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wms = []
+        w0e.record()
+        for _ in range(3):
+            wix.seed_run(opt)
+            wms.append(wix.seed_last_ms()["seed"])
+        w1e.record()
+        torch.cuda.synchronize()
+        wtot = wix.seed_totals()
+        wide = {"value": n * 3 / (w0e.elapsed_time(w1e) / 1e3), "unit": "reads/s", "k_seed_ms": float(np.mean(wms)), "steps": 3,
+                "index_hbm_gb": round(wix.device_bytes / 1e9, 2), "same_results_as_narrow": bool(wtot == (n_smems, n_hits)),
+                "how": "MEME_FORCE_WIDE=1: 5-byte positions / inverse SA and the WIDE kernel instantiations on the same index and reads"}
+        wix.close()
 
     # ---- final hit gather (the one collective of the path): per-rank totals + checksums over NCCL ----
     summary = mdist.gather_summary(ix, n, world, device)
@@ -414,6 +442,7 @@ def main_ours(a):
                                         "ceiling is well below the streaming peak"}
         else:
             line["roofline"] = None
+        line["wide"] = wide
         if a.bsw:
             line["bsw"] = bench_bsw(a, local)
         emit(line)

@@ -115,12 +115,13 @@ static int launch_kernel(meme_index_t *ix, const Args &A, K kernel, size_t dyn_s
     return MEME_OK;
 }
 
-// MEME_SEED_IMPL: "grp" (default) = tasks regrouped by state across the CTA (meme_seed_grp.cuh); "flat" = one task per
-// lane (meme_seed_flat.cuh), kept for comparison
+// MEME_SEED_IMPL: "flat" (default) = one task per lane (meme_seed_flat.cuh); "grp" = tasks regrouped by state across
+// the CTA (meme_seed_grp.cuh): parity-green and 17-25 active lanes per instruction instead of 6-8, but 2.6x the warp
+// instructions and 61 KB of code against a 32 KB instruction cache -- half the speed of the flat kernel (profiles/r2)
 static int seed_impl()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("MEME_SEED_IMPL"); v = (e && !strcmp(e, "flat")) ? 0 : 1; }
+    if (v < 0) { const char *e = getenv("MEME_SEED_IMPL"); v = (e && !strcmp(e, "grp")) ? 1 : 0; }
     return v;
 }
 
@@ -130,7 +131,7 @@ static int launch_grp_kernel(meme_index_t *ix, const Args &A, K kernel, size_t d
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device));
     static int warps = getenv("MEME_GRP_WARPS") ? atoi(getenv("MEME_GRP_WARPS")) : 12;
-    int nw = warps < 1 ? 1 : (warps > 16 ? 16 : warps);
+    int nw = warps < 1 ? 1 : (warps > 32 ? 32 : warps);
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     int64_t grid = sms, need = (A.n_tasks + 63) / 64;
     if (grid > need) grid = need;
@@ -206,6 +207,10 @@ static int seed_run_kernels(meme_index_t *ix, const meme_seed_opt_t *opt)
         A.pool_cap = ix->cap_pool_keys < ix->cap_pool_vals ? ix->cap_pool_keys : ix->cap_pool_vals;
         A.rd_nsmem = ix->d_rd_nsmem; A.rd_nhit = ix->d_rd_nhit; A.rd_full = ix->d_rd_full; A.rd_maxref = ix->d_rd_maxref;
         A.ctrl = ix->d_ctrl; A.opt = *opt;
+        {
+            static int th = getenv("MEME_GRP_TH") ? atoi(getenv("MEME_GRP_TH")) : 24;
+            A.grp_th = th;
+        }
         A.kind = 1; A.n_tasks = n;
         if ((rc = launch_seed<1>(ix, A))) return rc;
         CUDA_TRY(cudaMemcpyAsync(ix->h_ctrl, ix->d_ctrl, C_NCTRL * 8, cudaMemcpyDeviceToHost, st));

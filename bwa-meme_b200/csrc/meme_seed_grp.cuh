@@ -36,6 +36,7 @@
 #define GRP_WARP() (threadIdx.x >> 5)
 #define GRP_BALLOT(p) __ballot_sync(0xffffffffu, (p))
 #define GRP_SHFL(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define GRP_REDUCE_MIN(v) __reduce_min_sync(0xffffffffu, (unsigned)(v))
 #define GRP_SYNCWARP() __syncwarp()
 #define GRP_SYNCTHREADS() __syncthreads()
 #endif
@@ -47,14 +48,10 @@
 namespace grp {
 using namespace tpr;
 
-// pools (values of a slot's state byte) -- the first NCTL are control-entry states of the state machine
-enum {
-    P_TASK_LOADED = 0, P_S_ISA, P_S_EXACT, P_S_RMI1, P_S_RMI2, P_S_CENTER, P_S_LOC, P_E, P_D1_M, P_D2_C, NCTL,
-    Q_BLOCK = NCTL, Q_PAC, Q_EMPTY, NPOOL,
-    SL_BUSY = 0xfe, SL_DEAD = 0xff
-};
-// continuation codes (d_ret / as_ret), never pools
-enum { R_D1_F = 32, R_D1_L, R_D1_R, R_D2_F, R_D2_L, R_D2_R, R_D3_S };
+// A slot's state byte: a control label (< 0x40, the block its task resumes at: pool PL_CTL), or one of the codes below.
+enum { Q_BLOCK = 0x40, Q_PAC = 0x41, Q_EMPTY = 0x42, SL_BUSY = 0xfe, SL_DEAD = 0xff };
+// the four pools a warp can claim from
+enum { PL_CTL = 0, PL_BLOCK = 1, PL_PAC = 2, PL_EMPTY = 3 };
 enum { R_INIT_L = 0, R_INIT_R, R_LV_L, R_LV_R };
 enum { RMI_L2 = 0, RMI_L1 = 1 };
 enum { B_BLOCK = 0, B_PAC = 1, B_SIMPLE = 2 };
@@ -64,9 +61,6 @@ enum { B_BLOCK = 0, B_PAC = 1, B_SIMPLE = 2 };
 #endif
 #ifndef GRP_DEPTH
 #define GRP_DEPTH 3                       // pending batches per warp
-#endif
-#ifndef GRP_TH
-#define GRP_TH 20                         // a pool with at least this many lane classes is taken at once
 #endif
 
 template <bool WIDE> struct IdxT { typedef u32 type; typedef int stype; };
@@ -99,7 +93,7 @@ struct Lay {
     static constexpr size_t OFF_S16 = OFF_RD + (size_t)N_RD * NT * 4;
     static constexpr size_t OFF_LCP = OFF_S16 + (size_t)N_S16 * NT * 2;
     static constexpr size_t OFF_SST = OFF_LCP + (size_t)16 * NT * 2;    // state bytes [32 lane classes][16 slots]
-    static constexpr size_t OFF_TOK = OFF_SST + 512;                    // u32 tokens [16], then [16] live count, [17] stop flag
+    static constexpr size_t OFF_TOK = OFF_SST + 512;                    // u32 [0..3] pool tokens, [4..7] pool task counts, [8] live slots
     static constexpr size_t BYTES = OFF_TOK + 128;
 };
 
@@ -193,11 +187,26 @@ __device__ __forceinline__ u64 rmi_key_of(u64 q0, int q_V)
 }
 
 // =====================================================================================================================
-// one control step of one task: from "memory result available" to the next memory request (or the end of the task)
+// control pass: the state machine as a converged interpreter over its basic blocks
 // =====================================================================================================================
+// Every lane holds the label of the block its task executes next.  The warp repeatedly takes the SMALLEST label any
+// lane holds (one REDUX) and the lanes at that label run the block together; a block ends by naming the next label.
+// Labels are numbered along the flow of a search (entry blocks first, the shared downstream blocks -- located, level
+// handling, driver continuations, start selection, search begin -- later), so lanes that split at a data-dependent
+// branch wait at the merge points until the stragglers arrive.  A lane stops at L_STOP: its task has a memory request
+// pending or has ended.  (In the flat kernel the same code is one goto-based function per lane; with the gotos a warp
+// never reconverges after the first data-dependent branch: 3-6 active lanes per instruction, profiles/r2.)
+enum {
+    L_TASK_LOADED = 0, L_S_ISA, L_S_RMI1, L_S_RMI2, L_S_CENTER, L_S_LOC, L_LOC_INIT, L_LOC_NEXT, L_P_E, L_E_DONE, L_LOCATED,
+    L_INIT_RIGHT, L_LV_RIGHT, L_LV_DONE, L_LEVELED, L_LEVEL_LOOP, L_LV_BEGIN, L_D3_LEVELS, L_SEARCH_DONE, L_D1_M, L_D2_C,
+    L_C_D1_F, L_C_D1_L, L_C_D1_R, L_C_D2_F, L_C_D2_L, L_C_D2_R, L_C_D3_S, L_D2_LOOP, L_D1_LOOP, L_D1_ZZ, L_D2_FIRST, L_D3_LOOP,
+    L_AUTO_START, L_S_BEGIN, L_E_BEGIN, L_E_PROBE, L_C_TASK, L_STOP
+};
+static_assert(L_STOP < 0x40, "labels double as state bytes below the pool codes");
+
 template <int KIND, bool WIDE, bool LONG, bool STATS>
-__device__ __forceinline__ void ctl_step(const IndexView &ix, const Args &A, unsigned char *smb, const u32 sid, OutState &out,
-                                         Stats &st, bool &ended)
+__device__ __forceinline__ void ctl_pass(const IndexView &ix, const Args &A, unsigned char *smb, const u32 sid, const bool have,
+                                         OutState &out, Stats &st, bool &ended)
 {
     typedef Lay<WIDE, LONG> L;
     typedef typename IdxT<WIDE>::type idx_t;
@@ -275,377 +284,387 @@ __device__ __forceinline__ void ctl_step(const IndexView &ix, const Args &A, uns
     };
 
     ended = false;
-    mreq = M_NONE;
+    int lab = L_STOP;
+    if (have) { lab = state; mreq = M_NONE; }
+// leave the block for label X / stop with a memory request that resumes at label X / after a request that may be empty
+#define GO(X) do { lab = (X); goto next_block; } while (0)
+#define STOP_AT(X) do { state = (short)(X); lab = L_STOP; goto next_block; } while (0)
+#define REQ_OR_GO(X) do { if (mreq != M_NONE) STOP_AT(X); GO(X); } while (0)
     for (;;) {
-        switch (state) {
-        case P_TASK_LOADED:
-            min_seed_len = (short)opt_msl;
-            if (L_ <= 0) goto c_task;
-            if (KIND == 1) {
-                full_match = 0; use_cached = 0; max_refpos = 0; min_intv = 1;
+        const int cur = GRP_REDUCE_MIN(lab);
+        if (cur >= L_STOP) break;
+        if (lab == cur) {
+            switch (cur) {
+            case L_TASK_LOADED:
+                min_seed_len = (short)opt_msl;
+                if (L_ <= 0) GO(L_C_TASK);
+                if (KIND == 1) {
+                    full_match = 0; use_cached = 0; max_refpos = 0; min_intv = 1;
+                    pivot = 0;
+                    GO(L_D1_LOOP);
+                }
+                if (KIND == 2) {
+                    if (use_cached) {                            // cache_refpos = SA[lo] (reference L934-939)
+                        req_ld(LD_POS, cache_refpos);
+                        STOP_AT(L_D2_C);
+                    }
+                    GO(L_D2_FIRST);
+                }
+                // KIND == 3
+                use_cached = 0; min_intv = (u32)A.opt.max_mem_intv; min_seed_len = (short)(opt_msl + 1);
+                full_match = (ix.mode == 3 && A.rd_full[rid] != 0) ? 1 : 0;
+                max_refpos = full_match ? (idx_t)A.rd_maxref[rid] : 0;
                 pivot = 0;
-                goto d1_loop;
-            }
-            if (KIND == 2) {
-                if (use_cached) {                            // cache_refpos = SA[lo] (reference L934-939)
-                    req_ld(LD_POS, cache_refpos);
-                    state = P_D2_C;
+                GO(L_D3_LOOP);
+
+            // ------------------------------------------------ T1: zig-zag (reference L913-972, L1691-1894)
+            case L_D1_LOOP:
+                if (KIND != 1) GO(L_C_TASK);
+                while (pivot < L_ && is_n(pivot)) pivot = (L_ - pivot < min_seed_len) ? L_ : (short)(pivot + 1);
+                if (pivot >= L_) {
+                    if (A.rd_full) { A.rd_full[rid] = full_match ? 1 : 0; A.rd_maxref[rid] = max_refpos; }
+                    GO(L_C_TASK);
+                }
+                if (pivot != 0 && !is_n(pivot - 1)) { sp = pivot; GO(L_D1_ZZ); }
+                // first search of a segment: always through the RMI
+                s_pivot = pivot; q_strand = 0; s_emit = 1; s_need = 1; s_msl = min_seed_len; s_mode = ST_RMI; s_isa = 0;
+                s_stepwise = 0; d_ret = L_C_D1_F;
+                GO(L_S_BEGIN);
+            case L_C_D1_F:
+                if (KIND != 1) GO(L_C_TASK);
+                if (ix.mode == 3 && lev == L_) {                 // whole read matched (L1870-1875)
+                    req_ld(LD_POS, lo);
+                    STOP_AT(L_D1_M);
+                }
+                pivot += lev;
+                GO(L_D1_LOOP);
+            case L_D1_M:
+                if (KIND != 1) GO(L_C_TASK);
+                full_match = 1; max_refpos = ld_val();
+                pivot += lev;
+                GO(L_D1_LOOP);
+            case L_D1_ZZ:
+                if (KIND != 1) GO(L_C_TASK);
+                for (;;) {
+                    if (sp >= L_) { pivot = L_; GO(L_D1_LOOP); }
+                    if (!is_n(sp)) break;
+                    if (L_ - sp < min_seed_len) { pivot = L_; sp = L_; }
+                    else { sp += 1; pivot += 1; }
+                }
+                as_pv = pivot; as_right = 0; as_emit = 0; as_ret = L_C_D1_L;
+                GO(L_AUTO_START);
+            case L_C_D1_L:
+                if (KIND != 1) GO(L_C_TASK);
+                pivot = pivot - lev + 1;
+                if (L_ - pivot < min_seed_len) { pivot = L_; GO(L_D1_LOOP); }
+                as_pv = pivot; as_right = 1; as_emit = 1; as_ret = L_C_D1_R;
+                GO(L_AUTO_START);
+            case L_C_D1_R:
+                if (KIND != 1) GO(L_C_TASK);
+                sp = pivot + lev;
+                pivot = sp;
+                GO(L_D1_ZZ);
+
+            // ------------------------------------------------ T2: reseeding (reference L1897-2126)
+            case L_D2_C:
+                if (KIND != 2) GO(L_C_TASK);
+                cache_refpos = ld_val();
+                GO(L_D2_FIRST);
+            case L_D2_FIRST:
+                as_pv = pivot; as_right = 1; as_emit = 0; as_ret = L_C_D2_F;
+                GO(L_AUTO_START);
+            case L_C_D2_F:
+                if (KIND != 2) GO(L_C_TASK);
+                next = pivot + lev; sp = pivot;
+                GO(L_D2_LOOP);
+            case L_D2_LOOP:
+                if (sp >= next) GO(L_C_TASK);
+                as_pv = pivot; as_right = 0; as_emit = 0; as_ret = L_C_D2_L;
+                GO(L_AUTO_START);
+            case L_C_D2_L:
+                if (KIND != 2) GO(L_C_TASK);
+                pivot = pivot - lev + 1;
+                if (next - pivot < min_seed_len) GO(L_C_TASK);
+                as_pv = pivot; as_right = 1; as_emit = 1; as_ret = L_C_D2_R;
+                GO(L_AUTO_START);
+            case L_C_D2_R:
+                if (KIND != 2) GO(L_C_TASK);
+                sp = pivot + lev;
+                pivot = sp;
+                GO(L_D2_LOOP);
+
+            // ------------------------------------------------ T3: third round (reference L974-1466)
+            case L_D3_LOOP:
+                if (KIND != 3) GO(L_C_TASK);
+                for (;;) {
+                    if (pivot >= L_ - min_seed_len + 1) break;
+                    if (is_n(pivot)) { pivot++; continue; }
+                    int V = next_n(pivot) - pivot;
+                    if (V < min_seed_len) { pivot += V; continue; }
                     break;
                 }
-                goto d2_first;
-            }
-            // KIND == 3
-            use_cached = 0; min_intv = (u32)A.opt.max_mem_intv; min_seed_len = (short)(opt_msl + 1);
-            full_match = (ix.mode == 3 && A.rd_full[rid] != 0) ? 1 : 0;
-            max_refpos = full_match ? (idx_t)A.rd_maxref[rid] : 0;
-            pivot = 0;
-            goto d3_loop;
-
-        // ------------------------------------------------ T1: zig-zag (reference L913-972, L1691-1894)
-        d1_loop:
-            if (KIND != 1) goto c_task;
-            while (pivot < L_ && is_n(pivot)) pivot = (L_ - pivot < min_seed_len) ? L_ : (short)(pivot + 1);
-            if (pivot >= L_) {
-                if (A.rd_full) { A.rd_full[rid] = full_match ? 1 : 0; A.rd_maxref[rid] = max_refpos; }
-                goto c_task;
-            }
-            if (pivot != 0 && !is_n(pivot - 1)) { sp = pivot; goto d1_zz; }
-            // first search of a segment: always through the RMI
-            s_pivot = pivot; q_strand = 0; s_emit = 1; s_need = 1; s_msl = min_seed_len; s_mode = ST_RMI; s_isa = 0;
-            s_stepwise = 0; d_ret = R_D1_F;
-            goto s_begin;
-        c_d1_f:
-            if (KIND != 1) goto c_task;
-            if (ix.mode == 3 && lev == L_) {                 // whole read matched (L1870-1875)
-                req_ld(LD_POS, lo);
-                state = P_D1_M;
-                break;
-            }
-            pivot += lev;
-            goto d1_loop;
-        case P_D1_M:
-            if (KIND != 1) goto c_task;
-            full_match = 1; max_refpos = ld_val();
-            pivot += lev;
-            goto d1_loop;
-        d1_zz:
-            if (KIND != 1) goto c_task;
-            if (sp >= L_) { pivot = L_; goto d1_loop; }
-            if (is_n(sp)) {
-                if (L_ - sp < min_seed_len) { pivot = L_; sp = L_; }
-                else { sp += 1; pivot += 1; }
-                goto d1_zz;
-            }
-            as_pv = pivot; as_right = 0; as_emit = 0; as_ret = R_D1_L;
-            goto auto_start;
-        c_d1_l:
-            if (KIND != 1) goto c_task;
-            pivot = pivot - lev + 1;
-            if (L_ - pivot < min_seed_len) { pivot = L_; goto d1_loop; }
-            as_pv = pivot; as_right = 1; as_emit = 1; as_ret = R_D1_R;
-            goto auto_start;
-        c_d1_r:
-            if (KIND != 1) goto c_task;
-            sp = pivot + lev;
-            pivot = sp;
-            goto d1_zz;
-
-        // ------------------------------------------------ T2: reseeding (reference L1897-2126)
-        case P_D2_C:
-            if (KIND != 2) goto c_task;
-            cache_refpos = ld_val();
-        d2_first:
-            as_pv = pivot; as_right = 1; as_emit = 0; as_ret = R_D2_F;
-            goto auto_start;
-        c_d2_f:
-            if (KIND != 2) goto c_task;
-            next = pivot + lev; sp = pivot;
-        d2_loop:
-            if (sp >= next) goto c_task;
-            as_pv = pivot; as_right = 0; as_emit = 0; as_ret = R_D2_L;
-            goto auto_start;
-        c_d2_l:
-            if (KIND != 2) goto c_task;
-            pivot = pivot - lev + 1;
-            if (next - pivot < min_seed_len) goto c_task;
-            as_pv = pivot; as_right = 1; as_emit = 1; as_ret = R_D2_R;
-            goto auto_start;
-        c_d2_r:
-            if (KIND != 2) goto c_task;
-            sp = pivot + lev;
-            pivot = sp;
-            goto d2_loop;
-
-        // ------------------------------------------------ T3: third round (reference L974-1466)
-        d3_loop:
-            if (KIND != 3) goto c_task;
-            for (;;) {
-                if (pivot >= L_ - min_seed_len + 1) break;
-                if (is_n(pivot)) { pivot++; continue; }
-                int V = next_n(pivot) - pivot;
-                if (V < min_seed_len) { pivot += V; continue; }
-                break;
-            }
-            if (pivot >= L_ - min_seed_len + 1) goto c_task;
-            s_pivot = pivot; q_strand = 0; s_emit = 0; s_need = min_intv; s_msl = min_seed_len; s_stepwise = 1;
-            d_ret = R_D3_S;
-            if (full_match) { s_mode = ST_EXACT; s_hint = max_refpos + (idx_t)pivot; s_isa = 1; }
-            else { s_mode = ST_RMI; s_isa = 0; }
-            goto s_begin;
-        c_d3_s:
-            if (KIND != 3) goto c_task;
-            if (lev < min_seed_len) { pivot += min_seed_len; goto d3_loop; }
-            r3_last_lo = lo; r3_last_cnt = 0; it = 0;
-        d3_levels:
-            if (KIND != 3) goto c_task;
-            {
-                u64 cnt = (u64)(hi - lo) + 1;
-                if (cnt >= (u64)min_intv) {                                  // L1243-1251
-                    if (r3_last_cnt > 0) push(pivot, pivot + max((int)lev + 1, (int)min_seed_len), r3_last_lo, (u64)r3_last_cnt);
-                    pivot += lev + 1;
-                    goto d3_loop;
+                if (pivot >= L_ - min_seed_len + 1) GO(L_C_TASK);
+                s_pivot = pivot; q_strand = 0; s_emit = 0; s_need = min_intv; s_msl = min_seed_len; s_stepwise = 1;
+                d_ret = L_C_D3_S;
+                if (full_match) { s_mode = ST_EXACT; s_hint = max_refpos + (idx_t)pivot; s_isa = 1; }
+                else { s_mode = ST_RMI; s_isa = 0; }
+                GO(L_S_BEGIN);
+            case L_C_D3_S:
+                if (KIND != 3) GO(L_C_TASK);
+                if (lev < min_seed_len) { pivot += min_seed_len; GO(L_D3_LOOP); }
+                r3_last_lo = lo; r3_last_cnt = 0; it = 0;
+                GO(L_D3_LEVELS);
+            case L_D3_LEVELS:
+                if (KIND != 3) GO(L_C_TASK);
+                {
+                    u64 cnt = (u64)(hi - lo) + 1;
+                    if (cnt >= (u64)min_intv) {                                  // L1243-1251
+                        if (r3_last_cnt > 0) push(pivot, pivot + max((int)lev + 1, (int)min_seed_len), r3_last_lo, (u64)r3_last_cnt);
+                        pivot += lev + 1;
+                        GO(L_D3_LOOP);
+                    }
+                    if (max(nbl, nbr) < min_seed_len || ++it > 400) {            // L1252-1258
+                        push(pivot, pivot + min_seed_len, lo, cnt);
+                        pivot += min_seed_len;
+                        GO(L_D3_LOOP);
+                    }
+                    r3_last_lo = lo; r3_last_cnt = (idx_t)cnt;
                 }
-                if (max(nbl, nbr) < min_seed_len || ++it > 400) {            // L1252-1258
-                    push(pivot, pivot + min_seed_len, lo, cnt);
-                    pivot += min_seed_len;
-                    goto d3_loop;
-                }
-                r3_last_lo = lo; r3_last_cnt = (idx_t)cnt;
-            }
-            lv_limit = (idx_t)min_intv; lv_ret = 1;
-            goto lv_begin;
+                lv_limit = (idx_t)min_intv; lv_ret = 1;
+                GO(L_LV_BEGIN);
 
-        // ------------------------------------------------ start selection (reference L1741-1816 / L1926-2040)
-        auto_start:
-            s_pivot = as_pv; q_strand = as_right ? 0 : 1; s_emit = as_emit; s_need = min_intv; s_msl = min_seed_len;
-            s_stepwise = 0; d_ret = as_ret; s_mode = ST_RMI; s_isa = 0;
-            if (KIND != 1 && ix.mode == 3) {
-                if (full_match) {
-                    s_mode = ST_EXACT; s_isa = 1;
-                    s_hint = as_right ? max_refpos + (idx_t)as_pv : n - max_refpos - (idx_t)as_pv - 1;
-                } else if (KIND == 2 && use_cached) {
-                    if (as_right && cache_pivot_end >= as_pv + 18 && as_pv >= cache_pivot) {
-                        s_mode = ST_NEAR; s_isa = 1; s_hint = cache_refpos + (idx_t)(as_pv - cache_pivot);
-                    } else if (!as_right && as_pv < cache_pivot_end && cache_pivot + 18 <= as_pv) {
-                        s_mode = ST_NEAR; s_isa = 1; s_hint = n + (idx_t)cache_pivot - cache_refpos - (idx_t)as_pv - 1;
+            // ------------------------------------------------ start selection (reference L1741-1816 / L1926-2040)
+            case L_AUTO_START:
+                s_pivot = as_pv; q_strand = as_right ? 0 : 1; s_emit = as_emit; s_need = min_intv; s_msl = min_seed_len;
+                s_stepwise = 0; d_ret = as_ret; s_mode = ST_RMI; s_isa = 0;
+                if (KIND != 1 && ix.mode == 3) {
+                    if (full_match) {
+                        s_mode = ST_EXACT; s_isa = 1;
+                        s_hint = as_right ? max_refpos + (idx_t)as_pv : n - max_refpos - (idx_t)as_pv - 1;
+                    } else if (KIND == 2 && use_cached) {
+                        if (as_right && cache_pivot_end >= as_pv + 18 && as_pv >= cache_pivot) {
+                            s_mode = ST_NEAR; s_isa = 1; s_hint = cache_refpos + (idx_t)(as_pv - cache_pivot);
+                        } else if (!as_right && as_pv < cache_pivot_end && cache_pivot + 18 <= as_pv) {
+                            s_mode = ST_NEAR; s_isa = 1; s_hint = n + (idx_t)cache_pivot - cache_refpos - (idx_t)as_pv - 1;
+                        }
                     }
                 }
-            }
-        // ------------------------------------------------ search (right_smem_search / mem_search / *_tradeoff)
-        s_begin:
-            if (STATS) st.search++;
-            if (q_strand == 0) { q_from = s_pivot; q_V = (short)(next_n(s_pivot) - s_pivot); }
-            else { q_from = (short)(L_ - 1 - s_pivot); q_V = (short)(s_pivot - prev_n(s_pivot)); }
-            {
-                const u64 q0 = qword(0);
-                q0lo = (u32)q0; q0hi = (u32)(q0 >> 32);
-                if (KIND != 1 && s_isa) { req_ld(LD_ISA, s_hint); state = P_S_ISA; break; }
-                const u64 key = rmi_key_of(q0, q_V);                 // RMI key = Tokenization (L795-901)
-                req_rmi(RMI_L2, key >> ix.bit_shift);
-                state = P_S_RMI1;
-            }
-            break;
-        case P_S_ISA:
-            if (KIND == 1) goto c_task;
-            s_hint = ld_val();
-            if (s_mode == ST_EXACT) {
-                req_contig(s_hint > 3 ? s_hint - 3 : 0, q_V, s_hint > 0 ? s_hint - 1 : 0, s_hint + 1 < n ? s_hint + 1 : n - 1);
-                state = P_S_EXACT;
-                break;
-            }
-            center = s_hint; rad_lo = rad_hi = 2;
-            goto loc_init;
-        case P_S_EXACT:
-            goto located;
-        case P_S_RMI1:
-        case P_S_RMI2:
-            {
-                const uint4 ra = *GRP_STGQ(0), rb = *GRP_STGQ(1);
-                const double rmi_a = __longlong_as_double((long long)((u64)ra.x | ((u64)ra.y << 32)));
-                const double rmi_b = __longlong_as_double((long long)((u64)ra.z | ((u64)ra.w << 32)));
-                const u64 rmi_e = (u64)rb.x | ((u64)rb.y << 32);
-                const u64 key = rmi_key_of((u64)q0lo | ((u64)q0hi << 32), q_V);
-                const double p = fma(rmi_b, __ull2double_rn(key), rmi_a);
-                if (state == P_S_RMI1 && (rmi_e >> 63)) {
-                    u64 s0 = (rmi_e >> 32) & 0x7fffffff;
-                    double bound = (double)(rmi_e & 0xffffffffull) - 1;
-                    u64 sub = p < 0.0 ? 0 : (p > bound ? (u64)bound : (u64)p);
-                    req_rmi(RMI_L1, s0 + sub);
-                    state = P_S_RMI2;
-                    break;
+                GO(L_S_BEGIN);
+            // ------------------------------------------------ search (right_smem_search / mem_search / *_tradeoff)
+            case L_S_BEGIN:
+                if (STATS) st.search++;
+                if (q_strand == 0) { q_from = s_pivot; q_V = (short)(next_n(s_pivot) - s_pivot); }
+                else { q_from = (short)(L_ - 1 - s_pivot); q_V = (short)(s_pivot - prev_n(s_pivot)); }
+                {
+                    const u64 q0 = qword(0);
+                    q0lo = (u32)q0; q0hi = (u32)(q0 >> 32);
+                    if (KIND != 1 && s_isa) { req_ld(LD_ISA, s_hint); STOP_AT(L_S_ISA); }
+                    const u64 key = rmi_key_of(q0, q_V);                 // RMI key = Tokenization (L795-901)
+                    req_rmi(RMI_L2, key >> ix.bit_shift);
                 }
-                double bound = (double)ix.sa_num - 1.0;
-                center = p < 0.0 ? 0 : (p > bound ? (idx_t)bound : (idx_t)p);
-                rad_lo = (idx_t)((rmi_e >> 32) & 0x3fffffff);
-                rad_hi = (idx_t)(rmi_e & 0x7fffffff);
-            }
-        loc_init:
-            lo_b = 0; hi_b = n; it = 0;
-            // prediction errors concentrate near zero: try the block around the prediction first
-            if ((u64)rad_lo + (u64)rad_hi + 2 > 8 && (u64)rad_lo + (u64)rad_hi <= 40) {
-                req_contig(center > 4 ? center - 4 : 0, q_V, center > 1 ? center - 1 : 0, center + 2 < n ? center + 2 : n - 1);
-                state = P_S_CENTER;
-                break;
-            }
-            goto loc_next;
-        case P_S_CENTER:
-            {
-                int c = lead_less();
-                bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + (idx_t)nvalid == n;
-                if (left_ok && right_ok) goto located;
-                if (!left_ok) hi_b = base; else lo_b = base + (idx_t)nvalid;
-            }
-        loc_next:
-            {
-                u64 c64 = center;
-                u64 pa64 = c64 > (u64)rad_lo ? c64 - (u64)rad_lo : 0;
-                u64 pb64 = c64 + (u64)rad_hi + 1;
-                idx_t pa = pa64 < (u64)lo_b ? lo_b : (pa64 > (u64)hi_b ? hi_b : (idx_t)pa64);
-                idx_t pb = pb64 < (u64)lo_b ? lo_b : (pb64 > (u64)hi_b ? hi_b : (idx_t)pb64);
-                idx_t span = pb - pa;
-                k_contig = span <= 6;
+                STOP_AT(L_S_RMI1);
+            case L_S_ISA:
+                if (KIND == 1) GO(L_C_TASK);
+                s_hint = ld_val();
+                if (s_mode == ST_EXACT) {
+                    req_contig(s_hint > 3 ? s_hint - 3 : 0, q_V, s_hint > 0 ? s_hint - 1 : 0, s_hint + 1 < n ? s_hint + 1 : n - 1);
+                    STOP_AT(L_LOCATED);
+                }
+                center = s_hint; rad_lo = rad_hi = 2;
+                GO(L_LOC_INIT);
+            case L_S_RMI1:
+            case L_S_RMI2:
+                {
+                    const uint4 ra = *GRP_STGQ(0), rb = *GRP_STGQ(1);
+                    const double rmi_a = __longlong_as_double((long long)((u64)ra.x | ((u64)ra.y << 32)));
+                    const double rmi_b = __longlong_as_double((long long)((u64)ra.z | ((u64)ra.w << 32)));
+                    const u64 rmi_e = (u64)rb.x | ((u64)rb.y << 32);
+                    const u64 key = rmi_key_of((u64)q0lo | ((u64)q0hi << 32), q_V);
+                    const double p = fma(rmi_b, __ull2double_rn(key), rmi_a);
+                    if (cur == L_S_RMI1 && (rmi_e >> 63)) {
+                        u64 s0 = (rmi_e >> 32) & 0x7fffffff;
+                        double bound = (double)(rmi_e & 0xffffffffull) - 1;
+                        u64 sub = p < 0.0 ? 0 : (p > bound ? (u64)bound : (u64)p);
+                        req_rmi(RMI_L1, s0 + sub);
+                        STOP_AT(L_S_RMI2);
+                    }
+                    double bound = (double)ix.sa_num - 1.0;
+                    center = p < 0.0 ? 0 : (p > bound ? (idx_t)bound : (idx_t)p);
+                    rad_lo = (idx_t)((rmi_e >> 32) & 0x3fffffff);
+                    rad_hi = (idx_t)(rmi_e & 0x7fffffff);
+                }
+                GO(L_LOC_INIT);
+            case L_LOC_INIT:
+                lo_b = 0; hi_b = n; it = 0;
+                // prediction errors concentrate near zero: try the block around the prediction first
+                if ((u64)rad_lo + (u64)rad_hi + 2 > 8 && (u64)rad_lo + (u64)rad_hi <= 40) {
+                    req_contig(center > 4 ? center - 4 : 0, q_V, center > 1 ? center - 1 : 0, center + 2 < n ? center + 2 : n - 1);
+                    STOP_AT(L_S_CENTER);
+                }
+                GO(L_LOC_NEXT);
+            case L_S_CENTER:
+                {
+                    int c = lead_less();
+                    bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + (idx_t)nvalid == n;
+                    if (left_ok && right_ok) GO(L_LOCATED);
+                    if (!left_ok) hi_b = base; else lo_b = base + (idx_t)nvalid;
+                }
+                GO(L_LOC_NEXT);
+            case L_LOC_NEXT:
+                {
+                    u64 c64 = center;
+                    u64 pa64 = c64 > (u64)rad_lo ? c64 - (u64)rad_lo : 0;
+                    u64 pb64 = c64 + (u64)rad_hi + 1;
+                    idx_t pa = pa64 < (u64)lo_b ? lo_b : (pa64 > (u64)hi_b ? hi_b : (idx_t)pa64);
+                    idx_t pb = pb64 < (u64)lo_b ? lo_b : (pb64 > (u64)hi_b ? hi_b : (idx_t)pb64);
+                    idx_t span = pb - pa;
+                    k_contig = span <= 6;
+                    if (k_contig) {
+                        idx_t slack = (6 - span) / 2;
+                        req_contig(pa > 1 + slack ? pa - 1 - slack : 0, q_V, pa > 0 ? pa - 1 : 0, pb < n ? pb : n - 1);
+                    } else {
+                        k_stride = (span + 7) / 8; k_pa = pa;
+                        idx_t first = pa + k_stride - 1;
+                        int cnt = 0;
+                        if (first < pb) { idx_t c = (pb - 1 - first) / k_stride + 1; cnt = c < 8 ? (int)c : 8; }
+                        req_block(first, (sidx_t)k_stride, cnt, q_V);
+                        if (STATS) st.kary++;
+                    }
+                }
+                REQ_OR_GO(L_S_LOC);
+            case L_S_LOC:
                 if (k_contig) {
-                    idx_t slack = (6 - span) / 2;
-                    req_contig(pa > 1 + slack ? pa - 1 - slack : 0, q_V, pa > 0 ? pa - 1 : 0, pb < n ? pb : n - 1);
+                    int c = lead_less();
+                    bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + (idx_t)nvalid == n;
+                    if (left_ok && right_ok) GO(L_LOCATED);
+                    if (!left_ok) hi_b = base; else lo_b = base + (idx_t)nvalid;
                 } else {
-                    k_stride = (span + 7) / 8; k_pa = pa;
-                    idx_t first = pa + k_stride - 1;
-                    int cnt = 0;
-                    if (first < pb) { idx_t c = (pb - 1 - first) / k_stride + 1; cnt = c < 8 ? (int)c : 8; }
-                    req_block(first, (sidx_t)k_stride, cnt, q_V);
-                    if (STATS) st.kary++;
+                    int c = lead_less();
+                    if (c > 0) { idx_t nl = k_pa + (idx_t)c * k_stride; if (nl > lo_b) lo_b = nl; }
+                    if (c < r_count) { idx_t nh = k_pa + (idx_t)(c + 1) * k_stride - 1; if (nh < hi_b) hi_b = nh; }
                 }
-                state = P_S_LOC;
-            }
-            break;
-        case P_S_LOC:
-            if (k_contig) {
-                int c = lead_less();
-                bool left_ok = c > 0 || base == 0, right_ok = c < nvalid || base + (idx_t)nvalid == n;
-                if (left_ok && right_ok) goto located;
-                if (!left_ok) hi_b = base; else lo_b = base + (idx_t)nvalid;
-            } else {
-                int c = lead_less();
-                if (c > 0) { idx_t nl = k_pa + (idx_t)c * k_stride; if (nl > lo_b) lo_b = nl; }
-                if (c < r_count) { idx_t nh = k_pa + (idx_t)(c + 1) * k_stride - 1; if (nh < hi_b) hi_b = nh; }
-            }
-            rad_lo = rad_lo > (IDX_MAX >> 4) ? IDX_MAX >> 1 : rad_lo * 8 + 8;
-            rad_hi = rad_hi > (IDX_MAX >> 4) ? IDX_MAX >> 1 : rad_hi * 8 + 8;
-            if (++it < 64) goto loc_next;
-            // not reached for a sorted suffix array: use the last block
-        located:
-            // ---- first level = maximal lcp in the block, [lo,hi] = its interval ----
-            bl_off = rl_off; rl_off ^= 8;                   // keep this block's LCPs; later probes use the other buffer
-            {
-                int m = -1, first = 0;
+                rad_lo = rad_lo > (IDX_MAX >> 4) ? IDX_MAX >> 1 : rad_lo * 8 + 8;
+                rad_hi = rad_hi > (IDX_MAX >> 4) ? IDX_MAX >> 1 : rad_hi * 8 + 8;
+                if (++it < 64) GO(L_LOC_NEXT);
+                GO(L_LOCATED);                                   // not reached for a sorted suffix array: use the last block
+            case L_LOCATED:
+                // ---- first level = maximal lcp in the block, [lo,hi] = its interval ----
+                bl_off = rl_off; rl_off ^= 8;                   // keep this block's LCPs; later probes use the other buffer
+                {
+                    int m = -1, first = 0;
 #pragma unroll
-                for (int j = 0; j < 8; j++) { int l = j < nvalid ? BL(j) : -1; if (l > m) { m = l; first = j; } }
-                lev = (short)m;
-                int last = first;
-                while (last + 1 < nvalid && BL(last + 1) >= lev) last++;
-                lo = base + (idx_t)first; hi = base + (idx_t)last;
-                const bool exact = s_emit && lev >= s_msl;
-                if (!exact && (u64)(hi - lo) + 1 >= (u64)s_need) { nbl = nbr = lev; goto leveled; }
-                lv_limit = exact ? IDX_MAX : (idx_t)s_need;
-                nbl = first > 0 ? (short)BL(first - 1) : (base == 0 ? 0 : -1);
-                nbr = last < nvalid - 1 ? (short)BL(last + 1) : (base + (idx_t)nvalid == n ? 0 : -1);
-            }
-            if (nbl < 0) { e_dir = -1; e_from = lo; e_L = lev; e_limit = lv_limit; e_ret = R_INIT_L; goto e_begin; }
-        init_right:
-            if (nbr < 0) { e_dir = +1; e_from = hi; e_L = lev; e_limit = lv_limit; e_ret = R_INIT_R; goto e_begin; }
-        leveled:
-            if (KIND == 3 && s_stepwise) goto search_done;
-            it = 0;
-        level_loop:
-            if (KIND != 1 && (u64)(hi - lo) + 1 < (u64)s_need && it++ < 400) {
-                lv_limit = (s_emit && max(nbl, nbr) >= s_msl) ? IDX_MAX : (idx_t)s_need;
-                lv_ret = 0;
-                goto lv_begin;
-            }
-            if (KIND != 3 && s_emit && lev >= s_msl) push(s_pivot, s_pivot + lev, lo, (u64)(hi - lo) + 1);
-        search_done:
-            // straight to the driver continuation of this kind
-            if (KIND == 1) { if (d_ret == R_D1_F) goto c_d1_f; if (d_ret == R_D1_L) goto c_d1_l; goto c_d1_r; }
-            if (KIND == 2) { if (d_ret == R_D2_F) goto c_d2_f; if (d_ret == R_D2_L) goto c_d2_l; goto c_d2_r; }
-            goto c_d3_s;
-
-        // ------------------------------------------------ one level drop (reference L2569-2574)
-        lv_begin:
-            if (KIND == 1) goto c_task;
-            lev = nbl > nbr ? nbl : nbr;
-            if (lev <= 0) { lev = 0; lo = 0; hi = n - 1; nbl = nbr = 0; goto lv_done; }
-            if (nbl >= lev) {
-                if (lo > base && lo <= base + (idx_t)nvalid) {            // lo-1 lies in the located block
-                    int z = (int)(lo - base) - 1;
-                    while (z >= 0 && BL(z) >= lev) z--;
-                    if (z < 0) { lo = base; nbl = base == 0 ? 0 : -1; }
-                    else { lo = base + (idx_t)(z + 1); nbl = (short)BL(z); }
-                } else nbl = lo == 0 ? 0 : -1;
-                if (nbl < 0) { e_dir = -1; e_from = lo; e_L = lev; e_limit = lv_limit; e_ret = R_LV_L; goto e_begin; }
-            }
-        lv_right:
-            if (nbr >= lev) {
-                if (hi + 1 >= base && hi + 1 < base + (idx_t)nvalid) {    // hi+1 lies in the located block
-                    int z = (int)(hi + 1 - base);
-                    while (z < nvalid && BL(z) >= lev) z++;
-                    if (z >= nvalid) { hi = base + (idx_t)nvalid - 1; nbr = base + (idx_t)nvalid == n ? 0 : -1; }
-                    else { hi = base + (idx_t)z - 1; nbr = (short)BL(z); }
-                } else nbr = hi == n - 1 ? 0 : -1;
-                if (nbr < 0) { e_dir = +1; e_from = hi; e_L = lev; e_limit = lv_limit; e_ret = R_LV_R; goto e_begin; }
-            }
-        lv_done:
-            if (lv_ret == 0) goto level_loop;
-            goto d3_levels;
-
-        // ------------------------------------------------ extension: 8-ary gallop, then 8-ary narrowing
-        e_begin:
-            e_cur = e_from; e_s = 1; e_sh = 0; e_up = 1; e_guard = 0;
-        e_probe:
-            if (++e_guard > 400) { e_edge = e_cur; e_nb = 0; goto e_done; }
-            if (e_dir > 0) {
-                u64 room = (u64)(n - 1 - e_cur) >> e_sh;
-                e_cnt = room < 8 ? (short)room : 8;
-                req_block(e_cur + e_s, (sidx_t)e_s, e_cnt, e_L);
-            } else {
-                u64 room = (u64)e_cur >> e_sh;
-                e_cnt = room < 8 ? (short)room : 8;
-                req_block(e_cur - e_s, -(sidx_t)e_s, e_cnt, e_L);
-            }
-            if (STATS) st.ext++;
-            state = P_E;
-            break;
-        case P_E:
-            {
-                int c = 0;
-                while (c < e_cnt && RL(c) >= e_L) c++;
-                e_cur = e_dir > 0 ? e_cur + (idx_t)c * e_s : e_cur - (idx_t)c * e_s;
-                if (c == 8) {
-                    idx_t gone = e_dir > 0 ? e_cur - e_from : e_from - e_cur;
-                    if (gone >= e_limit) { e_edge = e_cur; e_nb = e_L; goto e_done; }
-                    if (e_up && e_s <= (n >> 3)) { e_s *= 8; e_sh += 3; }
-                    goto e_probe;
+                    for (int j = 0; j < 8; j++) { int l = j < nvalid ? BL(j) : -1; if (l > m) { m = l; first = j; } }
+                    lev = (short)m;
+                    int last = first;
+                    while (last + 1 < nvalid && BL(last + 1) >= lev) last++;
+                    lo = base + (idx_t)first; hi = base + (idx_t)last;
+                    const bool exact = s_emit && lev >= s_msl;
+                    if (!exact && (u64)(hi - lo) + 1 >= (u64)s_need) { nbl = nbr = lev; GO(L_LEVELED); }
+                    lv_limit = exact ? IDX_MAX : (idx_t)s_need;
+                    nbl = first > 0 ? (short)BL(first - 1) : (base == 0 ? 0 : -1);
+                    nbr = last < nvalid - 1 ? (short)BL(last + 1) : (base + (idx_t)nvalid == n ? 0 : -1);
                 }
-                if (e_s == 1) { e_nb = c < e_cnt ? (short)RL(c) : 0; e_edge = e_cur; goto e_done; }
-                e_up = 0;
-                e_s >>= 3; e_sh -= 3;
-                goto e_probe;
+                if (nbl < 0) { e_dir = -1; e_from = lo; e_L = lev; e_limit = lv_limit; e_ret = R_INIT_L; GO(L_E_BEGIN); }
+                GO(L_INIT_RIGHT);
+            case L_INIT_RIGHT:
+                if (nbr < 0) { e_dir = +1; e_from = hi; e_L = lev; e_limit = lv_limit; e_ret = R_INIT_R; GO(L_E_BEGIN); }
+                GO(L_LEVELED);
+            case L_LEVELED:
+                if (KIND == 3 && s_stepwise) GO(L_SEARCH_DONE);
+                it = 0;
+                GO(L_LEVEL_LOOP);
+            case L_LEVEL_LOOP:
+                if (KIND != 1 && (u64)(hi - lo) + 1 < (u64)s_need && it++ < 400) {
+                    lv_limit = (s_emit && max(nbl, nbr) >= s_msl) ? IDX_MAX : (idx_t)s_need;
+                    lv_ret = 0;
+                    GO(L_LV_BEGIN);
+                }
+                if (KIND != 3 && s_emit && lev >= s_msl) push(s_pivot, s_pivot + lev, lo, (u64)(hi - lo) + 1);
+                GO(L_SEARCH_DONE);
+            case L_SEARCH_DONE:
+                GO(d_ret);                                       // the driver continuation of this search
+
+            // ------------------------------------------------ one level drop (reference L2569-2574)
+            case L_LV_BEGIN:
+                if (KIND == 1) GO(L_C_TASK);
+                lev = nbl > nbr ? nbl : nbr;
+                if (lev <= 0) { lev = 0; lo = 0; hi = n - 1; nbl = nbr = 0; GO(L_LV_DONE); }
+                if (nbl >= lev) {
+                    if (lo > base && lo <= base + (idx_t)nvalid) {            // lo-1 lies in the located block
+                        int z = (int)(lo - base) - 1;
+                        while (z >= 0 && BL(z) >= lev) z--;
+                        if (z < 0) { lo = base; nbl = base == 0 ? 0 : -1; }
+                        else { lo = base + (idx_t)(z + 1); nbl = (short)BL(z); }
+                    } else nbl = lo == 0 ? 0 : -1;
+                    if (nbl < 0) { e_dir = -1; e_from = lo; e_L = lev; e_limit = lv_limit; e_ret = R_LV_L; GO(L_E_BEGIN); }
+                }
+                GO(L_LV_RIGHT);
+            case L_LV_RIGHT:
+                if (nbr >= lev) {
+                    if (hi + 1 >= base && hi + 1 < base + (idx_t)nvalid) {    // hi+1 lies in the located block
+                        int z = (int)(hi + 1 - base);
+                        while (z < nvalid && BL(z) >= lev) z++;
+                        if (z >= nvalid) { hi = base + (idx_t)nvalid - 1; nbr = base + (idx_t)nvalid == n ? 0 : -1; }
+                        else { hi = base + (idx_t)z - 1; nbr = (short)BL(z); }
+                    } else nbr = hi == n - 1 ? 0 : -1;
+                    if (nbr < 0) { e_dir = +1; e_from = hi; e_L = lev; e_limit = lv_limit; e_ret = R_LV_R; GO(L_E_BEGIN); }
+                }
+                GO(L_LV_DONE);
+            case L_LV_DONE:
+                if (lv_ret == 0) GO(L_LEVEL_LOOP);
+                GO(L_D3_LEVELS);
+
+            // ------------------------------------------------ extension: 8-ary gallop, then 8-ary narrowing
+            case L_E_BEGIN:
+                e_cur = e_from; e_s = 1; e_sh = 0; e_up = 1; e_guard = 0;
+                GO(L_E_PROBE);
+            case L_E_PROBE:
+                if (++e_guard > 400) { e_edge = e_cur; e_nb = 0; GO(L_E_DONE); }
+                if (e_dir > 0) {
+                    u64 room = (u64)(n - 1 - e_cur) >> e_sh;
+                    e_cnt = room < 8 ? (short)room : 8;
+                    req_block(e_cur + e_s, (sidx_t)e_s, e_cnt, e_L);
+                } else {
+                    u64 room = (u64)e_cur >> e_sh;
+                    e_cnt = room < 8 ? (short)room : 8;
+                    req_block(e_cur - e_s, -(sidx_t)e_s, e_cnt, e_L);
+                }
+                if (STATS) st.ext++;
+                REQ_OR_GO(L_P_E);
+            case L_P_E:
+                {
+                    int c = 0;
+                    while (c < e_cnt && RL(c) >= e_L) c++;
+                    e_cur = e_dir > 0 ? e_cur + (idx_t)c * e_s : e_cur - (idx_t)c * e_s;
+                    if (c == 8) {
+                        idx_t gone = e_dir > 0 ? e_cur - e_from : e_from - e_cur;
+                        if (gone >= e_limit) { e_edge = e_cur; e_nb = e_L; GO(L_E_DONE); }
+                        if (e_up && e_s <= (n >> 3)) { e_s *= 8; e_sh += 3; }
+                        GO(L_E_PROBE);
+                    }
+                    if (e_s == 1) { e_nb = c < e_cnt ? (short)RL(c) : 0; e_edge = e_cur; GO(L_E_DONE); }
+                    e_up = 0;
+                    e_s >>= 3; e_sh -= 3;
+                }
+                GO(L_E_PROBE);
+            case L_E_DONE:
+                if (e_ret == R_INIT_L) { lo = e_edge; nbl = e_nb; GO(L_INIT_RIGHT); }
+                if (e_ret == R_INIT_R) { hi = e_edge; nbr = e_nb; GO(L_LEVELED); }
+                if (e_ret == R_LV_L) { lo = e_edge; nbl = e_nb; GO(L_LV_RIGHT); }
+                hi = e_edge; nbr = e_nb;
+                GO(L_LV_DONE);
+            default:                                             // L_C_TASK: the task has ended
+                ended = true;
+                mreq = M_NONE;
+                lab = L_STOP;
+                break;
             }
-        e_done:
-            switch (e_ret) {
-            case R_INIT_L: lo = e_edge; nbl = e_nb; goto init_right;
-            case R_INIT_R: hi = e_edge; nbr = e_nb; goto leveled;
-            case R_LV_L: lo = e_edge; nbl = e_nb; goto lv_right;
-            default: hi = e_edge; nbr = e_nb; goto lv_done;
-            }
-        default:
-        c_task:
-            ended = true;
-            mreq = M_NONE;
-            return;
         }
-        if (mreq != M_NONE) return;
-        // a request for zero entries (e.g. an extension at the array end) completes at once: re-enter the state
+    next_block:;
     }
+#undef GO
+#undef STOP_AT
+#undef REQ_OR_GO
 #undef RL
 #undef BL
 }
@@ -884,22 +903,22 @@ __device__ __forceinline__ uint4 ld_state16(const volatile unsigned char *p)
 }
 
 template <int KIND, bool WIDE, bool LONG, bool STATS>
-__global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
+__global__ void __launch_bounds__(1024, 1) k_grp(IndexView ix, Args A)
 {
     typedef Lay<WIDE, LONG> L;
     typedef typename IdxT<WIDE>::type idx_t;
     GRP_SMEM_DECL;
     unsigned char *const smb = grp_smem;
     const int lane = GRP_LANE();
+    // [0..3] tokens of the four pools, [4..7] task counts of the pools, [8] live slots
     volatile u32 *const tok = reinterpret_cast<volatile u32 *>(smb + L::OFF_TOK);
+    volatile int *const cnt = reinterpret_cast<volatile int *>(smb + L::OFF_TOK) + 4;
     volatile unsigned char *const sst = smb + L::OFF_SST + lane * 16;      // this lane class's state bytes
-    // pools this kind can populate
-    constexpr u32 POOLS = ((1u << NPOOL) - 1) & ~(KIND == 1 ? (1u << P_S_ISA) | (1u << P_S_EXACT) | (1u << P_D2_C) : 0u) &
-                          ~(KIND == 2 ? (1u << P_D1_M) : 0u) & ~(KIND == 3 ? (1u << P_D1_M) | (1u << P_D2_C) : 0u);
 
     // ---- init: every slot empty (slots beyond K are dead), every token free ----
+    const u32 lanes_here = blockDim.x < 32u ? blockDim.x : 32u;
     for (u32 i = threadIdx.x; i < 512; i += blockDim.x) smb[L::OFF_SST + i] = (i & 15) < (u32)L::K ? (unsigned char)Q_EMPTY : (unsigned char)SL_DEAD;
-    for (u32 i = threadIdx.x; i < 32; i += blockDim.x) tok[i] = i == 16 ? (u32)L::K * (blockDim.x < 32u ? blockDim.x : 32u) : 0u;   // live slots
+    for (u32 i = threadIdx.x; i < 32; i += blockDim.x) tok[i] = (i == 8 || i == 4 + PL_EMPTY) ? (u32)L::K * lanes_here : 0u;
     GRP_SYNCTHREADS();
 
     OutState out; out.pslot = out.pend = out.tslot = out.tend = 0;
@@ -908,29 +927,38 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
 #pragma unroll
     for (int d = 0; d < GRP_DEPTH; d++) { pend[d] = GRP_NONE; pkind[d] = B_SIMPLE; }
     int npend = 0;
-    int rr = (int)(GRP_WARP() % NPOOL);
+
+    // move tasks between pools: the state byte of each moved slot, then one counter update per destination pool
+    auto publish = [&](const u32 sid, const int newbyte) {
+        GRP_FENCE();
+        if (newbyte >= 0) sst[sid >> 5] = (unsigned char)newbyte;
+        const int np = newbyte < 0 ? -1 : (newbyte < 0x40 ? (int)PL_CTL : (newbyte == SL_DEAD ? -1 : newbyte - 0x40 + 1));
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const u32 m = GRP_BALLOT(np == p);
+            if (m && lane == 0) atomicAdd(const_cast<int *>(&cnt[p]), __popc(m));
+        }
+    };
 
     for (;;) {
-        // ================================ pick a pool ================================
+        // ================================ pick a pool: the fullest one ================================
         int pool = -1, pool_n = 0;
         if (npend < GRP_DEPTH) {
-            const uint4 v = ld_state16(sst);
-            for (int c = 0; c < NPOOL; c++) {
-                int s = rr + c; if (s >= NPOOL) s -= NPOOL;
-                if (!((POOLS >> s) & 1)) continue;
-                const u32 pat = (u32)s * 0x01010101u;
-                const u32 has = zero_bytes(v.x ^ pat) | zero_bytes(v.y ^ pat) | zero_bytes(v.z ^ pat) | zero_bytes(v.w ^ pat);
-                const int nl = __popc(GRP_BALLOT(has != 0));
-                if (nl > pool_n) { pool_n = nl; pool = s; }
-                if (nl >= GRP_TH) break;
-            }
+            const int c0 = cnt[PL_CTL], c1 = cnt[PL_BLOCK], c2 = cnt[PL_PAC], c3 = cnt[PL_EMPTY];
+            pool = PL_CTL; pool_n = c0;
+            if (c1 > pool_n) { pool = PL_BLOCK; pool_n = c1; }
+            if (c2 > pool_n) { pool = PL_PAC; pool_n = c2; }
+            if (c3 > pool_n) { pool = PL_EMPTY; pool_n = c3; }
+            // counters are read by every lane on its own: agree on lane 0's view
+            pool = GRP_SHFL(pool, 0); pool_n = GRP_SHFL(pool_n, 0);
+            if (pool_n <= 0) pool = -1;
         }
-        const bool take = pool >= 0 && (pool_n >= GRP_TH || npend == 0);
-        GRP_TRACE("pass: pool %d n %d npend %d take %d live %u\n", pool, pool_n, npend, (int)take, tok[16]);
+        const bool take = pool >= 0 && (pool_n >= A.grp_th || npend == 0);
+        GRP_TRACE("pass: pool %d n %d npend %d take %d live %u\n", pool, pool_n, npend, (int)take, tok[8]);
         if (!take) {
             if (npend == 0) {                       // nothing ready, nothing pending
-                if (tok[16] == 0) break;            // every slot is dead: done
-                GRP_SLEEP(200);
+                if (tok[8] == 0) break;             // every slot is dead: done
+                GRP_SLEEP(100);
                 continue;
             }
             // ================================ retire the oldest pending batch ================================
@@ -940,32 +968,32 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
             pend[GRP_DEPTH - 1] = GRP_NONE;
             npend--;
             if (npend == 0) GRP_CP_WAIT(0); else if (npend == 1) GRP_CP_WAIT(1); else if (npend == 2) GRP_CP_WAIT(2); else GRP_CP_WAIT(3);
-            u32 requeue = GRP_NONE; int newpool = -1;
+            u32 requeue = GRP_NONE; int newbyte = -1;
             if (sid != GRP_NONE) {
                 GRP_DS(mreq); GRP_DS(state);
                 GRP_TRACE("  retire sid %u kind %d mreq %d state %d\n", sid, kind, (int)mreq, (int)state);
                 if (kind == B_BLOCK) {
                     compare_block<WIDE, LONG>(ix, smb, sid);
-                    newpool = mreq == M_PAC ? (int)Q_PAC : (int)state;
+                    newbyte = mreq == M_PAC ? (int)Q_PAC : (int)state;
                 } else if (kind == B_PAC) {
                     compare_pac<WIDE, LONG, STATS>(ix, smb, sid, st);
-                    newpool = mreq == M_PAC ? (int)Q_PAC : (int)state;
+                    newbyte = mreq == M_PAC ? (int)Q_PAC : (int)state;
                 } else if (mreq == M_T2REC) {
                     // reseed task record (emitted by T1): read, SMEM [start,end), hit count, start hint
                     const uint4 a = *GRP_STGQ(0), b = *GRP_STGQ(1);
                     GRP_DU(rid); GRP_DU(min_intv); GRP_DS(pivot); GRP_DS(full_match); GRP_DS(use_cached); GRP_DS(cache_pivot);
                     GRP_DS(cache_pivot_end); GRP_DI(max_refpos); GRP_DI(cache_refpos);
                     rid = a.x;
-                    const u32 se = a.y, cnt = a.z, full = a.w;
+                    const u32 se = a.y, c = a.z, full = a.w;
                     const u64 lo64 = (u64)b.x | ((u64)b.y << 32);
                     const int qb = se & 0xffff, qe = se >> 16;
                     pivot = (short)((qb + qe) >> 1);
-                    min_intv = cnt + 1;
+                    min_intv = c + 1;
                     full_match = full != 0;
                     max_refpos = full ? (idx_t)lo64 : 0;
-                    use_cached = (!full && ix.mode == 3 && cnt >= 1 && cnt < 10) ? 1 : 0;
+                    use_cached = (!full && ix.mode == 3 && c >= 1 && c < 10) ? 1 : 0;
                     cache_pivot = (short)qb; cache_pivot_end = (short)qe; cache_refpos = (idx_t)lo64;
-                    if (a.x == 0xffffffffu) newpool = Q_EMPTY;       // unused task slot
+                    if (a.x == 0xffffffffu) newbyte = Q_EMPTY;       // unused task slot
                     else { mreq = M_TASK; issue_task<WIDE, LONG>(A, smb, sid, a.x); requeue = sid; }
                 } else if (mreq == M_TASK) {
                     const uint4 o = *GRP_STGQ(0);
@@ -977,10 +1005,10 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
                     for (int w = 0; w < L::RWT; w++) any |= GRP_RD(2 * L::RWT + w);
                     anyn = any != 0;
                     rl_off = 0; bl_off = 8;
-                    state = P_TASK_LOADED;
-                    newpool = P_TASK_LOADED;
+                    state = L_TASK_LOADED;
+                    newbyte = L_TASK_LOADED;
                 } else {
-                    newpool = (int)state;           // M_RMI / M_LD: the result waits in the staging cells
+                    newbyte = (int)state;           // M_RMI / M_LD: the result waits in the staging cells
                 }
                 if (STATS) { st.iter++; }
             }
@@ -992,11 +1020,9 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
                 for (int d = 0; d < GRP_DEPTH; d++) if (d == npend) { pend[d] = requeue; pkind[d] = B_SIMPLE; }
                 npend++;
             }
-            GRP_FENCE();
-            if (newpool >= 0) sst[sid >> 5] = (unsigned char)newpool;
+            publish(sid, newbyte);
             continue;
         }
-        rr = pool + 1 == NPOOL ? 0 : pool + 1;
         // ================================ claim one slot of the pool per lane ================================
         u32 got = 0;
         if (lane == 0) got = atomicCAS(const_cast<u32 *>(&tok[pool]), 0u, 1u) == 0u;
@@ -1005,9 +1031,15 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
         GRP_FENCE();
         u32 sid = GRP_NONE;
         {
-            const uint4 v = ld_state16(sst);
-            const u32 pat = (u32)pool * 0x01010101u;
-            const u32 z0 = zero_bytes(v.x ^ pat), z1 = zero_bytes(v.y ^ pat), z2 = zero_bytes(v.z ^ pat), z3 = zero_bytes(v.w ^ pat);
+            uint4 v = ld_state16(sst);
+            u32 z0, z1, z2, z3;
+            if (pool == PL_CTL) {                    // any control label: the two top bits of the byte are clear
+                z0 = zero_bytes(v.x & 0xc0c0c0c0u); z1 = zero_bytes(v.y & 0xc0c0c0c0u);
+                z2 = zero_bytes(v.z & 0xc0c0c0c0u); z3 = zero_bytes(v.w & 0xc0c0c0c0u);
+            } else {
+                const u32 pat = (u32)(0x40 + pool - 1) * 0x01010101u;
+                z0 = zero_bytes(v.x ^ pat); z1 = zero_bytes(v.y ^ pat); z2 = zero_bytes(v.z ^ pat); z3 = zero_bytes(v.w ^ pat);
+            }
             int k = -1;
             if (z0) k = (__ffs(z0) - 1) >> 3;
             else if (z1) k = 4 + ((__ffs(z1) - 1) >> 3);
@@ -1015,23 +1047,29 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
             else if (z3) k = 12 + ((__ffs(z3) - 1) >> 3);
             if (k >= 0) { sst[k] = (unsigned char)SL_BUSY; sid = (u32)k * 32 + lane; }
         }
+        {
+            const u32 m = GRP_BALLOT(sid != GRP_NONE);
+            if (lane == 0 && m) atomicSub(const_cast<int *>(&cnt[pool]), __popc(m));
+        }
         GRP_FENCE();
         GRP_SYNCWARP();
         if (lane == 0) tok[pool] = 0u;
         // ================================ run the step ================================
-        int newpool = -1;                            // pool the task moves to now (else it waits in this warp's FIFO)
+        int newbyte = -1;                            // pool the task moves to now (else it waits in this warp's FIFO)
         bool queued = false; int bkind = B_SIMPLE;
-        if (pool == Q_EMPTY) {
+        const bool have = sid != GRP_NONE;
+        const u32 sid_ = have ? sid : (u32)lane;     // lanes without a task compute addresses only
+        if (pool == PL_EMPTY) {
             // ---- start tasks: one global counter bump for the whole warp ----
-            const u32 m = GRP_BALLOT(sid != GRP_NONE);
+            const u32 m = GRP_BALLOT(have);
             u64 t0 = 0;
             if (lane == 0 && m) t0 = atomicAdd((unsigned long long *)&A.ctrl[C_WORK], (unsigned long long)__popc(m));
             t0 = GRP_SHFL(t0, 0);
-            if (sid != GRP_NONE) {
+            if (have) {
                 const u64 task = t0 + (u64)__popc(m & ((1u << lane) - 1));
                 if (task >= (u64)A.n_tasks) {
-                    newpool = SL_DEAD;
-                    atomicSub(const_cast<u32 *>(&tok[16]), 1u);
+                    newbyte = SL_DEAD;
+                    atomicSub(const_cast<u32 *>(&tok[8]), 1u);
                 } else {
                     GRP_DS(mreq);
                     if (KIND == 2) {
@@ -1048,24 +1086,25 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
                     queued = true;
                 }
             }
-        } else if (pool == Q_BLOCK) {
-            if (sid != GRP_NONE) { issue_block<WIDE, LONG>(ix, smb, sid); queued = true; }
+        } else if (pool == PL_BLOCK) {
+            if (have) { issue_block<WIDE, LONG>(ix, smb, sid); queued = true; }
             bkind = B_BLOCK;
-            if (STATS) { st.pass_mem++; st.lanes_mem += sid != GRP_NONE; }
-        } else if (pool == Q_PAC) {
-            if (sid != GRP_NONE) { issue_pac<WIDE, LONG>(ix, smb, sid); queued = true; }
+            if (STATS) { st.pass_mem++; st.lanes_mem += have; }
+        } else if (pool == PL_PAC) {
+            if (have) { issue_pac<WIDE, LONG>(ix, smb, sid); queued = true; }
             bkind = B_PAC;
-            if (STATS) { st.pass_mem++; st.lanes_mem += sid != GRP_NONE; }
+            if (STATS) { st.pass_mem++; st.lanes_mem += have; }
         } else {
-            if (sid != GRP_NONE) {
-                bool ended;
-                ctl_step<KIND, WIDE, LONG, STATS>(ix, A, smb, sid, out, st, ended);
+            bool ended;
+            ctl_pass<KIND, WIDE, LONG, STATS>(ix, A, smb, sid_, have, out, st, ended);
+            if (have) {
+                const u32 sid = sid_;
                 GRP_DS(mreq);
-                if (ended) newpool = Q_EMPTY;
-                else if (mreq == M_BLOCK) newpool = Q_BLOCK;
+                if (ended) newbyte = Q_EMPTY;
+                else if (mreq == M_BLOCK) newbyte = Q_BLOCK;
                 else { issue_simple<WIDE, LONG>(ix, smb, sid); queued = true; }
             }
-            if (STATS) { st.pass_ctl++; st.lanes_ctl += sid != GRP_NONE; }
+            if (STATS) { st.pass_ctl++; st.lanes_ctl += have; }
         }
         GRP_SYNCWARP();
         if (GRP_BALLOT(queued) != 0) {
@@ -1074,8 +1113,7 @@ __global__ void __launch_bounds__(512, 1) k_grp(IndexView ix, Args A)
             for (int d = 0; d < GRP_DEPTH; d++) if (d == npend) { pend[d] = queued ? sid : GRP_NONE; pkind[d] = bkind; }
             npend++;
         }
-        GRP_FENCE();
-        if (newpool >= 0) sst[sid >> 5] = (unsigned char)newpool;
+        publish(sid, newbyte);
     }
     finish_thread<KIND>(A, out, st);
 }

@@ -32,6 +32,7 @@ struct Args {
     u32 *rd_nsmem; u64 *rd_nhit; uint8_t *rd_full; u64 *rd_maxref;
     u64 *ctrl;
     meme_seed_opt_t opt;
+    int grp_th;                         // regrouped kernel: a pool with at least this many tasks is taken at once
 };
 
 __device__ __forceinline__ u64 revcomp32(u64 w)

@@ -55,6 +55,7 @@ const bseq1_t *g_base = nullptr;
 int g_n = 0;
 meme_seed_result_t g_res;
 bool g_have = false;
+int g_max_occ = 0;
 double g_seed_s = 0;
 long g_seed_reads = 0;
 
@@ -117,7 +118,10 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     so.split_width = opt->split_width;
     so.max_mem_intv = (int32_t)opt->max_mem_intv;
     so.rounds = 3;
-    so.max_occ = 0;                 // mem_chain_Learned computes l_rep from hitcount and indexes hits with a stride
+    // only the hits mem_chain_Learned reads are materialised (k = 0, step, 2*step, ... at most max_occ of them,
+    // src/bwamem.cpp:L1154-1155): a repeat SMEM with 1e5 occurrences costs max_occ positions, not 1e5
+    so.max_occ = opt->max_occ > 0 ? opt->max_occ : 0;
+    g_max_occ = so.max_occ;
     int rc = a.seed_batch(g_index, codes.data(), off.data(), n, &so, &g_res);
     if (rc) die("meme_seed_batch", rc);
     g_base = seqs; g_n = n; g_have = true;
@@ -139,12 +143,37 @@ bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits)
     int64_t h0 = g_res.hit_off[idx], h1 = g_res.hit_off[idx + 1];
     size_t ns = (size_t)(s1 - s0), nh = (size_t)(h1 - h0);
     if (smems->m < ns) kv_resize(mem_tl, *smems, ns + 16);
-    if (hits->m < nh) kv_resize(uint64_t, *hits, nh + 16);
     static_assert(sizeof(mem_tl) == sizeof(meme_smem_t), "mem_tl layout");
     memcpy(smems->a, g_res.smems + s0, ns * sizeof(mem_tl));
-    memcpy(hits->a, g_res.hits + h0, nh * sizeof(uint64_t));
     smems->n = ns;
-    hits->n = nh;
+    // hits arrive compact (the sampled ones only); mem_chain_Learned indexes hits[hitbeg + k*step], so SMEMs with
+    // more than max_occ occurrences get their samples scattered to the strided slots of a full-size list
+    size_t full = 0; bool sampled = false;
+    for (size_t i = 0; i < ns; i++) {
+        size_t c = (size_t)smems->a[i].hitcount;
+        full += c;
+        if (g_max_occ > 0 && c > (size_t)g_max_occ) sampled = true;
+    }
+    if (!sampled) {
+        if (hits->m < nh) kv_resize(uint64_t, *hits, nh + 16);
+        memcpy(hits->a, g_res.hits + h0, nh * sizeof(uint64_t));
+        hits->n = nh;
+        return true;
+    }
+    if (hits->m < full) kv_resize(uint64_t, *hits, full + 16);
+    const uint64_t *src = g_res.hits + h0;
+    size_t beg = 0;
+    for (size_t i = 0; i < ns; i++) {
+        mem_tl &m = smems->a[i];
+        size_t c = (size_t)m.hitcount, mo = (size_t)g_max_occ;
+        size_t step = c > mo ? c / mo : 1, take = (c + step - 1) / step;
+        if (take > mo) take = mo;
+        const uint64_t *q = src + m.hitbeg;
+        for (size_t j = 0; j < take; j++) hits->a[beg + j * step] = q[j];
+        m.hitbeg = (int)beg;
+        beg += c;
+    }
+    hits->n = full;
     return true;
 }
 

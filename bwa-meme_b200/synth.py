@@ -147,10 +147,10 @@ def make_genome_large(length: int, seed: int = 20261017, n_families: int = 300, 
 
 
 def make_reads_torch(genome_t, n_reads: int, read_len: int = 150, seed: int = 7, sub_rate: float = 0.01,
-                     n_frac: float = 0.005, chunk: int = 1 << 20):
-    """Bench-scale read generator on a torch device (plumbing): uniform start, random strand, substitutions,
-    0.5 % of reads with one N.  Returns a uint8 tensor [n_reads, read_len] on
-    genome_t's device."""
+                     n_frac: float = 0.005, indel_frac: float = 0.05, chunk: int = 1 << 20):
+    """Bench-scale read generator on a torch device (plumbing): uniform start, random strand, 1 % substitutions,
+    5 % of reads with one 1-3 bp insertion or deletion, 0.5 % of reads with one N.
+    Returns a uint8 tensor [n_reads, read_len] on genome_t's device."""
     import torch
     dev = genome_t.device
     gen = torch.Generator(device=dev)
@@ -161,8 +161,21 @@ def make_reads_torch(genome_t, n_reads: int, read_len: int = 150, seed: int = 7,
     for a in range(0, n_reads, chunk):
         b = min(n_reads, a + chunk)
         m = b - a
-        starts = torch.randint(0, L - read_len, (m,), generator=gen, device=dev)
-        r = genome_t[(starts[:, None] + ar[None, :])]
+        starts = torch.randint(0, L - read_len - 4, (m,), generator=gen, device=dev)
+        # one indel per selected read: a deletion skips k source bases at p, an insertion puts k random bases there
+        has_indel = torch.rand((m,), generator=gen, device=dev) < indel_frac
+        is_del = torch.rand((m,), generator=gen, device=dev) < 0.5
+        ipos = torch.randint(10, max(11, read_len - 10), (m,), generator=gen, device=dev)
+        ilen = torch.randint(1, 4, (m,), generator=gen, device=dev)
+        dele = (has_indel & is_del)[:, None]
+        ins = (has_indel & ~is_del)[:, None]
+        after = ar[None, :] >= ipos[:, None]
+        inside = ins & after & (ar[None, :] < (ipos + ilen)[:, None])
+        shift = torch.where(dele & after, ilen[:, None], torch.zeros_like(after, dtype=torch.int64))
+        shift = shift - torch.where(ins & (ar[None, :] >= (ipos + ilen)[:, None]), ilen[:, None], torch.zeros_like(shift))
+        r = genome_t[(starts[:, None] + ar[None, :] + shift)]
+        rnd = torch.randint(0, 4, (m, read_len), generator=gen, device=dev, dtype=torch.uint8)
+        r = torch.where(inside, rnd, r)
         mut = torch.rand((m, read_len), generator=gen, device=dev) < sub_rate
         delta = torch.randint(1, 4, (m, read_len), generator=gen, device=dev, dtype=torch.uint8)
         r = torch.where(mut, (r + delta) & 3, r)

@@ -46,6 +46,8 @@ static inline int __any_sync(unsigned, int p) { return p; }
 
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned atomicSub(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline int atomicSub(int *p, int v) { int o = *p; *p = o - v; return o; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 // the device-only constructs of meme_seed_grp.cuh: a CTA of one warp of one lane
@@ -64,6 +66,7 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 #define GRP_WARP() 0
 #define GRP_BALLOT(p) ((p) ? 1u : 0u)
 #define GRP_SHFL(v, l) (v)
+#define GRP_REDUCE_MIN(v) ((int)(v))
 #define GRP_SYNCWARP() ((void)0)
 #define GRP_SYNCTHREADS() ((void)0)
 

@@ -117,7 +117,7 @@ extern "C" int flat_sim_seed(const uint8_t *text, uint64_t sa_num, const uint8_t
     A.t2_in = nullptr; A.t2_out = t2.data(); A.t2_cap = t2_cap;
     A.pool_keys = pool_keys.data(); A.pool_vals = pool_vals.data(); A.pool_cap = pool_cap;
     A.rd_nsmem = rd_nsmem.data(); A.rd_nhit = rd_nhit.data(); A.rd_full = rd_full.data(); A.rd_maxref = rd_maxref.data();
-    A.ctrl = ctrl; A.opt = *opt;
+    A.ctrl = ctrl; A.opt = *opt; A.grp_th = 24;
     const bool lng = max_len > 32 * (TPR_RW / 2);
     if (nr > 0) { if (wide) run_kinds<true>(ix, A, *opt, nr, t2, ctrl, lng); else run_kinds<false>(ix, A, *opt, nr, t2, ctrl, lng); }
     if (ctrl[C_POOL_OVF] || ctrl[C_T2_OVF]) return MEME_E_OVERFLOW;

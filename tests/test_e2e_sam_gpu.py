@@ -60,3 +60,42 @@ def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1"})
     assert "on the GPU" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+
+
+def _ref_binary():
+    flags = open("/proc/cpuinfo").read()
+    for isa in (["avx512bw"] if " avx512bw" in flags else []) + ["avx2"]:
+        p = os.path.join(ROOT, "oracle", "_ref", f"bwa-meme_mode3.{isa}")
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def test_high_copy_repeats_sampled_hits_sam_identical(pkg, tmp_path):
+    """SMEMs with more than max_occ (500) occurrences: the glue asks the kernel for the sampled hits only
+    (src/bwamem.cpp:L1154-1155) and scatters them to the strided slots mem_chain_Learned reads.  The SAM must equal the
+    unmodified reference binary's, run here on the same index and reads."""
+    from bwa_meme_b200 import synth, index_build
+    exe, ref = _binary(), _ref_binary()
+    if exe is None or ref is None:
+        pytest.skip("oracle/_ref binaries not built (needs the reference sources)")
+    rng = np.random.default_rng(41)
+    g = synth.make_genome(300000, seed=41, n_families=2, copies=10, rep_len=300)
+    unit = rng.integers(0, 4, size=70, dtype=np.uint8)
+    for p in rng.choice(np.arange(1000, 299000, 90), size=900, replace=False):      # 900 exact copies of a 70-mer
+        g[p:p + 70] = unit
+    prefix = str(tmp_path / "rep.fa")
+    index_build.build_index(prefix, g, bits=14)
+    codes, offs = synth.make_reads(g, 400, 150, seed=8)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, codes, offs)
+    want, _ = _run(ref, [prefix, fq], {})
+    got, err = _run(exe, [prefix, fq], {"MEME_B200": "1"})
+    assert "seeded 400 reads on the GPU" in err
+    assert got == want
+    # the case is really exercised: some SMEM has more than 500 hits
+    from bwa_meme_b200 import capi
+    ix = capi.MemeIndex(prefix, mode=3)
+    r = ix.seed(codes, offs)
+    ix.close()
+    assert int(r["smems"]["hitcount"].max()) > 500

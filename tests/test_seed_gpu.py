@@ -219,3 +219,45 @@ def test_wide_index_kernels_on_golden_fixtures(oracle, pkg, golden_index, golden
     want = oix.seed(codes, offs)
     oix.close()
     assert _canon(oracle, got, n) == _canon(oracle, want, n)
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_regrouped_kernel_matches_reference_dump(oracle, pkg, golden_index, mid_index, wide):
+    """The regrouped seeding kernel (MEME_SEED_IMPL=grp, meme_seed_grp.cuh) is selectable and must give the reference's
+    results too.  The choice is latched per process, so it runs in its own interpreter."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    meta = __import__("json").load(open(os.path.join(GOLDEN, "index_sha.json")))
+    mid_prefix, _ = mid_index
+    code = f"""
+import sys, os, numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+ge.load_pkg(); O = ge.load_oracle()
+from bwa_meme_b200 import capi, synth
+g = synth.make_genome({meta["genome_len"]}, seed={meta["genome_seed"]}, n_families=3, copies=12, rep_len=400)
+for mode in (3, 1):
+    ix = capi.MemeIndex({golden_index!r}, mode=mode)
+    for rl, nr, nf, seed in {GOLDEN_READ_SETS!r}:
+        codes, offs = synth.make_reads(g, nr, rl, seed=seed, n_frac=nf)
+        n = len(offs) - 1
+        got = ix.seed(codes, offs)
+        want = O.parse_ref_dump(os.path.join({GOLDEN!r}, f"smem_len{{rl}}.txt"), n)
+        assert O.canon_lines(got["smems"], got["smem_off"], got["hit_off"], got["hits"], n) == want, (mode, rl)
+    ix.close()
+g2 = synth.make_genome(400000, seed=77, n_families=6, copies=60, rep_len=800, divergence=0.01)
+codes, offs = synth.make_reads(g2, 1500, 320, seed=9, n_frac=0.05, len_jitter=300)
+n = len(offs) - 1
+ix = capi.MemeIndex({mid_prefix!r}, mode=3); got = ix.seed(codes, offs); ix.close()
+oix = O.OracleIndex({mid_prefix!r}, 3); want = oix.seed(codes, offs); oix.close()
+c = lambda r: O.canon_lines(r["smems"], r["smem_off"], r["hit_off"], r["hits"], n)
+assert c(got) == c(want)
+print("OK")
+"""
+    e = dict(os.environ)
+    e.update({"MEME_SEED_IMPL": "grp", "MEME_FORCE_WIDE": wide})
+    if wide == "0":
+        e.pop("MEME_FORCE_WIDE")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=900)
+    assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-2000:]
