@@ -24,6 +24,7 @@ EXPORTS = [
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
     "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
+    "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -94,6 +95,13 @@ def lib():
         L.meme_bsw_run.argtypes = [vp, i32, C.POINTER(BswOpt)]
         L.meme_bsw_download.argtypes = [vp, vp]
         L.meme_bsw_cells.argtypes = [vp, C.POINTER(u64)]
+        L.meme_bsw_batch_ext.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, C.POINTER(BswOpt), vp]
+        L.meme_bsw_set_match.argtypes = [vp, i32]
+        L.meme_bsw_run_ext.argtypes = [vp, i32, i32, i32, C.POINTER(BswOpt)]
+        L.meme_bsw_download_w.argtypes = [vp, vp]
+        L.meme_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.meme_pinned_free.argtypes = [vp]
+        L.meme_pinned_free.restype = None
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -247,7 +255,18 @@ class MemeBsw:
                                     len(qer), w, C.byref(self.opt)), "meme_bsw_batch")
         return out
 
+    def get_scores_ext(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int, tries: int = 2, prev_is_h0: bool = False):
+        """The extension driver's band retries on the device (src/bwamem.cpp:L2968-3376): returns (pairs, w_used)."""
+        out = np.ascontiguousarray(pairs.copy())
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        qer = np.ascontiguousarray(qer, dtype=np.uint8)
+        wu = np.zeros(len(out), np.int32)
+        _check(lib().meme_bsw_batch_ext(self.h, out.ctypes.data, len(out), ref.ctypes.data, len(ref), qer.ctypes.data, len(qer), w,
+                                        tries, int(prev_is_h0), C.byref(self.opt), wu.ctypes.data), "meme_bsw_batch_ext")
+        return out, wu
+
     def upload(self, pairs, ref, qer):
+        _check(lib().meme_bsw_set_match(self.h, self.opt.a), "meme_bsw_set_match")
         _check(lib().meme_bsw_upload(self.h, pairs.ctypes.data, len(pairs), ref.ctypes.data, len(ref), qer.ctypes.data,
                                      len(qer)), "meme_bsw_upload")
 

@@ -1,5 +1,9 @@
 // meme_bsw.cu -- kernel B: banded affine-gap Smith-Waterman seed extension on sm_100a.
 //
+// Two kernels: the inter-sequence kernel k_bsw_is (meme_bsw_is.cuh: one thread per pair, row in shared memory) takes
+// every pair whose scores fit 13 bits and whose query is at most 320 bases -- all of them on the 150/250 bp read path;
+// the warp-per-pair int32 kernel below (k_bsw<C>) and the one-thread generic kernel remain as the overflow classes.
+//
 // Computes, for every SeqPair, exactly what BandedPairWiseSW::scalarBandedSWA returns
 // (reference src/bandedSWA.cpp:L116-237) -- the semantic definition that the reference's
 // SSE/AVX2/AVX-512 inter-sequence kernels (getScores8/16, L412-4870) vectorise.
@@ -17,10 +21,14 @@
 // (L218-221) comes from two ballots.  All per-row control (z-drop, band, gscore) is warp-uniform.
 // Slots outside the current band keep their old contents, exactly like the reference's eh[] array.
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 #include "meme_common.cuh"
+#include "meme_bsw_is.cuh"
 
 #define BSW_WARPS 4
 #define BSW_NCLASS 10
+#define BSW_IS_NCLASS 5
+#define BSW_IS_THREADS 128
 #define FULL 0xffffffffu
 #define NEG_BIG (-(1 << 28))
 
@@ -34,6 +42,12 @@ struct meme_bsw {
     int64_t *d_scratch_off; size_t cap_scratch_off;
     u32 *d_order; size_t cap_order;
     int64_t cls_off[BSW_NCLASS + 1];
+    // inter-sequence path: device-sorted order of the pairs it takes, ranges per row-size class
+    u32 *d_keys, *d_keys2, *d_idx, *d_idx2; size_t cap_sort;
+    void *d_sort_tmp; size_t cap_sort_tmp;
+    int64_t is_off[BSW_IS_NCLASS + 1]; int64_t n_is, n_ovf;
+    int32_t *d_wused; size_t cap_wused;
+    int match_a;
     u64 *d_ctrl; u64 *h_ctrl;
     int64_t n_pairs, n_ref, n_qer;
     u64 launches;
@@ -271,12 +285,19 @@ __device__ void bsw_thread(const BswConst &P, const uint8_t *__restrict__ query,
 
 #define BSW_MAX_REG_QLEN (32 * 12 - 1)
 
-// One kernel instantiation per column count C: registers (and therefore resident warps) follow the class
-// instead of the worst case.  `order` lists the pairs of this class (built at upload, counting sort by C).
+// the extension driver's acceptance test (reference src/bwamem.cpp:L2985-2987): final when the score did not move,
+// when the best cell stayed within 3/4 of the band, or on the last try
+__device__ __forceinline__ bool bsw_final(int score, int max_off, int prev, int w, int t, int tries)
+{
+    return t + 1 >= tries || score == prev || max_off < (w >> 1) + (w >> 2);
+}
+
+// Overflow class 1: one warp per pair, int32 cells, one instantiation per column count C (registers follow the class).
+// `order` lists the pairs of this class.
 template <int C>
 __global__ void __launch_bounds__(BSW_WARPS * 32)
-k_bsw(BswConst P, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order, int64_t n_work,
-      const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer, u64 *__restrict__ ctrl)
+k_bsw(BswConst P, int tries, int prev_is_h0, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order, int64_t n_work,
+      const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer, int32_t *__restrict__ w_used, u64 *__restrict__ ctrl)
 {
     const int lane = threadIdx.x & 31;
     u64 cells = 0;
@@ -286,12 +307,21 @@ k_bsw(BswConst P, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ or
         r = __shfl_sync(FULL, r, 0);
         if (r >= (u64)n_work) break;
         meme_seqpair_t *p = pairs + order[r];
-        bsw_warp<C>(P, qer + p->idq, p->len2, ref + p->idr, p->len1, p->h0, p, cells);
+        const int h0 = p->h0, prev = prev_is_h0 ? h0 : -1;
+        BswConst Q = P;
+        for (int t = 0;; t++) {
+            Q.w = P.w << t;
+            bsw_warp<C>(Q, qer + p->idq, p->len2, ref + p->idr, p->len1, h0, p, cells);
+            int fin = 0;
+            if (lane == 0) fin = bsw_final(p->score, p->max_off, prev, Q.w, t, tries);
+            if (__shfl_sync(FULL, fin, 0)) break;
+        }
+        if (lane == 0 && w_used) w_used[order[r]] = Q.w;
     }
     if (lane == 0 && cells) atomicAdd((unsigned long long *)&ctrl[1], (unsigned long long)cells);
 }
 
-// classes: C = 1,2,3,4,5,6,8,10,12 and "long" (generic kernel)
+// classes of the warp kernel: C = 1,2,3,4,5,6,8,10,12 and "long" (generic kernel)
 static inline int bsw_class_of(int qlen)
 {
     if (qlen > BSW_MAX_REG_QLEN) return 9;
@@ -303,24 +333,75 @@ static inline int bsw_class_of(int qlen)
     return 8;
 }
 
-__global__ void k_bsw_long_offsets(const meme_seqpair_t *__restrict__ pairs, int64_t n_pairs, int64_t *__restrict__ off)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n_pairs) off[i] = (i < n_pairs && pairs[i].len2 > BSW_MAX_REG_QLEN) ? 2 * ((int64_t)pairs[i].len2 + 2) : 0;
-}
-
-__global__ void k_bsw_long(BswConst P, meme_seqpair_t *__restrict__ pairs, int64_t n_pairs, const uint8_t *__restrict__ ref,
-                           const uint8_t *__restrict__ qer, const int64_t *__restrict__ off, int32_t *__restrict__ scratch,
+// Overflow class 2: queries beyond the register kernel, one thread per pair, rows in global scratch.
+__global__ void k_bsw_long(BswConst P, int tries, int prev_is_h0, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order,
+                           int64_t n_work, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer,
+                           const int64_t *__restrict__ off, int32_t *__restrict__ scratch, int32_t *__restrict__ w_used,
                            u64 *__restrict__ ctrl)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pairs) return;
-    meme_seqpair_t *p = pairs + i;
-    if (p->len2 <= BSW_MAX_REG_QLEN) return;      // (pairs of the register classes are done by k_bsw<C>)
+    if (i >= n_work) return;
+    meme_seqpair_t *p = pairs + order[i];
     u64 cells = 0;
     int32_t *H = scratch + off[i], *E = H + p->len2 + 2;
-    bsw_thread(P, qer + p->idq, p->len2, ref + p->idr, p->len1, p->h0, H, E, p, cells);
+    const int h0 = p->h0, prev = prev_is_h0 ? h0 : -1;
+    BswConst Q = P;
+    for (int t = 0;; t++) {
+        Q.w = P.w << t;
+        bsw_thread(Q, qer + p->idq, p->len2, ref + p->idr, p->len1, h0, H, E, p, cells);
+        if (bsw_final(p->score, p->max_off, prev, Q.w, t, tries)) break;
+    }
+    if (w_used) w_used[order[i]] = Q.w;
     atomicAdd((unsigned long long *)&ctrl[1], (unsigned long long)cells);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the inter-sequence kernel (meme_bsw_is.cuh): one thread per pair, rows [column][thread] in shared memory
+// ---------------------------------------------------------------------------------------------
+// row words per thread of the five classes (query length + 2 <= words)
+static const int BSW_IS_WORDS[BSW_IS_NCLASS] = {34, 66, 98, 162, 322};
+static inline int bsw_is_class_of(int qlen)
+{
+    for (int c = 0; c < BSW_IS_NCLASS; c++) if (qlen + 2 <= BSW_IS_WORDS[c]) return c;
+    return -1;
+}
+
+__global__ void __launch_bounds__(BSW_IS_THREADS)
+k_bsw_is(BswIsConst P, int words, int w, int tries, int prev_is_h0, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order,
+         int64_t n_work, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer, int32_t *__restrict__ w_used,
+         u64 *__restrict__ ctrl)
+{
+    extern __shared__ u32 bsw_rows[];
+    u32 *row = bsw_rows + threadIdx.x;
+    uint8_t *qrow = reinterpret_cast<uint8_t *>(bsw_rows + (size_t)words * BSW_IS_THREADS) + threadIdx.x;
+    u64 cells = 0;
+    // static striding over the length-sorted order: the 32 pairs of a warp are neighbours in the sort
+    for (int64_t k = (int64_t)blockIdx.x * BSW_IS_THREADS + threadIdx.x; k < n_work; k += (int64_t)gridDim.x * BSW_IS_THREADS) {
+        const u32 pi = order[k];
+        meme_seqpair_t *p = pairs + pi;
+        const int h0 = p->h0;
+        BswIsOut o;
+        const int wu = bsw_is_retry(P, w, tries, prev_is_h0 ? h0 : -1, qer + p->idq, p->len2, ref + p->idr, p->len1, h0, row,
+                                    qrow, BSW_IS_THREADS, o, cells);
+        p->score = o.score; p->tle = o.tle; p->gtle = o.gtle; p->qle = o.qle; p->gscore = o.gscore; p->max_off = o.max_off;
+        if (w_used) w_used[pi] = wu;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd((unsigned long long *)&ctrl[1], (unsigned long long)cells);
+}
+
+// sort keys: pairs of the inter-sequence kernel by (query length, reference length), longest first; pairs of the
+// overflow classes get the largest key and are skipped by the inter-sequence launches
+__global__ void k_bsw_keys(const meme_seqpair_t *__restrict__ pairs, int64_t n, int match_a, u32 *__restrict__ keys, u32 *__restrict__ idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const meme_seqpair_t p = pairs[i];
+    const bool ovf = p.len2 > BSW_IS_MAX_QLEN || (long long)p.h0 + (long long)p.len2 * match_a >= BSW_IS_MAX_SCORE || p.h0 < 0;
+    u32 l1 = p.len1 > 0xffff ? 0xffffu : (u32)p.len1;
+    keys[i] = ovf ? 0xffffffffu : (((u32)p.len2 << 16) | l1);
+    idx[i] = (u32)i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -342,6 +423,7 @@ extern "C" int meme_bsw_create(int device, meme_bsw_t **out)
     b->stream = b->own_stream;
     CUDA_TRY(cudaMalloc((void **)&b->d_ctrl, 8 * 8));
     CUDA_TRY(cudaMallocHost((void **)&b->h_ctrl, 8 * 8));
+    b->match_a = 1;
     *out = b;
     return MEME_OK;
 }
@@ -351,7 +433,8 @@ extern "C" void meme_bsw_free(meme_bsw_t *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
-    void *dev[] = {b->d_pairs, b->d_ref, b->d_qer, b->d_scratch, b->d_scratch_off, b->d_ctrl, b->d_order};
+    void *dev[] = {b->d_pairs, b->d_ref, b->d_qer, b->d_scratch, b->d_scratch_off, b->d_ctrl, b->d_order, b->d_keys, b->d_keys2,
+                   b->d_idx, b->d_idx2, b->d_sort_tmp, b->d_wused};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_ctrl) cudaFreeHost(b->h_ctrl);
     cudaStreamDestroy(b->own_stream);
@@ -366,6 +449,137 @@ extern "C" int meme_bsw_set_stream(meme_bsw_t *b, void *cuda_stream)
     return MEME_OK;
 }
 
+// The match score decides which pairs fit the 13-bit cells of the inter-sequence kernel; it is part of the options of
+// a run, but the classes are built at upload: meme_bsw_set_match tells the handle before the upload (default 1).
+extern "C" int meme_bsw_set_match(meme_bsw_t *b, int32_t a)
+{
+    if (!b || a < 0) return MEME_E_ARG;
+    b->match_a = a;
+    return MEME_OK;
+}
+
+__global__ void k_bsw_rebase(meme_seqpair_t *__restrict__ pairs, int64_t n, int32_t ref_base, int32_t qer_base)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { pairs[i].idr += ref_base; pairs[i].idq += qer_base; }
+}
+
+// Upload of a batch given as `nseg` segments, each with its own pair array and sequence buffers (pair offsets are
+// relative to the segment's buffers): what a multi-threaded caller assembles without a gather copy.  The segments are
+// laid out back to back on the device and the pair offsets rebased there.
+extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_seqpair_t *const *pairs, const int64_t *n_pairs,
+                                        const uint8_t *const *ref, const int64_t *n_ref, const uint8_t *const *qer,
+                                        const int64_t *n_qer)
+{
+    if (!b || nseg < 0 || (nseg && (!pairs || !n_pairs || !ref || !n_ref || !qer || !n_qer))) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    int64_t tot_p = 0, tot_r = 0, tot_q = 0;
+    for (int s = 0; s < nseg; s++) {
+        if (n_pairs[s] < 0 || n_ref[s] < 0 || n_qer[s] < 0 || (n_pairs[s] && (!pairs[s] || !ref[s] || !qer[s]))) {
+            meme_set_error("bad segment %d", s);
+            return MEME_E_ARG;
+        }
+        tot_p += n_pairs[s]; tot_r += n_ref[s]; tot_q += n_qer[s];
+    }
+    if (tot_p >= (1ll << 31) || tot_r >= (1ll << 31) || tot_q >= (1ll << 31)) {
+        meme_set_error("batch too large for 32-bit pair offsets (%lld pairs, %lld + %lld sequence bytes)", (long long)tot_p, (long long)tot_r, (long long)tot_q);
+        return MEME_E_ARG;
+    }
+    // validation, class counts of the inter-sequence kernel, and the (few) pairs of the overflow classes
+    int64_t is_cnt[BSW_IS_NCLASS] = {0};
+    std::vector<u32> ovf;
+    std::vector<int32_t> ovf_len2;
+    {
+        int64_t base = 0;
+        for (int s = 0; s < nseg; s++) {
+            const meme_seqpair_t *ps = pairs[s];
+            for (int64_t i = 0; i < n_pairs[s]; i++) {
+                const meme_seqpair_t &p = ps[i];
+                if (p.len1 < 0 || p.len2 < 0 || p.idr < 0 || p.idq < 0 || (int64_t)p.idr + p.len1 > n_ref[s] ||
+                    (int64_t)p.idq + p.len2 > n_qer[s]) {
+                    meme_set_error("pair %lld of segment %d points outside the sequence buffers", (long long)i, s);
+                    return MEME_E_ARG;
+                }
+                const bool o = p.len2 > BSW_IS_MAX_QLEN || (long long)p.h0 + (long long)p.len2 * b->match_a >= BSW_IS_MAX_SCORE || p.h0 < 0;
+                if (o) { ovf.push_back((u32)(base + i)); ovf_len2.push_back(p.len2); }
+                else is_cnt[bsw_is_class_of(p.len2)]++;
+            }
+            base += n_pairs[s];
+        }
+    }
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = b->stream;
+    int rc;
+    const int64_t n_all = tot_p;
+    if ((rc = meme_grow_device((void **)&b->d_pairs, &b->cap_pairs, (size_t)n_all + 1, sizeof(meme_seqpair_t), st))) return rc;
+    if ((rc = meme_grow_device((void **)&b->d_ref, &b->cap_ref, (size_t)tot_r + 64, 1, st))) return rc;
+    if ((rc = meme_grow_device((void **)&b->d_qer, &b->cap_qer, (size_t)tot_q + 64, 1, st))) return rc;
+    {
+        int64_t pb = 0, rb = 0, qb = 0;
+        for (int s = 0; s < nseg; s++) {
+            if (n_pairs[s]) {
+                CUDA_TRY(cudaMemcpyAsync(b->d_pairs + pb, pairs[s], (size_t)n_pairs[s] * sizeof(meme_seqpair_t), cudaMemcpyHostToDevice, st));
+                if (n_ref[s]) CUDA_TRY(cudaMemcpyAsync(b->d_ref + rb, ref[s], (size_t)n_ref[s], cudaMemcpyHostToDevice, st));
+                if (n_qer[s]) CUDA_TRY(cudaMemcpyAsync(b->d_qer + qb, qer[s], (size_t)n_qer[s], cudaMemcpyHostToDevice, st));
+                if (rb || qb) k_bsw_rebase<<<(unsigned)((n_pairs[s] + 255) / 256), 256, 0, st>>>(b->d_pairs + pb, n_pairs[s], (int32_t)rb, (int32_t)qb);
+            }
+            pb += n_pairs[s]; rb += n_ref[s]; qb += n_qer[s];
+        }
+    }
+    b->n_pairs = n_all; b->n_ref = tot_r; b->n_qer = tot_q;
+    b->n_ovf = (int64_t)ovf.size(); b->n_is = n_all - b->n_ovf;
+    // ---- inter-sequence order: device radix sort by (query length, reference length), longest first ----
+    // sorted descending, the overflow pairs (key 0xffffffff) come first, then the classes from the widest rows down
+    b->is_off[BSW_IS_NCLASS] = b->n_ovf;
+    for (int c = BSW_IS_NCLASS - 1; c >= 0; c--) b->is_off[c] = b->is_off[c + 1] + is_cnt[c];
+    // (is_off[c+1] .. is_off[c]) is the range of class c in the sorted index array
+    if (n_all) {
+        size_t need = (size_t)n_all + 1;
+        if (need > b->cap_sort) {
+            void **bufs[] = {(void **)&b->d_keys, (void **)&b->d_keys2, (void **)&b->d_idx, (void **)&b->d_idx2};
+            size_t cap = 0;
+            for (void **q : bufs) { size_t c0 = b->cap_sort; if ((rc = meme_grow_device(q, &c0, need, 4, st))) return rc; cap = c0; }
+            b->cap_sort = cap;
+        }
+        k_bsw_keys<<<(unsigned)((n_all + 255) / 256), 256, 0, st>>>(b->d_pairs, n_all, b->match_a, b->d_keys, b->d_idx);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, b->d_keys, b->d_keys2, b->d_idx, b->d_idx2, (int)n_all, 0, 32, st);
+        if ((rc = meme_grow_device(&b->d_sort_tmp, &b->cap_sort_tmp, tmp + 256, 1, st))) return rc;
+        size_t t2 = b->cap_sort_tmp;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(b->d_sort_tmp, t2, b->d_keys, b->d_keys2, b->d_idx, b->d_idx2, (int)n_all,
+                                                          0, 32, st));
+        b->launches += 2;
+    }
+    // ---- overflow classes: counting sort of their indices by the warp kernel's column class ----
+    {
+        int64_t cnt[BSW_NCLASS] = {0};
+        for (int32_t l2 : ovf_len2) cnt[bsw_class_of(l2)]++;
+        b->cls_off[0] = 0;
+        for (int c = 0; c < BSW_NCLASS; c++) b->cls_off[c + 1] = b->cls_off[c] + cnt[c];
+        std::vector<u32> order(ovf.size() + 1);
+        std::vector<int32_t> olen(ovf.size() + 1);
+        int64_t cur[BSW_NCLASS];
+        for (int c = 0; c < BSW_NCLASS; c++) cur[c] = b->cls_off[c];
+        for (size_t k = 0; k < ovf.size(); k++) { int64_t d = cur[bsw_class_of(ovf_len2[k])]++; order[(size_t)d] = ovf[k]; olen[(size_t)d] = ovf_len2[k]; }
+        if ((rc = meme_grow_device((void **)&b->d_order, &b->cap_order, ovf.size() + 1, 4, st))) return rc;
+        // rows of the generic kernel (queries beyond the register kernel): 2 * (len2 + 2) int32 per pair
+        const int64_t l0 = b->cls_off[BSW_NCLASS - 1], n_long = b->cls_off[BSW_NCLASS] - l0;
+        std::vector<int64_t> off((size_t)n_long + 1);
+        int64_t acc = 0;
+        for (int64_t i = 0; i < n_long; i++) { off[(size_t)i] = acc; acc += 2 * ((int64_t)olen[(size_t)(l0 + i)] + 2); }
+        off[(size_t)n_long] = acc;
+        if (n_long) {
+            if ((rc = meme_grow_device((void **)&b->d_scratch_off, &b->cap_scratch_off, (size_t)n_long + 1, 8, st))) return rc;
+            if ((rc = meme_grow_device((void **)&b->d_scratch, &b->cap_scratch, (size_t)acc + 16, 4, st))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(b->d_scratch_off, off.data(), (size_t)(n_long + 1) * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (!ovf.empty()) {
+            CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), ovf.size() * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));       // `order` and `off` are temporaries
+        }
+    }
+    return MEME_OK;
+}
+
 extern "C" int meme_bsw_upload(meme_bsw_t *b, const meme_seqpair_t *pairs, int64_t n_pairs, const uint8_t *ref,
                                int64_t n_ref, const uint8_t *qer, int64_t n_qer)
 {
@@ -373,59 +587,71 @@ extern "C" int meme_bsw_upload(meme_bsw_t *b, const meme_seqpair_t *pairs, int64
         meme_set_error("bad argument");
         return MEME_E_ARG;
     }
-    for (int64_t i = 0; i < n_pairs; i++) {
-        const meme_seqpair_t &p = pairs[i];
-        if (p.len1 < 0 || p.len2 < 0 || p.idr < 0 || p.idq < 0 || (int64_t)p.idr + p.len1 > n_ref ||
-            (int64_t)p.idq + p.len2 > n_qer) {
-            meme_set_error("pair %lld points outside the sequence buffers", (long long)i);
-            return MEME_E_ARG;
-        }
-    }
+    return meme_bsw_upload_segments(b, 1, &pairs, &n_pairs, &ref, &n_ref, &qer, &n_qer);
+}
+
+// Results of the last run, segment by segment (the six result fields; offsets are returned rebased to the device
+// layout, callers keep their own copies of idr/idq), and the final band width of every pair.
+extern "C" int meme_bsw_download_segments(meme_bsw_t *b, int32_t nseg, meme_seqpair_t *const *pairs, const int64_t *n_pairs,
+                                          int32_t *const *w_used)
+{
+    if (!b || nseg < 0 || (nseg && (!pairs || !n_pairs))) return MEME_E_ARG;
     CUDA_TRY(cudaSetDevice(b->device));
-    cudaStream_t st = b->stream;
-    int rc;
-    if ((rc = meme_grow_device((void **)&b->d_pairs, &b->cap_pairs, (size_t)n_pairs + 1, sizeof(meme_seqpair_t), st))) return rc;
-    if ((rc = meme_grow_device((void **)&b->d_ref, &b->cap_ref, (size_t)n_ref + 64, 1, st))) return rc;
-    if ((rc = meme_grow_device((void **)&b->d_qer, &b->cap_qer, (size_t)n_qer + 64, 1, st))) return rc;
-    if (n_pairs) {
-        CUDA_TRY(cudaMemcpyAsync(b->d_pairs, pairs, (size_t)n_pairs * sizeof(meme_seqpair_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(b->d_ref, ref, (size_t)n_ref, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(b->d_qer, qer, (size_t)n_qer, cudaMemcpyHostToDevice, st));
-    }
-    b->n_pairs = n_pairs; b->n_ref = n_ref; b->n_qer = n_qer;
-    // counting sort of the pair indices by register class (columns per lane); within a class longer
-    // references first, so that the dynamic scheduler does not end on a long pair
-    {
-        int64_t cnt[BSW_NCLASS] = {0};
-        for (int64_t i = 0; i < n_pairs; i++) cnt[bsw_class_of(pairs[i].len2)]++;
-        b->cls_off[0] = 0;
-        for (int c = 0; c < BSW_NCLASS; c++) b->cls_off[c + 1] = b->cls_off[c] + cnt[c];
-        std::vector<u32> order((size_t)n_pairs + 1);
-        int64_t cur[BSW_NCLASS];
-        for (int c = 0; c < BSW_NCLASS; c++) cur[c] = b->cls_off[c];
-        for (int64_t i = 0; i < n_pairs; i++) order[(size_t)cur[bsw_class_of(pairs[i].len2)]++] = (u32)i;
-        if ((rc = meme_grow_device((void **)&b->d_order, &b->cap_order, (size_t)n_pairs + 1, 4, st))) return rc;
-        if (n_pairs) {
-            CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));       // `order` is a temporary
+    int64_t pb = 0;
+    for (int s = 0; s < nseg; s++) {
+        if (pb + n_pairs[s] > b->n_pairs) { meme_set_error("segments exceed the uploaded batch"); return MEME_E_ARG; }
+        if (n_pairs[s]) {
+            CUDA_TRY(cudaMemcpyAsync(pairs[s], b->d_pairs + pb, (size_t)n_pairs[s] * sizeof(meme_seqpair_t), cudaMemcpyDeviceToHost, b->stream));
+            if (w_used && w_used[s] && b->d_wused)
+                CUDA_TRY(cudaMemcpyAsync(w_used[s], b->d_wused + pb, (size_t)n_pairs[s] * 4, cudaMemcpyDeviceToHost, b->stream));
         }
+        pb += n_pairs[s];
     }
-    b->h_ctrl[4] = b->cls_off[BSW_NCLASS] > b->cls_off[BSW_NCLASS - 1];   // any pair for the long-query path?
+    CUDA_TRY(cudaMemcpyAsync(b->h_ctrl, b->d_ctrl, 2 * 8, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
     return MEME_OK;
 }
 
-extern "C" int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt)
+extern "C" int meme_bsw_run_ext(meme_bsw_t *b, int32_t w, int32_t tries, int32_t prev_is_h0, const meme_bsw_opt_t *opt)
 {
     if (!b || !opt) { meme_set_error("null argument"); return MEME_E_ARG; }
-    if (opt->e_del <= 0 || opt->e_ins <= 0 || w < 0) { meme_set_error("bad BSW options"); return MEME_E_ARG; }
+    if (opt->e_del <= 0 || opt->e_ins <= 0 || w < 0 || tries < 1 || tries > 8) { meme_set_error("bad BSW options"); return MEME_E_ARG; }
+    if (opt->a != b->match_a) { meme_set_error("match score %d differs from the one the classes were built for (%d): call meme_bsw_set_match before the upload", opt->a, b->match_a); return MEME_E_ARG; }
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = b->stream;
     int64_t n = b->n_pairs;
     CUDA_TRY(cudaMemsetAsync(b->d_ctrl, 0, 8 * 8, st));
     if (n == 0) return MEME_OK;
-    BswConst P = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->end_bonus, opt->a, opt->b, w};
+    int rc;
+    if ((rc = meme_grow_device((void **)&b->d_wused, &b->cap_wused, (size_t)n + 1, 4, st))) return rc;
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    // ---- inter-sequence classes ----
+    {
+        BswIsConst P = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->end_bonus, opt->a, opt->b};
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_bsw_is, cudaFuncAttributeMaxDynamicSharedMemorySize, BSW_IS_WORDS[BSW_IS_NCLASS - 1] * BSW_IS_THREADS * 5));
+            attr_set = true;
+        }
+        for (int c = BSW_IS_NCLASS - 1; c >= 0; c--) {
+            const int64_t lo = b->is_off[c + 1], cn = b->is_off[c] - lo;
+            if (cn <= 0) continue;
+            const size_t sm = (size_t)BSW_IS_WORDS[c] * BSW_IS_THREADS * 5;      // 4-byte H|E word + 1-byte query base per column
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bsw_is, BSW_IS_THREADS, sm));
+            if (per_sm < 1) per_sm = 1;
+            int64_t grid = (int64_t)sms * per_sm, need = (cn + BSW_IS_THREADS - 1) / BSW_IS_THREADS;
+            if (grid > need) grid = need;
+            k_bsw_is<<<(unsigned)grid, BSW_IS_THREADS, sm, st>>>(P, BSW_IS_WORDS[c], w, tries, prev_is_h0, b->d_pairs, b->d_idx2 + lo, cn, b->d_ref, b->d_qer,
+                                                              b->d_wused, b->d_ctrl);
+            CUDA_TRY(cudaGetLastError());
+            b->launches++;
+        }
+    }
+    if (b->n_ovf == 0) return MEME_OK;
+    // ---- overflow classes ----
+    BswConst P = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->end_bonus, opt->a, opt->b, w};
 #define LAUNCH_CLASS(ci, CC)                                                                                          \
     do {                                                                                                              \
         int64_t cn = b->cls_off[(ci) + 1] - b->cls_off[ci];                                                           \
@@ -436,8 +662,8 @@ extern "C" int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt)
             int64_t grid = (int64_t)sms * per_sm, need = (cn + BSW_WARPS - 1) / BSW_WARPS;                            \
             if (grid > need) grid = need;                                                                             \
             CUDA_TRY(cudaMemsetAsync(b->d_ctrl, 0, 8, st));                                                           \
-            k_bsw<CC><<<(unsigned)grid, BSW_WARPS * 32, 0, st>>>(P, b->d_pairs, b->d_order + b->cls_off[ci], cn, b->d_ref, \
-                                                                b->d_qer, b->d_ctrl);                                 \
+            k_bsw<CC><<<(unsigned)grid, BSW_WARPS * 32, 0, st>>>(P, tries, prev_is_h0, b->d_pairs, b->d_order + b->cls_off[ci], cn, \
+                                                                b->d_ref, b->d_qer, b->d_wused, b->d_ctrl);           \
             CUDA_TRY(cudaGetLastError());                                                                             \
             b->launches++;                                                                                            \
         }                                                                                                             \
@@ -445,26 +671,20 @@ extern "C" int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt)
     LAUNCH_CLASS(0, 1); LAUNCH_CLASS(1, 2); LAUNCH_CLASS(2, 3); LAUNCH_CLASS(3, 4); LAUNCH_CLASS(4, 5);
     LAUNCH_CLASS(5, 6); LAUNCH_CLASS(6, 8); LAUNCH_CLASS(7, 10); LAUNCH_CLASS(8, 12);
 #undef LAUNCH_CLASS
-    if (b->h_ctrl[4]) {
-        int rc;
-        if ((rc = meme_grow_device((void **)&b->d_scratch_off, &b->cap_scratch_off, (size_t)n + 1, 8, st))) return rc;
-        k_bsw_long_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(b->d_pairs, n, b->d_scratch_off);
-        // exclusive scan on the host side is avoided: offsets are small in number, do it with one thread block
-        // (long queries are rare on this path: reads are <= 301 bp)
-        std::vector<int64_t> off((size_t)n + 1);
-        CUDA_TRY(cudaMemcpyAsync(off.data(), b->d_scratch_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        int64_t acc = 0;
-        for (int64_t i = 0; i <= n; i++) { int64_t v = off[i]; off[i] = acc; acc += v; }
-        CUDA_TRY(cudaMemcpyAsync(b->d_scratch_off, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        if ((rc = meme_grow_device((void **)&b->d_scratch, &b->cap_scratch, (size_t)acc + 16, 4, st))) return rc;
-        k_bsw_long<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(P, b->d_pairs, n, b->d_ref, b->d_qer, b->d_scratch_off,
-                                                          b->d_scratch, b->d_ctrl);
+    const int64_t n_long = b->cls_off[BSW_NCLASS] - b->cls_off[BSW_NCLASS - 1];
+    if (n_long > 0) {
+        k_bsw_long<<<(unsigned)((n_long + 63) / 64), 64, 0, st>>>(P, tries, prev_is_h0, b->d_pairs, b->d_order + b->cls_off[BSW_NCLASS - 1],
+                                                               n_long, b->d_ref, b->d_qer, b->d_scratch_off, b->d_scratch, b->d_wused,
+                                                               b->d_ctrl);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(st));
-        b->launches += 2;
+        b->launches++;
     }
     return MEME_OK;
+}
+
+extern "C" int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt)
+{
+    return meme_bsw_run_ext(b, w, 1, 0, opt);
 }
 
 extern "C" int meme_bsw_download(meme_bsw_t *b, meme_seqpair_t *pairs)
@@ -474,6 +694,15 @@ extern "C" int meme_bsw_download(meme_bsw_t *b, meme_seqpair_t *pairs)
     if (b->n_pairs)
         CUDA_TRY(cudaMemcpyAsync(pairs, b->d_pairs, (size_t)b->n_pairs * sizeof(meme_seqpair_t), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaMemcpyAsync(b->h_ctrl, b->d_ctrl, 2 * 8, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return MEME_OK;
+}
+
+extern "C" int meme_bsw_download_w(meme_bsw_t *b, int32_t *w_used)
+{
+    if (!b || (b->n_pairs && (!w_used || !b->d_wused))) return MEME_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (b->n_pairs) CUDA_TRY(cudaMemcpyAsync(w_used, b->d_wused, (size_t)b->n_pairs * 4, cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return MEME_OK;
 }
@@ -491,7 +720,34 @@ extern "C" int meme_bsw_batch(meme_bsw_t *b, meme_seqpair_t *pairs, int64_t n_pa
                               const uint8_t *qer, int64_t n_qer, int32_t w, const meme_bsw_opt_t *opt)
 {
     int rc;
+    if (b && opt && (rc = meme_bsw_set_match(b, opt->a))) return rc;
     if ((rc = meme_bsw_upload(b, pairs, n_pairs, ref, n_ref, qer, n_qer))) return rc;
     if ((rc = meme_bsw_run(b, w, opt))) return rc;
     return meme_bsw_download(b, pairs);
+}
+
+extern "C" int meme_bsw_batch_ext(meme_bsw_t *b, meme_seqpair_t *pairs, int64_t n_pairs, const uint8_t *ref, int64_t n_ref,
+                                  const uint8_t *qer, int64_t n_qer, int32_t w, int32_t tries, int32_t prev_is_h0,
+                                  const meme_bsw_opt_t *opt, int32_t *w_used)
+{
+    int rc;
+    if (b && opt && (rc = meme_bsw_set_match(b, opt->a))) return rc;
+    if ((rc = meme_bsw_upload(b, pairs, n_pairs, ref, n_ref, qer, n_qer))) return rc;
+    if ((rc = meme_bsw_run_ext(b, w, tries, prev_is_h0, opt))) return rc;
+    if ((rc = meme_bsw_download(b, pairs))) return rc;
+    return w_used ? meme_bsw_download_w(b, w_used) : MEME_OK;
+}
+
+// pinned host memory for callers that assemble large batches (the chunk-level extension driver of the glue)
+extern "C" int meme_pinned_alloc(size_t bytes, void **out)
+{
+    if (!out) return MEME_E_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { meme_set_error("cudaMallocHost(%zu bytes): %s", bytes, cudaGetErrorString(e)); return MEME_E_NOMEM; }
+    return MEME_OK;
+}
+
+extern "C" void meme_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }

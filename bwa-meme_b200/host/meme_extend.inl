@@ -1,0 +1,330 @@
+// meme_extend.inl -- chunk-level seed extension: the host side of kernel B for a whole chunk of reads.
+//
+// Included at the end of the (patched) reference src/bwamem.cpp, so that it can call that file's own helpers
+// (cal_max_gap, mem_sort_dedup_patch[_mate_sort], the mem_* types).  It stands where the reference runs
+//     kt_for(worker_aln) -> mem_kernel2_core -> mem_chain2aln_across_reads_V2        src/bwamem.cpp:L1945, L1633-1723, L2573-3490
+// once per 512-read block and host thread, and does the same work for the WHOLE chunk in three steps:
+//   1. every host thread walks its share of the reads and writes the left / right extension pairs of all their seeds
+//      into its own pinned arena (alignment-region bookkeeping as in L2612-2934: reference window per chain, seeds in
+//      score order, reversed copies for the left side);
+//   2. ONE device call per side (meme_glue_bsw_segments -> meme_bsw_upload_segments / meme_bsw_run_ext): the band
+//      retries (MAX_BAND_TRY, w then 2w, L2968-3376) are decided by the kernel, the right side starts from the scores
+//      the left side produced (h0 = region score, L3168-3173);
+//   3. results are folded into the regions (clip decision with pen_clip5/3, seed coverage), contained seeds are purged
+//      (L3391-3485), and the tail of mem_kernel2_core runs per read (chains freed, empty regions dropped,
+//      mem_sort_dedup_patch, ALT marking, L1666-1719).
+// The 8-bit / 16-bit / scalar classing of the reference (L2804-2812) is a CPU SIMD artefact and does not exist here.
+// Off unless MEME_B200_BSW=1; SAM output is identical either way (tests/test_e2e_sam_gpu.py).
+#include <algorithm>
+#include <vector>
+#include <omp.h>
+
+namespace meme_ext {
+
+// pairs and sequences of one side, written by one host thread; pinned, kept across chunks
+struct Arena {
+    SeqPair *pairs = nullptr; int64_t n = 0, cap = 0;
+    uint8_t *ref = nullptr; int64_t n_ref = 0, cap_ref = 0;
+    uint8_t *qer = nullptr; int64_t n_qer = 0, cap_qer = 0;
+    int32_t *w_used = nullptr; int64_t cap_w = 0;
+
+    template <class T> static void grow(T *&p, int64_t &cap, int64_t keep, int64_t need)
+    {
+        if (need <= cap) return;
+        int64_t ncap = std::max<int64_t>(need + need / 2, 1 << 16);
+        T *q = (T *)meme_glue_pinned_alloc((size_t)ncap * sizeof(T));
+        if (p) { if (keep) memcpy(q, p, (size_t)keep * sizeof(T)); meme_glue_pinned_free(p); }
+        p = q; cap = ncap;
+    }
+    void reset() { n = n_ref = n_qer = 0; }
+    SeqPair *new_pair() { grow(pairs, cap, n, n + 1); return &pairs[n++]; }
+    uint8_t *take_ref(int64_t len) { grow(ref, cap_ref, n_ref, n_ref + len + 1); uint8_t *p = ref + n_ref; n_ref += len; return p; }
+    uint8_t *take_qer(int64_t len) { grow(qer, cap_qer, n_qer, n_qer + len + 1); uint8_t *p = qer + n_qer; n_qer += len; return p; }
+};
+
+struct ThreadState {
+    Arena left, right;
+    std::vector<uint32_t> srt;          // seeds of every chain in ascending score order, read after read
+    std::vector<uint64_t> key;
+};
+
+static std::vector<ThreadState> g_ts;
+static std::vector<int64_t> g_srt_off;  // per read: offset of its first chain in its thread's srt
+
+static inline void seed_coverage(mem_alnreg_t *a)
+{   // seeds of the chain fully inside the region (L3003-3013)
+    if (a->rb != H0_ && a->qb != H0_ && a->qe != H0_ && a->re != H0_) {
+        int cov = 0;
+        for (int i = 0; i < a->c->n; ++i) {
+            const mem_seed_t *t = &a->c->seeds[i];
+            if (t->qbeg >= a->qb && t->qbeg + t->len <= a->qe && t->rbeg >= a->rb && t->rbeg + t->len <= a->re) cov += t->len;
+        }
+        a->seedcov = cov;
+    }
+}
+
+// step 1 for one read: regions and extension pairs of all seeds of all chains
+static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *ref_string, const bseq1_t *seq,
+                         int l, mem_chain_v *chn, mem_alnreg_v *av, ThreadState &T)
+{
+    const int64_t l_pac = bns->l_pac;
+    const uint8_t *query = (const uint8_t *)seq->seq;
+    const int l_query = seq->l_seq;
+    kv_init(*av);
+    size_t total = 0;
+    for (size_t j = 0; j < chn->n; j++) total += chn->a[j].n;
+    av->m = total;
+    av->a = (mem_alnreg_t *)calloc(av->m, sizeof(mem_alnreg_t));
+    for (size_t j = 0; j < chn->n; j++) {
+        mem_chain_t *c = &chn->a[j];
+        if (c->n == 0) continue;
+        // the window of the reference any extension of this chain can reach (L2649-2668)
+        int64_t rmax0 = l_pac << 1, rmax1 = 0;
+        for (int i = 0; i < c->n; ++i) {
+            const mem_seed_t *t = &c->seeds[i];
+            int64_t b = t->rbeg - (t->qbeg + cal_max_gap(opt, t->qbeg));
+            int64_t e = t->rbeg + t->len + ((l_query - t->qbeg - t->len) + cal_max_gap(opt, l_query - t->qbeg - t->len));
+            if (b < rmax0) rmax0 = b;
+            if (e > rmax1) rmax1 = e;
+        }
+        if (rmax0 < 0) rmax0 = 0;
+        if (rmax1 > l_pac << 1) rmax1 = l_pac << 1;
+        if (rmax0 < l_pac && l_pac < rmax1) {          // never across the forward / reverse boundary
+            if (c->seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac;
+        }
+        int rid = 0;
+        const uint8_t *rseq = bns_fetch_seq_v2(bns, pac, &rmax0, c->seeds[0].rbeg, &rmax1, &rid, ref_string, nullptr);
+        assert(c->rid == rid);
+        // seeds by score, best first (keys are unique: any sort gives the reference's order, L2693-2696)
+        T.key.resize((size_t)c->n);
+        for (int i = 0; i < c->n; ++i) T.key[(size_t)i] = (uint64_t)c->seeds[i].score << 32 | (uint32_t)i;
+        std::sort(T.key.begin(), T.key.end());
+        for (int i = 0; i < c->n; ++i) T.srt.push_back((uint32_t)T.key[(size_t)i]);
+        for (int k = c->n - 1; k >= 0; k--) {
+            mem_seed_t *s = &c->seeds[(uint32_t)T.key[(size_t)k]];
+            mem_alnreg_t *a = &av->a[av->n++];
+            memset(a, 0, sizeof(mem_alnreg_t));
+            s->aln = (int)av->n - 1;
+            a->w = opt->w;
+            a->score = a->truesc = -1;
+            a->rid = c->rid;
+            a->frac_rep = c->frac_rep;
+            a->seedlen0 = s->len;
+            a->c = c;
+            a->rb = a->qb = a->re = a->qe = H0_;
+            if (s->qbeg) {                              // left extension: reversed query prefix against reversed reference
+                SeqPair *sp = T.left.new_pair();
+                memset(sp, 0, sizeof(SeqPair));
+                const int64_t tl = s->rbeg - rmax0;
+                sp->h0 = s->len * opt->a;
+                sp->seqid = l; sp->regid = (int)av->n - 1;
+                sp->len2 = s->qbeg; sp->len1 = (int32_t)tl;
+                sp->idq = (int32_t)T.left.n_qer; sp->idr = (int32_t)T.left.n_ref;
+                uint8_t *qs = T.left.take_qer(s->qbeg);
+                for (int i = 0; i < s->qbeg; ++i) qs[i] = query[s->qbeg - 1 - i];
+                uint8_t *rs = T.left.take_ref(tl);
+                for (int64_t i = 0; i < tl; ++i) rs[i] = rseq[tl - 1 - i];
+                a->qb = s->qbeg; a->rb = s->rbeg;
+            } else {
+                a->score = a->truesc = s->len * opt->a; a->qb = 0; a->rb = s->rbeg;
+            }
+            if (s->qbeg + s->len != l_query) {          // right extension
+                const int64_t qe = s->qbeg + s->len, re = s->rbeg + s->len - rmax0;
+                assert(re >= 0);
+                SeqPair *sp = T.right.new_pair();
+                memset(sp, 0, sizeof(SeqPair));
+                sp->h0 = H0_;                           // known after the left side
+                sp->seqid = l; sp->regid = (int)av->n - 1;
+                sp->len2 = (int32_t)(l_query - qe); sp->len1 = (int32_t)(rmax1 - rmax0 - re);
+                sp->idq = (int32_t)T.right.n_qer; sp->idr = (int32_t)T.right.n_ref;
+                memcpy(T.right.take_qer(sp->len2), query + qe, (size_t)sp->len2);
+                memcpy(T.right.take_ref(sp->len1), rseq + re, (size_t)sp->len1);
+                a->qe = (int)qe; a->re = rmax0 + re;
+            } else {
+                a->qe = l_query; a->re = s->rbeg + s->len;
+                if (a->rb != H0_ && a->qb != H0_) {     // (L2920-2930)
+                    int cov = 0;
+                    for (int i = 0; i < c->n; ++i) {
+                        const mem_seed_t *t = &c->seeds[i];
+                        if (t->qbeg >= a->qb && t->qbeg + t->len <= a->qe && t->rbeg >= a->rb && t->rbeg + t->len <= a->re) cov += t->len;
+                    }
+                    a->seedcov = cov;
+                }
+            }
+        }
+    }
+}
+
+// step 3a for one read: seeds (almost) contained in an alignment already made do not keep theirs (L3391-3485)
+static void purge_contained(const mem_opt_t *opt, const bseq1_t *seq, mem_chain_v *chn, mem_alnreg_v *av, uint32_t *srtg)
+{
+    const int l_query = seq->l_seq;
+    int lim = 0, s_start = 0;
+    for (size_t j = 0; j < chn->n; j++) {
+        mem_chain_t *c = &chn->a[j];
+        uint32_t *srt2 = srtg + s_start;
+        s_start += c->n;
+        for (int k = c->n - 1; k >= 0; k--) {
+            mem_seed_t *s = &c->seeds[srt2[k]];
+            size_t i = 0;
+            int v = 0;
+            for (i = 0; i < av->n && v < lim; ++i) {    // has an extension covering this seed been made before?
+                mem_alnreg_t *p = &av->a[i];
+                if (p->qb == -1 && p->qe == -1) continue;
+                int64_t rd;
+                int qd, w, max_gap;
+                if (s->rbeg < p->rb || s->rbeg + s->len > p->re || s->qbeg < p->qb || s->qbeg + s->len > p->qe) { v++; continue; }
+                if (s->len - p->seedlen0 > .1 * l_query) { v++; continue; }
+                qd = s->qbeg - p->qb; rd = s->rbeg - p->rb;            // the region ahead of the seed
+                max_gap = cal_max_gap(opt, qd < rd ? qd : rd);
+                w = max_gap < p->w ? max_gap : p->w;
+                if (qd - rd < w && rd - qd < w) break;
+                qd = p->qe - (s->qbeg + s->len); rd = p->re - (s->rbeg + s->len);   // and the region behind it
+                max_gap = cal_max_gap(opt, qd < rd ? qd : rd);
+                w = max_gap < p->w ? max_gap : p->w;
+                if (qd - rd < w && rd - qd < w) break;
+                v++;
+            }
+            if (v < lim) {                              // contained: keep it only if an overlapping seed says otherwise
+                for (v = k + 1; v < c->n; ++v) {
+                    if (srt2[v] == UINT_MAX) continue;
+                    const mem_seed_t *t = &c->seeds[srt2[v]];
+                    if (t->len < s->len * .95) continue;
+                    if (s->qbeg <= t->qbeg && s->qbeg + s->len - t->qbeg >= s->len >> 2 && t->qbeg - s->qbeg != t->rbeg - s->rbeg) break;
+                    if (t->qbeg <= s->qbeg && t->qbeg + t->len - s->qbeg >= s->len >> 2 && s->qbeg - t->qbeg != s->rbeg - t->rbeg) break;
+                }
+                if (v == c->n) {
+                    mem_alnreg_t *ar = &av->a[s->aln];
+                    ar->qb = ar->qe = -1;
+                    srt2[k] = UINT_MAX;
+                    continue;
+                }
+            }
+            lim++;
+        }
+    }
+}
+
+// step 3b for one read: the tail of mem_kernel2_core (L1666-1719)
+static void finish_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq1_t *seq, mem_chain_v *chn, mem_alnreg_v *av)
+{
+    for (size_t i = 0; i < chn->n; ++i)
+        if (chn->a[i].m > SEEDS_PER_CHAIN) free(chn->a[i].seeds);
+    free(chn->a);
+    mem_alnreg_t *a = av->a;
+    size_t m = 0;
+#if MATE_SORT
+    av->useMateSort = true;
+#endif
+    for (size_t i = 0; i < av->n; ++i)
+        if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+    av->n = m;
+#if MATE_SORT
+    av->n = mem_sort_dedup_patch_mate_sort(opt, bns, pac, (uint8_t *)seq->seq, av->n, av->a, &av->useMateSort);
+#else
+    av->n = mem_sort_dedup_patch(opt, bns, pac, (uint8_t *)seq->seq, av->n, av->a);
+#endif
+    for (size_t i = 0; i < av->n; ++i) {
+        mem_alnreg_t *p = &av->a[i];
+        if (p->rid >= 0 && bns->anns[p->rid].is_alt) p->is_alt = 1;
+    }
+}
+
+}  // namespace meme_ext
+
+// Replaces kt_for(worker_aln, &w, n) in mem_process_seqs for the whole chunk.  Returns false when the GPU extension is
+// off (the caller then runs the reference's own loop).
+bool meme_extend_chunk(worker_t &w, int n)
+{
+    using namespace meme_ext;
+    if (!meme_glue_bsw_enabled() || n <= 0) return false;
+    const mem_opt_t *opt = w.opt;
+    const bntseq_t *bns = w.fmi->idx->bns;
+    const uint8_t *pac = w.fmi->idx->pac;
+    const int T = std::max(1, (int)w.nthreads);
+    if ((int)g_ts.size() < T) g_ts.resize((size_t)T);
+    g_srt_off.resize((size_t)n + 1);
+    double t0 = omp_get_wtime();
+    // ---- 1. regions + pairs: contiguous shares of the reads, one arena pair per host thread ----
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        ThreadState &S = g_ts[(size_t)t];
+        S.left.reset(); S.right.reset(); S.srt.clear();
+        const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
+        for (int l = r0; l < r1; l++) {
+            g_srt_off[(size_t)l] = (int64_t)S.srt.size();
+            collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S);
+        }
+    }
+    double t1 = omp_get_wtime();
+    std::vector<SeqPair *> pp((size_t)T);
+    std::vector<int64_t> np((size_t)T), nr((size_t)T), nq((size_t)T);
+    std::vector<uint8_t *> pr((size_t)T), pq((size_t)T);
+    std::vector<int32_t *> pw((size_t)T);
+    int64_t tot_left = 0, tot_right = 0;
+    // ---- 2a. left side on the device, folded into the regions (L2968-3161) ----
+    for (int t = 0; t < T; t++) {
+        Arena &A = g_ts[(size_t)t].left;
+        Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
+        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer; nq[(size_t)t] = A.n_qer;
+        pw[(size_t)t] = A.w_used; tot_left += A.n;
+    }
+    meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 0, opt->o_del,
+                           opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->pen_clip5, opt->a, opt->b, pw.data());
+    double t2 = omp_get_wtime();
+#pragma omp parallel num_threads(T)
+    {
+        ThreadState &S = g_ts[(size_t)omp_get_thread_num()];
+        for (int64_t k = 0; k < S.left.n; k++) {
+            const SeqPair *sp = &S.left.pairs[k];
+            mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
+            a->score = sp->score;
+            if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip5) { a->qb -= sp->qle; a->rb -= sp->tle; a->truesc = a->score; }
+            else { a->qb = 0; a->rb -= sp->gtle; a->truesc = sp->gscore; }
+            a->w = max_(a->w, S.left.w_used[k]);
+            seed_coverage(a);
+        }
+        // the right side starts from the region's score so far (L3168-3173)
+        for (int64_t k = 0; k < S.right.n; k++) {
+            SeqPair *sp = &S.right.pairs[k];
+            sp->h0 = w.regs[sp->seqid].a[sp->regid].score;
+        }
+    }
+    // ---- 2b. right side (L3175-3376) ----
+    for (int t = 0; t < T; t++) {
+        Arena &A = g_ts[(size_t)t].right;
+        Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
+        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer; nq[(size_t)t] = A.n_qer;
+        pw[(size_t)t] = A.w_used; tot_right += A.n;
+    }
+    double t3 = omp_get_wtime();
+    meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 1, opt->o_del,
+                           opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->pen_clip3, opt->a, opt->b, pw.data());
+    double t4 = omp_get_wtime();
+    // ---- 3. fold the right side, purge contained seeds, finish every read ----
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        ThreadState &S = g_ts[(size_t)t];
+        for (int64_t k = 0; k < S.right.n; k++) {
+            const SeqPair *sp = &S.right.pairs[k];
+            mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
+            a->score = sp->score;
+            if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip3) { a->qe += sp->qle; a->re += sp->tle; a->truesc += a->score - sp->h0; }
+            else { a->qe = w.seqs[sp->seqid].l_seq; a->re += sp->gtle; a->truesc += sp->gscore - sp->h0; }
+            a->w = max_(a->w, S.right.w_used[k]);
+            seed_coverage(a);
+        }
+        const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
+        for (int l = r0; l < r1; l++) {
+            purge_contained(opt, &w.seqs[l], &w.chain_ar[l], &w.regs[l], S.srt.data() + g_srt_off[(size_t)l]);
+            finish_read(opt, bns, pac, &w.seqs[l], &w.chain_ar[l], &w.regs[l]);
+        }
+    }
+    double t5 = omp_get_wtime();
+    fprintf(stderr, "[meme_b200] extended %d reads on the GPU: %ld left + %ld right pairs; pairs %.1f ms, left %.1f ms, fold %.1f ms, "
+            "right %.1f ms, finish %.1f ms\n", n, (long)tot_left, (long)tot_right, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
+            (t4 - t3) * 1e3, (t5 - t4) * 1e3);
+    return true;
+}

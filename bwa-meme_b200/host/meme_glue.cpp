@@ -20,6 +20,12 @@ struct Api {
     decltype(&meme_bsw_create) bsw_create = nullptr;
     decltype(&meme_bsw_batch) bsw_batch = nullptr;
     decltype(&meme_last_error) last_error = nullptr;
+    decltype(&meme_bsw_upload_segments) bsw_upload_segments = nullptr;
+    decltype(&meme_bsw_download_segments) bsw_download_segments = nullptr;
+    decltype(&meme_bsw_run_ext) bsw_run_ext = nullptr;
+    decltype(&meme_bsw_set_match) bsw_set_match = nullptr;
+    decltype(&meme_pinned_alloc) pinned_alloc = nullptr;
+    decltype(&meme_pinned_free) pinned_free = nullptr;
     bool ok = false;
 };
 
@@ -36,7 +42,14 @@ Api &api()
         a.bsw_create = (decltype(a.bsw_create))dlsym(a.so, "meme_bsw_create");
         a.bsw_batch = (decltype(a.bsw_batch))dlsym(a.so, "meme_bsw_batch");
         a.last_error = (decltype(a.last_error))dlsym(a.so, "meme_last_error");
-        a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error;
+        a.bsw_upload_segments = (decltype(a.bsw_upload_segments))dlsym(a.so, "meme_bsw_upload_segments");
+        a.bsw_download_segments = (decltype(a.bsw_download_segments))dlsym(a.so, "meme_bsw_download_segments");
+        a.bsw_run_ext = (decltype(a.bsw_run_ext))dlsym(a.so, "meme_bsw_run_ext");
+        a.bsw_set_match = (decltype(a.bsw_set_match))dlsym(a.so, "meme_bsw_set_match");
+        a.pinned_alloc = (decltype(a.pinned_alloc))dlsym(a.so, "meme_pinned_alloc");
+        a.pinned_free = (decltype(a.pinned_free))dlsym(a.so, "meme_pinned_free");
+        a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+               a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.pinned_alloc && a.pinned_free;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
     });
     return a;
@@ -213,4 +226,72 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
         pairs[i].qle = tmp[i].qle; pairs[i].gscore = tmp[i].gscore; pairs[i].max_off = tmp[i].max_off;
     }
     return true;
+}
+
+// ---- chunk-level seed extension (meme_extend.inl, included by the patched bwamem.cpp) ----
+bool meme_glue_bsw_enabled() { return env_on("MEME_B200_BSW"); }
+
+void *meme_glue_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    int rc = api().pinned_alloc(bytes, &p);
+    if (rc) die("meme_pinned_alloc", rc);
+    return p;
+}
+
+void meme_glue_pinned_free(void *p) { api().pinned_free(p); }
+
+// One side of the extension of a whole chunk: segments written by the host threads -> one device batch with the band
+// retries decided by the kernel -> results back into the same pair arrays (and the band width that was final).
+void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
+                            int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
+                            int a, int b, int32_t **w_used)
+{
+    Api &A = api();
+    static meme_bsw_t *h = nullptr;
+    if (!h) {
+        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+        int rc = A.bsw_create(dev, &h);
+        if (rc) die("meme_bsw_create", rc);
+    }
+    static_assert(sizeof(SeqPair) == sizeof(meme_seqpair_t), "SeqPair layout");
+    meme_bsw_opt_t o = {o_del, e_del, o_ins, e_ins, zdrop, end_bonus, a, b};
+    // MEME_B200_DUMP_PAIRS=<path>: the extension pairs of the first chunk (left side, then right side with its real h0)
+    // are written out once, for the kernel-B bench and its CPU baseline (bench.py, profiles/bench_bsw.py)
+    static int dumped = 0;
+    if (const char *dp = getenv("MEME_B200_DUMP_PAIRS")) {
+        if (dumped < 2) {
+            std::string path = std::string(dp) + (prev_is_h0 ? ".right" : ".left");
+            FILE *f = fopen(path.c_str(), "wb");
+            if (f) {
+                int64_t tp = 0, tr = 0, tq = 0;
+                for (int s = 0; s < nseg; s++) { tp += n_pairs[s]; tr += n_ref[s]; tq += n_qer[s]; }
+                int64_t hdr[3] = {tp, tr, tq};
+                int32_t par[12] = {w, tries, prev_is_h0, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, a, b, 0};
+                fwrite(hdr, 8, 3, f); fwrite(par, 4, 12, f);
+                int64_t rb = 0, qb = 0;
+                for (int s = 0; s < nseg; s++) {
+                    for (int64_t i = 0; i < n_pairs[s]; i++) {
+                        SeqPair p = pairs[s][i];
+                        p.idr += (int32_t)rb; p.idq += (int32_t)qb;
+                        fwrite(&p, sizeof p, 1, f);
+                    }
+                    rb += n_ref[s]; qb += n_qer[s];
+                }
+                for (int s = 0; s < nseg; s++) fwrite(ref[s], 1, (size_t)n_ref[s], f);
+                for (int s = 0; s < nseg; s++) fwrite(qer[s], 1, (size_t)n_qer[s], f);
+                fclose(f);
+            }
+            dumped++;
+        }
+    }
+    int rc = A.bsw_set_match(h, a);
+    if (rc) die("meme_bsw_set_match", rc);
+    rc = A.bsw_upload_segments(h, nseg, (const meme_seqpair_t *const *)pairs, n_pairs, (const uint8_t *const *)ref, n_ref,
+                               (const uint8_t *const *)qer, n_qer);
+    if (rc) die("meme_bsw_upload_segments", rc);
+    rc = A.bsw_run_ext(h, w, tries, prev_is_h0, &o);
+    if (rc) die("meme_bsw_run_ext", rc);
+    rc = A.bsw_download_segments(h, nseg, (meme_seqpair_t *const *)pairs, n_pairs, w_used);
+    if (rc) die("meme_bsw_download_segments", rc);
 }

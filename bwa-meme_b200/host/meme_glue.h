@@ -8,6 +8,9 @@
 //   meme_glue_take         in mem_kernel1_core_Learned(), around the seeding calls  src/bwamem.cpp:L1366-1397
 //   meme_glue_bsw          first line of BandedPairWiseSW::getScores8/16 and scalarBandedSWAWrapper
 //                                                             src/bandedSWA.cpp:L242, L412, L1117, L1970, L2664, L3469, L4198
+//                          (per-call seam; reached only by callers other than the chunk-level driver below)
+//   meme_extend_chunk      in mem_process_seqs(), instead of kt_for(worker_aln)     src/bwamem.cpp:L1945
+//                          (defined in meme_extend.inl, which the patched bwamem.cpp includes at its end)
 //
 // Everything is off unless the environment says MEME_B200=1 (seeding) / MEME_B200_BSW=1 (extension), so the
 // patched binary is byte-for-byte the reference's behaviour by default.
@@ -22,3 +25,11 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
 bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits);
 bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
                    int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b);
+
+// used by meme_extend.inl
+bool meme_glue_bsw_enabled();
+void *meme_glue_pinned_alloc(size_t bytes);
+void meme_glue_pinned_free(void *p);
+void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
+                            int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
+                            int a, int b, int32_t **w_used);

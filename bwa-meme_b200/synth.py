@@ -116,6 +116,22 @@ def write_fasta(path: str, genome: np.ndarray, name: str = "chrS", width: int = 
 
 def write_fastq(path: str, codes: np.ndarray, offsets: np.ndarray, prefix: str = "r") -> None:
     s = _ASCII[codes].tobytes()
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    if n > 20000 and (lens == lens[0]).all():
+        # fixed-length reads: one byte matrix per block of reads (names padded to a fixed width with a space-free scheme)
+        L = int(lens[0])
+        seq = np.frombuffer(s, dtype=np.uint8).reshape(n, L)
+        width = len(str(n - 1))
+        with open(path, "wb") as f:
+            for a in range(0, n, 1 << 18):
+                b = min(n, a + (1 << 18))
+                names = np.array([("@%s%0*d\n" % (prefix, width, i)).encode() for i in range(a, b)], dtype=f"S{2 + len(prefix) + width}")
+                nm = np.frombuffer(names.tobytes(), dtype=np.uint8).reshape(b - a, -1)
+                rec = np.concatenate([nm, seq[a:b], np.frombuffer(b"\n+\n", dtype=np.uint8)[None, :].repeat(b - a, 0),
+                                      np.full((b - a, L), ord("I"), np.uint8), np.full((b - a, 1), 10, np.uint8)], axis=1)
+                f.write(rec.tobytes())
+        return
     with open(path, "wb") as f:
         for i in range(len(offsets) - 1):
             a, b = int(offsets[i]), int(offsets[i + 1])
@@ -188,3 +204,33 @@ def make_reads_torch(genome_t, n_reads: int, read_len: int = 150, seed: int = 7,
         r = torch.where(nmask, torch.full_like(r, 4), r)
         out[a:b] = r
     return out
+
+
+def make_pairs_torch(genome_t, n_pairs: int, read_len: int = 150, seed: int = 11, sub_rate: float = 0.01,
+                     ins_mean: float = 400.0, ins_std: float = 50.0, chunk: int = 1 << 20):
+    """Paired-end reads on a torch device (plumbing): fragments of length N(400, 50^2), FR orientation, the fragment's
+    strand random, 1 % substitutions.  Returns two uint8 tensors [n_pairs, read_len]."""
+    import torch
+    dev = genome_t.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    L = genome_t.numel()
+    r1 = torch.empty((n_pairs, read_len), dtype=torch.uint8, device=dev)
+    r2 = torch.empty((n_pairs, read_len), dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, device=dev)
+    for a in range(0, n_pairs, chunk):
+        b = min(n_pairs, a + chunk)
+        m = b - a
+        ins = (torch.randn((m,), generator=gen, device=dev) * ins_std + ins_mean).round().clamp(read_len + 20, 1000).to(torch.int64)
+        starts = (torch.rand((m,), generator=gen, device=dev, dtype=torch.float64) * (L - 1001)).to(torch.int64)
+        left = genome_t[starts[:, None] + ar[None, :]]                          # fragment start, forward
+        right = genome_t[(starts + ins)[:, None] - 1 - ar[None, :]]             # fragment end, read backwards ...
+        right = 3 - right                                                       # ... and complemented
+        for r in (left, right):
+            mut = torch.rand((m, read_len), generator=gen, device=dev) < sub_rate
+            delta = torch.randint(1, 4, (m, read_len), generator=gen, device=dev, dtype=torch.uint8)
+            r[:] = torch.where(mut, (r + delta) & 3, r)
+        flip = torch.rand((m,), generator=gen, device=dev) < 0.5                # the fragment comes from the other strand
+        r1[a:b] = torch.where(flip[:, None], right, left)
+        r2[a:b] = torch.where(flip[:, None], left, right)
+    return r1, r2

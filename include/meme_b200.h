@@ -33,7 +33,7 @@ extern "C" {
 #define MEME_E_IO           -2   /* index file missing / short / inconsistent */
 #define MEME_E_ARG          -3   /* bad argument (NULL, negative count, read longer than MEME_MAX_READ_LEN) */
 #define MEME_E_NOMEM        -4   /* host or device allocation failed */
-#define MEME_E_OVERFLOW     -5   /* a read produced more than MEME_MAX_SMEMS_PER_READ seeds */
+#define MEME_E_OVERFLOW     -5   /* (reserved; the seeding kernels have no per-read SMEM limit) */
 #define MEME_E_NOGPU        -6   /* no CUDA device: this library has no CPU path */
 
 /* The reference asserts len <= ERT_MAX_READ_LEN (301) on the -7 path, src/bwamem.cpp:L1276. */
@@ -105,7 +105,7 @@ int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_
 
 /* The same in three steps, so that a caller (and bench.py) can keep inputs resident in HBM. */
 int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads);
-int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);          /* asynchronous on the stream */
+int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);          /* synchronises between the task kinds; the final gather is asynchronous */
 int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out);        /* synchronises               */
 /* Totals of the last run without copying the lists (synchronises). */
 int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits);
@@ -146,13 +146,37 @@ int meme_bsw_batch(meme_bsw_t *b, meme_seqpair_t *pairs, int64_t n_pairs,
                    const uint8_t *ref, int64_t n_ref, const uint8_t *qer, int64_t n_qer,
                    int32_t w, const meme_bsw_opt_t *opt);
 
-/* Three-step variant (inputs stay in HBM between run calls). */
+/* The same with the band retries of the extension driver decided on the device (replaces the MAX_BAND_TRY loops
+ * around getScores8/16/scalar in mem_chain2aln_across_reads_V2, src/bwamem.cpp:L2968-3376): every pair is run with
+ * w, 2w, ... (at most `tries` widths) until its result is final -- score == prev, or max_off < 3w/4, or the last try --
+ * where prev is -1 (left extensions: the region has no score yet) or the pair's h0 (right extensions, prev_is_h0 = 1:
+ * the region's score after the left extension).  w_used (may be NULL) receives the width of the final try. */
+int meme_bsw_batch_ext(meme_bsw_t *b, meme_seqpair_t *pairs, int64_t n_pairs,
+                       const uint8_t *ref, int64_t n_ref, const uint8_t *qer, int64_t n_qer,
+                       int32_t w, int32_t tries, int32_t prev_is_h0, const meme_bsw_opt_t *opt, int32_t *w_used);
+
+/* Three-step variant (inputs stay in HBM between run calls).  The match score decides which pairs fit the 13-bit
+ * cells of the main kernel, and the classes are built at upload: call meme_bsw_set_match first when it is not 1. */
+int meme_bsw_set_match(meme_bsw_t *b, int32_t a);
 int meme_bsw_upload(meme_bsw_t *b, const meme_seqpair_t *pairs, int64_t n_pairs,
                     const uint8_t *ref, int64_t n_ref, const uint8_t *qer, int64_t n_qer);
-int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt);
-int meme_bsw_download(meme_bsw_t *b, meme_seqpair_t *pairs);
-/* DP cells evaluated by the last run (band-limited), for GCUPS accounting. */
+int meme_bsw_run(meme_bsw_t *b, int32_t w, const meme_bsw_opt_t *opt);             /* asynchronous on the stream */
+int meme_bsw_run_ext(meme_bsw_t *b, int32_t w, int32_t tries, int32_t prev_is_h0, const meme_bsw_opt_t *opt);
+int meme_bsw_download(meme_bsw_t *b, meme_seqpair_t *pairs);                       /* synchronises */
+int meme_bsw_download_w(meme_bsw_t *b, int32_t *w_used);
+/* A batch assembled by several host threads: nseg segments, each with its own pair array and sequence buffers
+ * (idr/idq relative to the segment's buffers).  Replaces the per-thread seqPairArray / seqBuf* of the reference's
+ * mem_cache (src/bwamem.cpp:L2579-2590) when the whole chunk is extended in one call. */
+int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_seqpair_t *const *pairs, const int64_t *n_pairs,
+                             const uint8_t *const *ref, const int64_t *n_ref, const uint8_t *const *qer, const int64_t *n_qer);
+int meme_bsw_download_segments(meme_bsw_t *b, int32_t nseg, meme_seqpair_t *const *pairs, const int64_t *n_pairs,
+                               int32_t *const *w_used);
+/* DP cells evaluated by the last run (band-limited, retries included), for GCUPS accounting. */
 int meme_bsw_cells(meme_bsw_t *b, uint64_t *cells);
+
+/* Pinned host memory for callers that assemble large batches (the chunk-level extension driver of the glue). */
+int  meme_pinned_alloc(size_t bytes, void **out);
+void meme_pinned_free(void *p);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char *meme_last_error(void);     /* thread-local text of the last failure */

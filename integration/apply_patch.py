@@ -15,7 +15,7 @@ HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_d
 
 
 def patch_bwamem(src: str) -> str:
-    out, n_seed, n_close, n_chunk, n_inc = [], 0, 0, 0, 0
+    out, n_seed, n_close, n_chunk, n_inc, n_aln = [], 0, 0, 0, 0, 0
     for line in src.splitlines(keepends=True):
         if line.startswith('#include "bwamem.h"') and not n_inc:
             out.append(line)
@@ -37,9 +37,16 @@ def patch_bwamem(src: str) -> str:
             out.append(line)
             n_chunk += 1
             continue
+        if re.match(r"\s*kt_for\(worker_aln, &w, n_\);", line):
+            out.append("    if (!meme_extend_chunk(w, n_))   // meme_b200: whole-chunk GPU seed extension\n")
+            out.append(line)
+            n_aln += 1
+            continue
+        if line.startswith("void mem_process_seqs(") and not n_aln:
+            out.append("bool meme_extend_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
         out.append(line)
-    assert (n_inc, n_seed, n_close, n_chunk) == (1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk)
-    return "".join(out)
+    assert (n_inc, n_seed, n_close, n_chunk, n_aln) == (1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln)
+    return "".join(out) + '\n#include "meme_extend.inl"   // meme_b200: chunk-level seed extension\n'
 
 
 def patch_banded(src: str) -> str:

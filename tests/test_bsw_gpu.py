@@ -82,3 +82,34 @@ def test_cells_counter_and_determinism(oracle, bsw):
     assert bsw.cells() == cpu_cells
     b = bsw.get_scores(pairs, ref, qer, 100)
     assert (a == b).all() and (a["score"] == want["score"]).all()
+
+
+def test_band_retry_on_device(oracle, bsw):
+    """w, then 2w when the first result is not final (src/bwamem.cpp:L2968-3000), decided by the kernel: emulated here
+    with two oracle runs.  Covers the inter-sequence kernel and (long queries, huge h0) the overflow classes."""
+    for mq, mx, h0m, n in ((150, 110, 120, 20000), (700, 200, 300, 300), (100, 60, 70000, 500)):
+        pairs, ref, qer = oracle.make_pairs(n, seed=77 + mq, max_q=mq, max_extra_ref=mx, h0_max=h0m)
+        for w, prev_is_h0 in ((3, False), (3, True), (100, True)):
+            a = oracle.bsw_batch(pairs, ref, qer, w)
+            b = oracle.bsw_batch(pairs, ref, qer, 2 * w)
+            prev = pairs["h0"] if prev_is_h0 else np.full(len(pairs), -1)
+            final = (a["score"] == prev) | (a["max_off"] < (w >> 1) + (w >> 2))
+            got, wu = bsw.get_scores_ext(pairs, ref, qer, w, tries=2, prev_is_h0=prev_is_h0)
+            for f in oracle.RESULT_FIELDS:
+                bad = np.nonzero(got[f] != np.where(final, a[f], b[f]))[0]
+                assert len(bad) == 0, (mq, w, prev_is_h0, f, bad[:3], pairs[bad[0]])
+            assert (wu == np.where(final, w, 2 * w)).all()
+
+
+def test_sorted_launch_order_covers_every_pair(oracle, bsw):
+    """Pairs are processed in a device-sorted order and in per-length classes: every pair must be written exactly once,
+    whatever its position (ragged lengths, empty queries, empty references)."""
+    pairs, ref, qer = oracle.make_pairs(50000, seed=5, max_q=318, max_extra_ref=60, h0_max=100)
+    pairs = pairs.copy()
+    pairs["len2"][::97] = 0
+    pairs["len1"][::89] = 0
+    pairs["score"] = -12345
+    want = oracle.bsw_batch(pairs, ref, qer, 100)
+    got = bsw.get_scores(pairs, ref, qer, 100)
+    for f in oracle.RESULT_FIELDS:
+        assert (got[f] == want[f]).all(), f
