@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the 64-bit-index sub-record")
-    ap.add_argument("--bsw", action="store_true", help="also time the banded-SW kernel on synthetic extension pairs")
+    ap.add_argument("--no-align", action="store_true", help="skip the end-to-end `mem -7` and kernel-B records")
+    ap.add_argument("--align-genome", type=int, default=int(os.environ.get("MEME_BENCH_ALIGN_GENOME", 20_000_000)))
+    ap.add_argument("--align-reads", type=int, default=int(os.environ.get("MEME_BENCH_ALIGN_READS", 2_000_000)))
     return ap.parse_args()
 
 
@@ -423,18 +425,23 @@ def main_ours(a):
             ab = os.path.join(ROOT, "profiles", "algorithmic_bytes.json")
             if os.path.exists(ab):
                 bytes_per_read = float(json.load(open(ab))["bytes_seed_per_read"])
-        traffic = None
+        # DRAM traffic of the seeding kernels: not measurable from inside this process (it needs ncu's replay), so it is
+        # the per-read figure of the committed ncu capture of THIS command's kernels, scaled to the reads of one launch
+        # sequence; null when no capture of the current kernels is committed (profiles/traffic.json names its source)
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("seed_kernels_dram_bytes_per_read")
-                traffic = traffic * n if traffic else None
+                tj = json.load(open(tp))
+                if tj.get("seed_kernels_dram_bytes_per_read") and tj.get("kernel") == "k_flat" and tj.get("workload_reads") == n:
+                    traffic = tj["seed_kernels_dram_bytes_per_read"] * n
+                    traffic_src = tj.get("source")
             except Exception:
                 traffic = None
         if bytes_per_read:
             achieved = bytes_per_read * n / (kseed_ms / 1e3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": traffic, "kernel": "seeding kernels k_flat<1|2|3> (T1 zig-zag, T2 reseed, T3 third round) + k_pack_reads",
+                                "traffic": traffic, "traffic_source": traffic_src, "kernel": "seeding kernels k_flat<1|2|3> (T1 zig-zag, T2 reseed, T3 third round) + k_pack_reads",
                                 "algorithmic_bytes_per_read": bytes_per_read,
                                 "peak_source": peak_src,
                                 "note": "algorithmic bytes = SURVEY §8d formula with counters from oracle/seed_oracle.c on a "
@@ -443,34 +450,83 @@ def main_ours(a):
         else:
             line["roofline"] = None
         line["wide"] = wide
-        if a.bsw:
-            line["bsw"] = bench_bsw(a, local)
+        if world == 1 and not a.no_align:
+            try:
+                line["align_e2e"], line["bsw"] = bench_align_and_bsw(a, device, local)
+            except Exception as e:      # the headline (seeding) line must survive a failure of the secondary records
+                line["align_e2e"] = {"error": repr(e)[:400]}
         emit(line)
     ix.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_bsw(a, device: int) -> dict:
-    """Secondary measurement: banded-SW kernel on extension-like pairs (GCUPS; kernel B is issue-bound)."""
+def bench_align_and_bsw(a, device: int, local: int) -> tuple[dict, dict]:
+    """The second half of BASELINE.json's metric and kernel B, measured next to the seeding numbers (rank 0, N=1):
+    `align_e2e` = Mbases aligned / s of `bwa-meme mem -7` end to end -- unmodified reference on all host cores vs the
+    patched aligner with GPU seeding + GPU seed extension -- on the same FASTQ, SE and PE, SAM compared;
+    `bsw` = kernel B on the extension pairs the aligner really builds (dumped from a short run), with the reference's
+    getScores8/16 on the same pairs and all host cores beside it."""
     import torch
-    from bwa_meme_b200 import capi
-    O = ge.load_oracle()
-    pairs, ref, qer = O.make_pairs(200000, seed=5, max_q=150, max_extra_ref=110, h0_max=120)
-    reps = 8
-    big = np.tile(pairs, reps)
-    b = capi.MemeBsw(device=device)
-    b.upload(big, ref, qer)
-    for _ in range(2):
-        b.run(100)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        b.run(100)
-    cells = b.cells()
-    dt = (time.perf_counter() - t0) / 3
-    b.close()
-    return {"pairs_per_s": len(big) / dt, "gcups": cells / dt / 1e9, "pairs": len(big), "ms": dt * 1e3}
+    from bwa_meme_b200 import synth, index_build, e2e
+    cores = host_cores()
+    d = os.path.join(CACHE, f"align-g{a.align_genome}-v2")
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, "ref.fa")
+    ref_exe, b200_exe, _ = e2e.binaries(3)
+    if not (os.path.exists(ref_exe) and os.path.exists(b200_exe)):
+        return {"unavailable": "oracle/_ref aligner binaries are not in this tree"}, {"unavailable": "no pair dump without the aligner"}
+    t0 = time.time()
+    if not os.path.exists(prefix + ".pos_packed"):
+        g = synth.make_genome_large(a.align_genome, n_families=30, copies=100)
+        g.tofile(os.path.join(d, "genome.u8"))
+        index_build.build_index(prefix, g, device=device, write_keys_file=False)
+    g = np.fromfile(os.path.join(d, "genome.u8"), dtype=np.uint8)
+    gt = torch.from_numpy(g).to(device)
+    L = a.read_len
+    n_se, n_pe = a.align_reads, a.align_reads // 2
+    se = os.path.join(d, f"se{n_se}.fq")
+    if not os.path.exists(se):
+        r = synth.make_reads_torch(gt, n_se, L, seed=3).cpu().numpy()
+        synth.write_fastq(se, r.reshape(-1), np.arange(n_se + 1, dtype=np.int64) * L)
+        synth.write_fastq(os.path.join(d, "dump.fq"), r[:200000].reshape(-1), np.arange(200001, dtype=np.int64) * L)
+    pe = [os.path.join(d, f"pe{n_pe}_1.fq"), os.path.join(d, f"pe{n_pe}_2.fq")]
+    if not os.path.exists(pe[1]):
+        r1, r2 = synth.make_pairs_torch(gt, n_pe, L, seed=5)
+        offs = np.arange(n_pe + 1, dtype=np.int64) * L
+        synth.write_fastq(pe[0], r1.cpu().numpy().reshape(-1), offs, prefix="p")
+        synth.write_fastq(pe[1], r2.cpu().numpy().reshape(-1), offs, prefix="p")
+    del gt
+    torch.cuda.empty_cache()
+    log(f"align_e2e inputs ready in {time.time() - t0:.1f}s")
+    os.environ.setdefault("MEME_B200_DEVICE", str(local))
+    align = {"workload": f"{a.align_genome} bp synthetic genome, mode-3 index, {L} bp reads, -K 100000000, {cores} host threads; "
+                         "time = the aligner's own 'Processed N reads in ... real sec' (index load excluded on both sides)",
+             "unit": "Mbases/s"}
+    align["se"] = e2e.compare_arms(prefix, [se], n_se, L, cores, d, tag="se")
+    align["pe"] = e2e.compare_arms(prefix, pe, 2 * n_pe, L, cores, d, tag="pe")
+    # ---- kernel B on real pairs ----
+    dump = os.path.join(d, "pairs")
+    e2e.run_mem(b200_exe, prefix, [os.path.join(d, "dump.fq")], os.path.join(d, "dump.sam"), cores,
+                {"MEME_B200": "1", "MEME_B200_BSW": "1", "MEME_B200_DUMP_PAIRS": dump, "MEME_B200_WARM_READS": "0"})
+    bsw = {"pairs_from": "left/right extension pairs of 200000 reads, dumped by the patched aligner (real h0, real windows)",
+           "band": "w=100 then 200 for pairs that are not final (MAX_BAND_TRY), decided on the device"}
+    tot_cells = tot_ms = tot_pairs = 0
+    cpu_ms = 0.0
+    for side in ("left", "right"):
+        r = e2e.bench_bsw_dump(f"{dump}.{side}", device=local)
+        c = e2e.bench_bsw_cpu(f"{dump}.{side}", cores)
+        bsw[side] = {"gpu": r, "cpu_getScores": c}
+        tot_cells += r["cells"]; tot_ms += r["ms"]; tot_pairs += r["pairs"]
+        if c and "ms_mean" in c:
+            cpu_ms += c["ms_mean"]
+    bsw["gcups"] = tot_cells / (tot_ms / 1e3) / 1e9
+    bsw["pairs_per_s"] = tot_pairs / (tot_ms / 1e3)
+    if cpu_ms:
+        bsw["cpu_baseline"] = {"pairs_per_s": tot_pairs / (cpu_ms / 1e3), "gcups_same_cells": tot_cells / (cpu_ms / 1e3) / 1e9, "cores": cores,
+                               "kind": "reference", "what": "BandedPairWiseSW::getScores8/16 (oracle/_ref/bsw_shim bench), pairs classed and "
+                               "sorted as the extension driver does, blocks of 4096 pairs per host thread"}
+    return align, bsw
 
 
 def emit(line: dict):

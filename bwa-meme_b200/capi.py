@@ -20,9 +20,9 @@ SEQPAIR_DTYPE = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1"
 RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
 
 EXPORTS = [
-    "meme_index_load", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
+    "meme_index_load", "meme_index_load_devices", "meme_seed_batch_multi", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
-    "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
+    "meme_seed_warmup", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_last_error", "meme_device_count", "meme_version",

@@ -27,7 +27,7 @@
 
 #define BSW_WARPS 4
 #define BSW_NCLASS 10
-#define BSW_IS_NCLASS 5
+#define BSW_IS_NCLASS 6
 #define BSW_IS_THREADS 128
 #define FULL 0xffffffffu
 #define NEG_BIG (-(1 << 28))
@@ -359,7 +359,7 @@ __global__ void k_bsw_long(BswConst P, int tries, int prev_is_h0, meme_seqpair_t
 // the inter-sequence kernel (meme_bsw_is.cuh): one thread per pair, rows [column][thread] in shared memory
 // ---------------------------------------------------------------------------------------------
 // row words per thread of the five classes (query length + 2 <= words)
-static const int BSW_IS_WORDS[BSW_IS_NCLASS] = {34, 66, 98, 162, 322};
+static const int BSW_IS_WORDS[BSW_IS_NCLASS] = {34, 66, 98, 130, 162, 322};
 static inline int bsw_is_class_of(int qlen)
 {
     for (int c = 0; c < BSW_IS_NCLASS; c++) if (qlen + 2 <= BSW_IS_WORDS[c]) return c;

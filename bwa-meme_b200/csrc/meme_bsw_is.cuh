@@ -26,7 +26,15 @@
 #define BSW_HD __host__ __device__ __forceinline__
 #define BSW_ADDMAX(a, b, c) __viaddmax_s32((a), (b), (c))          /* max(a + b, c) */
 #define BSW_MAX3(a, b, c) __vimax3_s32((a), (b), (c))
-#define BSW_PRMT(lo, hi, sel) ((int)__byte_perm((lo), (hi), (sel)))
+// prmt.b32 in its default mode: bit 3 of a selector nibble replicates the sign of the selected byte
+// (__byte_perm masks the selector to 3 bits per nibble, so the PTX instruction is written out)
+__device__ __forceinline__ int bsw_prmt_dev(unsigned lo, unsigned hi, unsigned sel)
+{
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
+#define BSW_PRMT(lo, hi, sel) bsw_prmt_dev((lo), (hi), (sel))
 #else
 #define BSW_HD inline
 #define BSW_ADDMAX(a, b, c) (((a) + (b)) > (c) ? ((a) + (b)) : (c))
@@ -60,17 +68,26 @@ BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qle
                        u32 *row, uint8_t *qrow, const int stride, BswIsOut &out, u64 &cells)
 {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins, e_del = P.e_del, e_ins = P.e_ins;
-    // ---- first row (reference L143-145) and the query bases ----
+    // ---- first row (reference L143-145) and the query bases: 16 columns at a time, their loads in flight together ----
     {
         int hv = h0;
-        for (int j = 0; j <= qlen; j++) {
-            int v;
-            if (j == 0) v = h0;
-            else if (j == 1) { hv = h0 > oe_ins ? h0 - oe_ins : 0; v = hv; }
-            else { if (hv > e_ins) hv -= e_ins; else hv = 0; v = hv; }
-            // (the reference stops at the first H <= e_ins and leaves zeros behind: same values)
-            row[j * stride] = (u32)v;
-            qrow[j * stride] = j < qlen ? query[j] : (uint8_t)4;
+        for (int j0 = 0; j0 <= qlen; j0 += 16) {
+            uint8_t qb[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) qb[k] = j0 + k < qlen ? query[j0 + k] : (uint8_t)4;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int j = j0 + k;
+                if (j <= qlen) {
+                    int v;
+                    if (j == 0) v = h0;
+                    else if (j == 1) { hv = h0 > oe_ins ? h0 - oe_ins : 0; v = hv; }
+                    else { if (hv > e_ins) hv -= e_ins; else hv = 0; v = hv; }
+                    // (the reference stops at the first H <= e_ins and leaves zeros behind: same values)
+                    row[j * stride] = (u32)v;
+                    qrow[j * stride] = qb[k];
+                }
+            }
         }
     }
     // ---- band (L147-156) ----
@@ -85,8 +102,10 @@ BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qle
     }
     int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen;
+    int tc_next = tlen > 0 ? target[0] : 0;
     for (int i = 0; i < tlen; i++) {
-        const int tc = target[i];
+        const int tc = tc_next;
+        if (i + 1 < tlen) tc_next = target[i + 1];                 // the next row's base arrives while this row is computed
         int f = 0, h1, key = -1;
         if (beg < i - w) beg = i - w;
         if (end > i + w + 1) end = i + w + 1;
@@ -136,13 +155,16 @@ BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qle
             if (di > dj) { if (best - m - (di - dj) * e_del > P.zdrop) break; }
             else { if (best - m - (dj - di) * e_ins > P.zdrop) break; }
         }
-        // ---- shrink the band to the live cells (L218-221) ----
-        int j = beg;
-        while (j < end && row[(size_t)j * stride] == 0) j++;
-        beg = j;
-        j = end;
-        while (j >= beg && row[(size_t)j * stride] == 0) j--;
-        end = j + 2 < qlen ? j + 2 : qlen;
+        // ---- shrink the band to the live cells (L218-221): the usual first probes are loaded together ----
+        {
+            const u32 wb = beg < end ? row[(size_t)beg * stride] : 1u, we = row[(size_t)end * stride];   // (beg < end here: an empty band ended the loop above)
+            int j = beg;
+            if (wb == 0 && beg < end) { j++; while (j < end && row[(size_t)j * stride] == 0) j++; }
+            beg = j;
+            j = end;
+            if (we == 0 && end >= beg) { j--; while (j >= beg && row[(size_t)j * stride] == 0) j--; }
+            end = j + 2 < qlen ? j + 2 : qlen;
+        }
     }
     out.score = best; out.tle = best_i + 1; out.gtle = best_ie + 1; out.qle = best_j + 1;
     out.gscore = gscore; out.max_off = max_off;

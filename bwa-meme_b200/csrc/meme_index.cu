@@ -14,6 +14,9 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <string>
+#include <vector>
 #include "meme_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -173,6 +176,8 @@ static int upload_rmi(Source &src, RmiRec **d_out, u64 *n_out, cudaStream_t st, 
     return MEME_OK;
 }
 
+extern "C" void meme_index_free(meme_index_t *ix);
+
 static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mode, int device, meme_index_t **out)
 {
     int ndev = 0;
@@ -193,6 +198,11 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
     meme_index *ix = (meme_index *)calloc(1, sizeof(meme_index));
     if (!ix) return MEME_E_NOMEM;
     ix->device = device;
+    // every early return below releases what was allocated so far (the handle, its arrays, the staging buffers)
+    struct Guard {
+        meme_index *ix; uint8_t *h_stage = nullptr, *d_stage = nullptr; bool ok = false;
+        ~Guard() { if (h_stage) cudaFreeHost(h_stage); if (d_stage) cudaFree(d_stage); if (!ok) meme_index_free(ix); }
+    } guard{ix};
     CUDA_TRY(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     cudaStream_t st = ix->stream;
@@ -217,15 +227,16 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
     }
     // chunked staging: pinned host buffer + device buffer
     const size_t CH = (size_t)160 << 20;                    // bytes; multiple of 32 and of 5
-    uint8_t *h_stage = nullptr, *d_stage = nullptr;
-    CUDA_TRY(cudaMallocHost((void **)&h_stage, CH));
-    CUDA_TRY(cudaMalloc((void **)&d_stage, CH));
+    CUDA_TRY(cudaMallocHost((void **)&guard.h_stage, CH));
+    CUDA_TRY(cudaMalloc((void **)&guard.d_stage, CH));
+    uint8_t *const h_stage = guard.h_stage, *const d_stage = guard.d_stage;
     for (u64 done = 0; done < n;) {                         // text -> pac
         size_t got = text.read(h_stage, CH);
         if (!got) { meme_set_error("short read of .0123"); return MEME_E_IO; }
         CUDA_TRY(cudaMemcpyAsync(d_stage, h_stage, got, cudaMemcpyHostToDevice, st));
         u64 words = (got + 31) / 32;
         k_pack_text<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(d_stage, got, ix->d_pac, done / 32);
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(st));
         done += got;
     }
@@ -235,11 +246,10 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
         u64 cnt = got / 5;
         CUDA_TRY(cudaMemcpyAsync(d_stage, h_stage, got, cudaMemcpyHostToDevice, st));
         k_unpack_pos<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_stage, cnt, done, ix->d_pos_lo, ix->d_pos_hi);
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(st));
         done += cnt;
     }
-    cudaFreeHost(h_stage);
-    cudaFree(d_stage);
     v.pac = ix->d_pac; v.pos_lo = ix->d_pos_lo; v.pos_hi = ix->d_pos_hi;
     if (mode >= 2) {
         k_build_keys_isa<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, ix->d_keys, ix->d_isa_lo, ix->d_isa_hi);
@@ -259,6 +269,7 @@ static int build_index(Source &text, Source &pos, Source &l1, Source &l2, int mo
     for (int k = 0; k < 6; k++) CUDA_TRY(cudaEventCreate(&ix->ev[k]));
     CUDA_TRY(cudaStreamSynchronize(st));
     ix->launches = 3;
+    guard.ok = true;
     *out = ix;
     return MEME_OK;
 }
@@ -279,6 +290,31 @@ extern "C" int meme_index_load(const char *prefix, int mode, int device, meme_in
     if (l1.f) fclose(l1.f);
     if (l2.f) fclose(l2.f);
     return rc;
+}
+
+// The index replicated on `ndev` devices (reads shard across GPUs, the index does not: SURVEY.md section 8e).  The
+// devices are loaded concurrently, one host thread each; out receives ndev handles (all or none).
+extern "C" int meme_index_load_devices(const char *prefix, int mode, const int *devices, int ndev, meme_index_t **out)
+{
+    if (!prefix || !devices || ndev < 1 || !out) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    std::vector<int> rc((size_t)ndev, MEME_OK);
+    std::vector<std::string> err((size_t)ndev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++) {
+        out[d] = nullptr;
+        th.emplace_back([&, d] {
+            rc[(size_t)d] = meme_index_load(prefix, mode, devices[d], &out[d]);
+            if (rc[(size_t)d]) err[(size_t)d] = meme_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; d++)
+        if (rc[(size_t)d]) {
+            for (int k = 0; k < ndev; k++) if (out[k]) { meme_index_free(out[k]); out[k] = nullptr; }
+            meme_set_error("device %d: %s", devices[d], err[(size_t)d].c_str());
+            return rc[(size_t)d];
+        }
+    return MEME_OK;
 }
 
 extern "C" int meme_index_from_host(const uint8_t *text0123, uint64_t sa_num, const uint8_t *pos_packed,
@@ -311,7 +347,7 @@ extern "C" void meme_index_free(meme_index_t *ix)
     void *host[] = {ix->h_smems, ix->h_hits, ix->h_smem_off, ix->h_hit_off, ix->h_ctrl};
     for (void *p : host) if (p) cudaFreeHost(p);
     for (int k = 0; k < 6; k++) if (ix->ev[k]) cudaEventDestroy(ix->ev[k]);
-    cudaStreamDestroy(ix->own_stream);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     free(ix);
 }
 

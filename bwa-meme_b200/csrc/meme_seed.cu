@@ -13,6 +13,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
 #include <utility>
 #include "meme_common.cuh"
 #include "meme_seed_task.cuh"
@@ -592,6 +595,49 @@ static int seed_batch_pipelined(meme_index_t *ix, const uint8_t *codes, const in
     return MEME_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warm-up: one throw-away batch of reads sampled from the indexed text itself (1 % pseudo-random substitutions), so that
+// module loading and every pool the batch path grows on demand (device pools, pinned result arrays) are paid where the
+// caller loads the index, not inside its first timed chunk.
+// ---------------------------------------------------------------------------------------------
+extern "C" int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                               const meme_seed_opt_t *opt, meme_seed_result_t *out);
+
+__global__ void k_warm_reads(IndexView ix, int64_t n_reads, int read_len, uint8_t *__restrict__ codes)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_reads * read_len) return;
+    const int64_t r = t / read_len;
+    const int k = (int)(t % read_len);
+    const u64 span = ix.sa_num > (u64)read_len + 1 ? ix.sa_num - (u64)read_len - 1 : 1;
+    const u64 p = ((u64)r * 0x9E3779B97F4A7C15ull >> 11) % span + (u64)k;
+    u32 c = (u32)(ix.pac[p >> 5] >> (2 * (p & 31))) & 3;
+    u64 h = (u64)t * 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    if (h % 100 == 0) c = (c + 1 + (u32)(h >> 40) % 3) & 3;
+    codes[t] = (uint8_t)c;
+}
+
+extern "C" int meme_seed_warmup(meme_index_t *ix, int64_t n_reads, int32_t read_len)
+{
+    if (!ix || n_reads <= 0 || read_len <= 0 || read_len > MEME_MAX_READ_LEN) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const size_t nb = (size_t)n_reads * (size_t)read_len;
+    uint8_t *d = nullptr, *h = nullptr;
+    int64_t *off = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, nb));
+    CUDA_TRY(cudaMallocHost((void **)&h, nb));
+    CUDA_TRY(cudaMallocHost((void **)&off, (size_t)(n_reads + 1) * 8));
+    k_warm_reads<<<(unsigned)((nb + 255) / 256), 256, 0, ix->stream>>>(ix->v, n_reads, read_len, d);
+    CUDA_TRY(cudaMemcpyAsync(h, d, nb, cudaMemcpyDeviceToHost, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    for (int64_t i = 0; i <= n_reads; i++) off[i] = i * read_len;
+    meme_seed_opt_t opt = {19, 28, 10, 20, 3, 500};
+    meme_seed_result_t res;
+    int rc = meme_seed_batch(ix, h, off, n_reads, &opt, &res);
+    cudaFree(d); cudaFreeHost(h); cudaFreeHost(off);
+    return rc;
+}
+
 extern "C" int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
                                const meme_seed_opt_t *opt, meme_seed_result_t *out)
 {
@@ -602,4 +648,40 @@ extern "C" int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int
     if ((rc = meme_seed_upload(ix, codes, read_off, n_reads))) return rc;
     if ((rc = meme_seed_run(ix, opt))) return rc;
     return meme_seed_download(ix, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: reads are independent units, so a chunk is cut into `ndev` contiguous read ranges (pair-aligned when
+// `pair_aligned` != 0: both mates of a pair stay on one device) and every range runs through meme_seed_batch on its own
+// device, concurrently, one host thread per device.  The index is replicated (meme_index_load_devices).  There is no
+// device-to-device exchange on this path: each device delivers its lists into its own pinned host arrays, and
+// shard_begin[d] .. shard_begin[d+1] tells the caller which reads outs[d] describes.
+// ---------------------------------------------------------------------------------------------
+extern "C" int meme_seed_batch_multi(meme_index_t *const *ixs, int ndev, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                                     int pair_aligned, const meme_seed_opt_t *opt, meme_seed_result_t *outs, int64_t *shard_begin)
+{
+    if (!ixs || ndev < 1 || !read_off || !opt || !outs || !shard_begin || n_reads < 0) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    for (int d = 0; d <= ndev; d++) {
+        int64_t b = n_reads * d / ndev;
+        if (pair_aligned) b &= ~(int64_t)1;
+        shard_begin[d] = d == ndev ? n_reads : b;
+    }
+    std::vector<int> rc((size_t)ndev, MEME_OK);
+    std::vector<std::string> err((size_t)ndev);
+    std::vector<std::vector<int64_t>> offs((size_t)ndev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++) {
+        th.emplace_back([&, d] {
+            const int64_t r0 = shard_begin[d], r1 = shard_begin[d + 1], n = r1 - r0;
+            std::vector<int64_t> &o = offs[(size_t)d];
+            o.resize((size_t)n + 1);
+            for (int64_t i = 0; i <= n; i++) o[(size_t)i] = read_off[r0 + i] - read_off[r0];
+            rc[(size_t)d] = meme_seed_batch(ixs[d], codes ? codes + read_off[r0] : nullptr, o.data(), n, opt, &outs[d]);
+            if (rc[(size_t)d]) err[(size_t)d] = meme_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; d++)
+        if (rc[(size_t)d]) { meme_set_error("shard %d: %s", d, err[(size_t)d].c_str()); return rc[(size_t)d]; }
+    return MEME_OK;
 }

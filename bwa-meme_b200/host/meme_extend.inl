@@ -36,6 +36,12 @@ struct Arena {
         if (p) { if (keep) memcpy(q, p, (size_t)keep * sizeof(T)); meme_glue_pinned_free(p); }
         p = q; cap = ncap;
     }
+    template <class T> static void reserve(T *&p, int64_t &cap, int64_t count)
+    {   // exact size (no growth margin): matches a pre-pinned block of the glue's cache
+        if (p || count <= cap) return;
+        p = (T *)meme_glue_pinned_alloc((size_t)count * sizeof(T));
+        cap = count;
+    }
     void reset() { n = n_ref = n_qer = 0; }
     SeqPair *new_pair() { grow(pairs, cap, n, n + 1); return &pairs[n++]; }
     uint8_t *take_ref(int64_t len) { grow(ref, cap_ref, n_ref, n_ref + len + 1); uint8_t *p = ref + n_ref; n_ref += len; return p; }
@@ -252,6 +258,14 @@ bool meme_extend_chunk(worker_t &w, int n)
         ThreadState &S = g_ts[(size_t)t];
         S.left.reset(); S.right.reset(); S.srt.clear();
         const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
+        {   // first chunk: the arenas take their typical share (up to 6 pairs per read, 200 + 100 sequence bytes per pair),
+            // from the blocks the glue page-locked at index load when it could
+            const int64_t est = (int64_t)(r1 - r0) * 6;
+            for (Arena *A : {&S.left, &S.right}) {
+                Arena::reserve(A->pairs, A->cap, est); Arena::reserve(A->ref, A->cap_ref, est * 200); Arena::reserve(A->qer, A->cap_qer, est * 100);
+                Arena::reserve(A->w_used, A->cap_w, est);
+            }
+        }
         for (int l = r0; l < r1; l++) {
             g_srt_off[(size_t)l] = (int64_t)S.srt.size();
             collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S);

@@ -1,12 +1,14 @@
 // meme_glue.cpp -- see meme_glue.h.  Compiled together with the (patched) reference sources; binds
 // libmeme_b200.so with dlopen so that the aligner has no link-time CUDA dependency.
 #include <dlfcn.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
 #include <mutex>
+#include <thread>
 #include <chrono>
 #include "meme_glue.h"
 #include "../../include/meme_b200.h"
@@ -17,6 +19,9 @@ struct Api {
     void *so = nullptr;
     decltype(&meme_index_load) index_load = nullptr;
     decltype(&meme_seed_batch) seed_batch = nullptr;
+    decltype(&meme_seed_warmup) seed_warmup = nullptr;
+    decltype(&meme_index_load_devices) index_load_devices = nullptr;
+    decltype(&meme_seed_batch_multi) seed_batch_multi = nullptr;
     decltype(&meme_bsw_create) bsw_create = nullptr;
     decltype(&meme_bsw_batch) bsw_batch = nullptr;
     decltype(&meme_last_error) last_error = nullptr;
@@ -39,6 +44,9 @@ Api &api()
         if (!a.so) { fprintf(stderr, "[meme_b200] cannot load the CUDA library: %s\n", dlerror()); exit(EXIT_FAILURE); }
         a.index_load = (decltype(a.index_load))dlsym(a.so, "meme_index_load");
         a.seed_batch = (decltype(a.seed_batch))dlsym(a.so, "meme_seed_batch");
+        a.seed_warmup = (decltype(a.seed_warmup))dlsym(a.so, "meme_seed_warmup");
+        a.index_load_devices = (decltype(a.index_load_devices))dlsym(a.so, "meme_index_load_devices");
+        a.seed_batch_multi = (decltype(a.seed_batch_multi))dlsym(a.so, "meme_seed_batch_multi");
         a.bsw_create = (decltype(a.bsw_create))dlsym(a.so, "meme_bsw_create");
         a.bsw_batch = (decltype(a.bsw_batch))dlsym(a.so, "meme_bsw_batch");
         a.last_error = (decltype(a.last_error))dlsym(a.so, "meme_last_error");
@@ -49,7 +57,8 @@ Api &api()
         a.pinned_alloc = (decltype(a.pinned_alloc))dlsym(a.so, "meme_pinned_alloc");
         a.pinned_free = (decltype(a.pinned_free))dlsym(a.so, "meme_pinned_free");
         a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
-               a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.pinned_alloc && a.pinned_free;
+               a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
+               a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
     });
     return a;
@@ -62,11 +71,14 @@ bool env_on(const char *name)
 }
 
 std::string g_prefix;
-meme_index_t *g_index = nullptr;
+// one index handle per GPU (MEME_B200_DEVICES=0,1,..; default: MEME_B200_DEVICE or 0): reads shard, the index is replicated
+std::vector<int> g_devices;
+std::vector<meme_index_t *> g_index;
+std::vector<meme_seed_result_t> g_shard;       // results of the chunk being processed, one per device
+std::vector<int64_t> g_shard_begin;
 // results of the chunk being processed (valid until the next meme_glue_seed_chunk)
 const bseq1_t *g_base = nullptr;
 int g_n = 0;
-meme_seed_result_t g_res;
 bool g_have = false;
 int g_max_occ = 0;
 double g_seed_s = 0;
@@ -82,15 +94,39 @@ long g_seed_reads = 0;
 
 static void ensure_index()
 {
-    if (g_index) return;
+    if (!g_index.empty()) return;
     Api &a = api();
     int mode = getenv("MEME_B200_MODE") ? atoi(getenv("MEME_B200_MODE")) : MODE;
-    int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+    if (const char *ds = getenv("MEME_B200_DEVICES")) {
+        for (const char *p = ds; *p;) { g_devices.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; }
+    }
+    if (g_devices.empty()) g_devices.push_back(getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0);
+    const int nd = (int)g_devices.size();
+    g_index.assign((size_t)nd, nullptr);
+    g_shard.resize((size_t)nd);
+    g_shard_begin.assign((size_t)nd + 1, 0);
     auto t0 = std::chrono::steady_clock::now();
-    int rc = a.index_load(g_prefix.c_str(), mode, dev, &g_index);
-    if (rc) die("meme_index_load", rc);
-    fprintf(stderr, "[meme_b200] index %s resident on GPU %d (mode %d) in %.2f s\n", g_prefix.c_str(), dev, mode,
+    int rc = a.index_load_devices(g_prefix.c_str(), mode, g_devices.data(), nd, g_index.data());
+    if (rc) die("meme_index_load_devices", rc);
+    fprintf(stderr, "[meme_b200] index %s resident on %d GPU(s) (mode %d) in %.2f s\n", g_prefix.c_str(), nd, mode,
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    // kernels loaded and pools sized for a typical chunk before the first timed chunk (-K 100000000 at 150 bp ~ 667 k reads)
+    long warm = getenv("MEME_B200_WARM_READS") ? atol(getenv("MEME_B200_WARM_READS")) : 700000;
+    if (warm > 0) {
+        auto w0 = std::chrono::steady_clock::now();
+        for (int d = 0; d < nd; d++) {
+            rc = a.seed_warmup(g_index[(size_t)d], warm / nd + 1, 150);
+            if (rc) die("meme_seed_warmup", rc);
+        }
+        fprintf(stderr, "[meme_b200] warm-up batch of %ld reads in %.2f s\n", warm,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
+        if (env_on("MEME_B200_BSW")) {
+            int threads = getenv("MEME_B200_THREADS") ? atoi(getenv("MEME_B200_THREADS")) : (int)std::thread::hardware_concurrency();
+            cpu_set_t cs;
+            if (!getenv("MEME_B200_THREADS") && sched_getaffinity(0, sizeof cs, &cs) == 0) threads = CPU_COUNT(&cs);
+            meme_glue_pinned_reserve(threads, warm);
+        }
+    }
 }
 
 // Called from memoryAllocLearned(): the index goes to HBM where the reference loads its own copy, i.e. outside
@@ -135,14 +171,18 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     // src/bwamem.cpp:L1154-1155): a repeat SMEM with 1e5 occurrences costs max_occ positions, not 1e5
     so.max_occ = opt->max_occ > 0 ? opt->max_occ : 0;
     g_max_occ = so.max_occ;
-    int rc = a.seed_batch(g_index, codes.data(), off.data(), n, &so, &g_res);
-    if (rc) die("meme_seed_batch", rc);
+    // pairs stay together: with paired-end input consecutive reads are mates (the chunk holds whole pairs)
+    int rc = a.seed_batch_multi(g_index.data(), (int)g_index.size(), codes.data(), off.data(), n, (opt->flag & MEM_F_PE) ? 1 : 0, &so,
+                                g_shard.data(), g_shard_begin.data());
+    if (rc) die("meme_seed_batch_multi", rc);
+    long tot_smems = 0, tot_hits = 0;
+    for (auto &r : g_shard) { tot_smems += (long)r.n_smems; tot_hits += (long)r.n_hits; }
     g_base = seqs; g_n = n; g_have = true;
     g_seed_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     g_seed_reads += n;
     auto t2 = std::chrono::steady_clock::now();
     fprintf(stderr, "[meme_b200] seeded %d reads on the GPU: %ld SMEMs, %ld hits (cumulative %.3f s for %ld reads; this chunk: "
-            "codes %.1f ms, meme_seed_batch %.1f ms)\n", n, (long)g_res.n_smems, (long)g_res.n_hits, g_seed_s, g_seed_reads,
+            "codes %.1f ms, meme_seed_batch %.1f ms)\n", n, tot_smems, tot_hits, g_seed_s, g_seed_reads,
             std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3);
 }
 
@@ -152,6 +192,10 @@ bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits)
     if (!g_have) return false;
     long idx = (long)(s - g_base);
     if (idx < 0 || idx >= g_n) return false;
+    size_t sh = 0;
+    while (sh + 1 < g_shard.size() && idx >= g_shard_begin[sh + 1]) sh++;
+    const meme_seed_result_t &g_res = g_shard[sh];
+    idx -= (long)g_shard_begin[sh];
     int64_t s0 = g_res.smem_off[idx], s1 = g_res.smem_off[idx + 1];
     int64_t h0 = g_res.hit_off[idx], h1 = g_res.hit_off[idx + 1];
     size_t ns = (size_t)(s1 - s0), nh = (size_t)(h1 - h0);
@@ -201,7 +245,7 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
     static thread_local meme_bsw_t *h = nullptr;
     static thread_local std::vector<meme_seqpair_t> tmp;
     if (!h) {
-        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
+        int dev = g_devices.empty() ? (getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0) : g_devices[0];
         int rc = A.bsw_create(dev, &h);
         if (rc) die("meme_bsw_create", rc);
     }
@@ -231,8 +275,44 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
 // ---- chunk-level seed extension (meme_extend.inl, included by the patched bwamem.cpp) ----
 bool meme_glue_bsw_enabled() { return env_on("MEME_B200_BSW"); }
 
+// Pinned blocks reserved where the index is loaded (outside the aligner's per-chunk timers): page-locking the ~2 GB of
+// pair arenas a chunk needs costs about a second, which the first chunk would otherwise pay.
+namespace {
+struct PinnedBlock { void *p; size_t bytes; };
+std::vector<PinnedBlock> g_pin_cache;
+std::mutex g_pin_mu;
+}
+
+void meme_glue_pinned_reserve(int threads, long reads_per_chunk)
+{
+    if (threads < 1 || reads_per_chunk < 1) return;
+    auto t0 = std::chrono::steady_clock::now();
+    // the same sizes meme_extend.inl asks for on its first chunk (6 pairs per read of head-room, 56 + 200 + 100 + 4 bytes each)
+    const size_t est = (size_t)(reads_per_chunk / threads + 1) * 6;
+    const size_t sizes[4] = {est * sizeof(SeqPair), est * 200, est * 100, est * 4};
+    size_t total = 0;
+    for (int t = 0; t < threads * 2; t++)
+        for (size_t b : sizes) {
+            void *p = nullptr;
+            if (api().pinned_alloc(b, &p)) return;          // not fatal: the arenas fall back to allocating on demand
+            std::lock_guard<std::mutex> lk(g_pin_mu);
+            g_pin_cache.push_back({p, b});
+            total += b;
+        }
+    fprintf(stderr, "[meme_b200] %.2f GB of pinned pair arenas reserved for %d threads in %.2f s\n", total / 1e9, threads,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+
 void *meme_glue_pinned_alloc(size_t bytes)
 {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < g_pin_cache.size(); i++)
+            if (g_pin_cache[i].bytes >= bytes && g_pin_cache[i].bytes <= bytes + bytes / 2 + (1 << 20) &&
+                (best == (size_t)-1 || g_pin_cache[i].bytes < g_pin_cache[best].bytes)) best = i;
+        if (best != (size_t)-1) { void *p = g_pin_cache[best].p; g_pin_cache.erase(g_pin_cache.begin() + (long)best); return p; }
+    }
     void *p = nullptr;
     int rc = api().pinned_alloc(bytes, &p);
     if (rc) die("meme_pinned_alloc", rc);
@@ -248,11 +328,15 @@ void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t
                             int a, int b, int32_t **w_used)
 {
     Api &A = api();
-    static meme_bsw_t *h = nullptr;
-    if (!h) {
-        int dev = getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0;
-        int rc = A.bsw_create(dev, &h);
-        if (rc) die("meme_bsw_create", rc);
+    static std::vector<meme_bsw_t *> hs;
+    if (hs.empty()) {
+        if (g_devices.empty()) g_devices.push_back(getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0);
+        for (int dev : g_devices) {
+            meme_bsw_t *h = nullptr;
+            int rc = A.bsw_create(dev, &h);
+            if (rc) die("meme_bsw_create", rc);
+            hs.push_back(h);
+        }
     }
     static_assert(sizeof(SeqPair) == sizeof(meme_seqpair_t), "SeqPair layout");
     meme_bsw_opt_t o = {o_del, e_del, o_ins, e_ins, zdrop, end_bonus, a, b};
@@ -285,13 +369,29 @@ void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t
             dumped++;
         }
     }
-    int rc = A.bsw_set_match(h, a);
-    if (rc) die("meme_bsw_set_match", rc);
-    rc = A.bsw_upload_segments(h, nseg, (const meme_seqpair_t *const *)pairs, n_pairs, (const uint8_t *const *)ref, n_ref,
-                               (const uint8_t *const *)qer, n_qer);
-    if (rc) die("meme_bsw_upload_segments", rc);
-    rc = A.bsw_run_ext(h, w, tries, prev_is_h0, &o);
-    if (rc) die("meme_bsw_run_ext", rc);
-    rc = A.bsw_download_segments(h, nseg, (meme_seqpair_t *const *)pairs, n_pairs, w_used);
-    if (rc) die("meme_bsw_download_segments", rc);
+    // the segments (one per host thread) are dealt round-robin to the devices; every device runs its share concurrently
+    const int nd = (int)hs.size();
+    std::vector<std::thread> th;
+    std::vector<int> rcs((size_t)nd, 0);
+    std::vector<std::string> errs((size_t)nd);
+    for (int d = 0; d < nd; d++) {
+        th.emplace_back([&, d] {
+            std::vector<const meme_seqpair_t *> sp; std::vector<meme_seqpair_t *> spw; std::vector<int64_t> np, nr, nq;
+            std::vector<const uint8_t *> pr, pq; std::vector<int32_t *> pw;
+            for (int s = d; s < nseg; s += nd) {
+                sp.push_back((const meme_seqpair_t *)pairs[s]); spw.push_back((meme_seqpair_t *)pairs[s]); np.push_back(n_pairs[s]);
+                pr.push_back(ref[s]); nr.push_back(n_ref[s]); pq.push_back(qer[s]); nq.push_back(n_qer[s]); pw.push_back(w_used[s]);
+            }
+            const int k = (int)sp.size();
+            int rc = A.bsw_set_match(hs[(size_t)d], a);
+            if (!rc) rc = A.bsw_upload_segments(hs[(size_t)d], k, sp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data());
+            if (!rc) rc = A.bsw_run_ext(hs[(size_t)d], w, tries, prev_is_h0, &o);
+            if (!rc) rc = A.bsw_download_segments(hs[(size_t)d], k, spw.data(), np.data(), pw.data());
+            rcs[(size_t)d] = rc;
+            if (rc) errs[(size_t)d] = A.last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rcs[(size_t)d]) { fprintf(stderr, "[meme_b200] seed extension on GPU %d failed (%d): %s\n", g_devices[(size_t)d], rcs[(size_t)d], errs[(size_t)d].c_str()); exit(EXIT_FAILURE); }
 }

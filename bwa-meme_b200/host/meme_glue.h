@@ -28,6 +28,7 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
 
 // used by meme_extend.inl
 bool meme_glue_bsw_enabled();
+void meme_glue_pinned_reserve(int threads, long reads_per_chunk);
 void *meme_glue_pinned_alloc(size_t bytes);
 void meme_glue_pinned_free(void *p);
 void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,

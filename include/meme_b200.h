@@ -82,6 +82,10 @@ typedef struct {
  * GPU.  mode: 1 = positions only, 2 = + inline keys, 3 = + inverse SA (Makefile:L40-46). */
 int meme_index_load(const char *prefix, int mode, int device, meme_index_t **out);
 
+/* The index replicated on ndev devices, loaded concurrently; out receives ndev handles (all or none).  Reads shard
+ * across GPUs, the index does not. */
+int meme_index_load_devices(const char *prefix, int mode, const int *devices, int ndev, meme_index_t **out);
+
 /* Same, from host buffers (what the files would contain). l1/l2 are 24-byte records. */
 int meme_index_from_host(const uint8_t *text0123, uint64_t sa_num, const uint8_t *pos_packed,
                          const void *l1_params, uint64_t n_l1, const void *l2_params, uint64_t n_l2,
@@ -102,6 +106,18 @@ int meme_index_download(const meme_index_t *ix, uint64_t *keys, uint64_t *pos, u
  * One call = upload + run + download. */
 int meme_seed_batch(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
                     const meme_seed_opt_t *opt, meme_seed_result_t *out);
+
+/* Multi-GPU form: the chunk is cut into ndev contiguous read ranges (both mates of a pair on one device when
+ * pair_aligned != 0), every range runs on its own device concurrently; outs[d] describes reads
+ * shard_begin[d] .. shard_begin[d+1] (shard_begin has ndev+1 entries).  No device-to-device exchange: each device
+ * delivers into its own pinned host arrays. */
+int meme_seed_batch_multi(meme_index_t *const *ixs, int ndev, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                          int pair_aligned, const meme_seed_opt_t *opt, meme_seed_result_t *outs, int64_t *shard_begin);
+
+/* One throw-away batch of n_reads reads of read_len bases sampled from the indexed text: loads the kernels and sizes
+ * every pool of the batch path (device pools, pinned result arrays) for chunks of that size, so that a caller's first
+ * real chunk does not pay for it.  Call once after meme_index_load with the expected chunk size. */
+int meme_seed_warmup(meme_index_t *ix, int64_t n_reads, int32_t read_len);
 
 /* The same in three steps, so that a caller (and bench.py) can keep inputs resident in HBM. */
 int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads);
