@@ -20,7 +20,7 @@ SEQPAIR_DTYPE = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1"
 RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
 
 EXPORTS = [
-    "meme_index_load", "meme_index_load_devices", "meme_seed_batch_multi", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
+    "meme_index_load", "meme_rmi_lookup", "meme_index_load_devices", "meme_seed_batch_multi", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
     "meme_seed_warmup", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
@@ -206,6 +206,14 @@ class MemeIndex:
             return {"n_reads": int(res.n_reads), "n_smems": int(res.n_smems), "n_hits": int(res.n_hits)}
         return self._wrap(res)
 
+    def rmi_lookup(self, keys: np.ndarray):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        pred = np.zeros(len(keys), np.uint64)
+        err = np.zeros(len(keys), np.uint64)
+        lib().meme_rmi_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        _check(lib().meme_rmi_lookup(self.h, keys.ctypes.data, len(keys), pred.ctypes.data, err.ctypes.data), "meme_rmi_lookup")
+        return pred, err
+
     def seed_totals(self):
         a, b = C.c_int64(), C.c_int64()
         _check(lib().meme_seed_totals(self.h, C.byref(a), C.byref(b)), "meme_seed_totals")
@@ -220,7 +228,7 @@ class MemeIndex:
         c = (C.c_uint64 * 8)()
         _check(lib().meme_seed_counters(self.h, C.byref(c)), "meme_seed_counters")
         return {"searches": int(c[0]), "block_probes": int(c[1]), "kary_rounds": int(c[2]), "ext_rounds": int(c[3]),
-                "overflow_reads": int(c[4]), "launches": int(c[5]), "redo_reads": int(c[6]), "group": int(c[7])}
+                "pac_rounds": int(c[4]), "launches": int(c[5]), "reseed_tasks": int(c[6]), "round_trips": int(c[7])}
 
 
 class MemeBsw:

@@ -292,6 +292,49 @@ extern "C" int meme_index_load(const char *prefix, int mode, int device, meme_in
     return rc;
 }
 
+// P-RMI inference for a batch of keys (learned_index_lookup, reference src/LearnedIndex_seeding.cpp:L186-210), with the
+// same arithmetic the seeding kernels use on the re-laid-out records: fp64 fma, optional partial layer, clamp.  The
+// seeding kernels inline this between their memory requests; this entry point exists so that tests can pin the device
+// prediction and error word against the reference formula key by key.
+__global__ void k_rmi_lookup(IndexView ix, const u64 *__restrict__ keys, int64_t n, u64 *__restrict__ pred, u64 *__restrict__ err)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 key = keys[i];
+    RmiRec r = ix.l2[key >> ix.bit_shift];
+    double p = fma(r.beta, __ull2double_rn(key), r.alpha);
+    u64 e = r.err;
+    if (e >> 63) {
+        const u64 st = (e >> 32) & 0x7fffffff;
+        const double bound = (double)(e & 0xffffffffull) - 1;
+        const u64 sub = p < 0.0 ? 0 : (p > bound ? (u64)bound : (u64)p);
+        r = ix.l1[st + sub];
+        p = fma(r.beta, __ull2double_rn(key), r.alpha);
+        e = r.err;
+    }
+    const double bound = (double)ix.sa_num - 1.0;
+    pred[i] = p < 0.0 ? 0 : (p > bound ? (u64)bound : (u64)p);
+    err[i] = e;
+}
+
+extern "C" int meme_rmi_lookup(meme_index_t *ix, const uint64_t *keys, int64_t n, uint64_t *pred, uint64_t *err)
+{
+    if (!ix || n < 0 || (n && (!keys || !pred || !err))) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    if (n == 0) return MEME_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    u64 *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, (size_t)n * 8 * 3));
+    CUDA_TRY(cudaMemcpyAsync(d, keys, (size_t)n * 8, cudaMemcpyHostToDevice, ix->stream));
+    k_rmi_lookup<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(ix->v, d, n, d + n, d + 2 * n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pred, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(err, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { meme_set_error("meme_rmi_lookup: %s", cudaGetErrorString(e)); return MEME_E_CUDA; }
+    return MEME_OK;
+}
+
 // The index replicated on `ndev` devices (reads shard across GPUs, the index does not: SURVEY.md section 8e).  The
 // devices are loaded concurrently, one host thread each; out receives ndev handles (all or none).
 extern "C" int meme_index_load_devices(const char *prefix, int mode, const int *devices, int ndev, meme_index_t **out)

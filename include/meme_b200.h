@@ -97,6 +97,11 @@ uint64_t meme_index_device_bytes(const meme_index_t *ix);
 /* Use an existing CUDA stream (a cudaStream_t passed as void*); NULL restores the handle's own. */
 int      meme_index_set_stream(meme_index_t *ix, void *cuda_stream);
 
+/* P-RMI inference for a batch of 64-bit keys (first base in the most significant bits), as learned_index_lookup
+ * (src/LearnedIndex_seeding.cpp:L186-210) computes it: pred = clamped position estimate, err = the error word of the
+ * model that answered (window below = (err>>32)&0x3fffffff, above = err&0x7fffffff, L2145-2146). */
+int meme_rmi_lookup(meme_index_t *ix, const uint64_t *keys, int64_t n, uint64_t *pred, uint64_t *err);
+
 /* Copies index arrays back (tests): any pointer may be NULL.  keys/pos/isa have sa_num entries. */
 int meme_index_download(const meme_index_t *ix, uint64_t *keys, uint64_t *pos, uint64_t *isa);
 
@@ -125,9 +130,9 @@ int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);          /* syn
 int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out);        /* synchronises               */
 /* Totals of the last run without copying the lists (synchronises). */
 int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits);
-/* Device-side work counters of the last run: [0] searches, [1] SA block probes, [2] k-ary rounds,
- * [3] extension rounds, [4] reads flagged overflow, [5] kernel launches since the handle was created,
- * [6] reads re-run by the wide fallback launch, [7] lanes per read of the main launch. */
+/* Work counters of the last run: [0] searches, [1] contiguous SA block probes, [2] k-ary narrowing rounds,
+ * [3] extension rounds, [4] packed-reference rounds, [5] kernel launches since the handle was created, [6] reseed tasks,
+ * [7] memory round trips.  [0..4] and [7] are counted only when MEME_SEED_STATS=1 (they cost registers in the hot loop). */
 int meme_seed_counters(meme_index_t *ix, uint64_t counters[8]);
 /* CUDA-event durations (ms) of the last meme_seed_run on its stream: [0] the seeding kernel,
  * [1] offset scans, [2] the hit-materialisation kernel. */

@@ -78,6 +78,16 @@ class OracleIndex:
             self.lib.oracle_index_free(self.h)
             self.h = None
 
+    def rmi_lookup(self, keys: np.ndarray):
+        """learned_index_lookup (src/LearnedIndex_seeding.cpp:L186-210) for a batch of keys: (prediction, error word)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        pred = np.zeros(len(keys), np.uint64)
+        err = np.zeros(len(keys), np.uint64)
+        self.lib.oracle_rmi_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        self.lib.oracle_rmi_lookup.restype = None
+        self.lib.oracle_rmi_lookup(self.h, keys.ctypes.data, len(keys), pred.ctypes.data, err.ctypes.data)
+        return pred, err
+
     def seed(self, codes: np.ndarray, offsets: np.ndarray, opt: SeedOpt | None = None) -> dict:
         """Returns dict(smems=record array, smem_off, hit_off, hits, counters)."""
         opt = opt or default_opt()

@@ -140,6 +140,14 @@ fail:
 
 uint64_t oracle_index_sa_num(const oracle_index_t *x) { return x->sa_num; }
 
+static uint64_t rmi_lookup_raw(const oracle_index_t *x, uint64_t key, uint64_t *err);
+
+/* learned_index_lookup for a batch of keys (tests pin the device inference against it) */
+void oracle_rmi_lookup(const oracle_index_t *x, const uint64_t *keys, int64_t n, uint64_t *pred, uint64_t *err)
+{
+    for (int64_t i = 0; i < n; i++) pred[i] = rmi_lookup_raw(x, keys[i], &err[i]);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     const oracle_index_t *ix;
@@ -166,6 +174,26 @@ static inline size_t fclamp(double v, double bound)
 }
 
 /* learned_index_lookup, L186-210 */
+static uint64_t rmi_lookup_raw(const oracle_index_t *x, uint64_t key, uint64_t *err)
+{
+    size_t m = (size_t)(key >> x->bit_shift);
+    double a, b;
+    memcpy(&a, x->l2 + m * 24, 8);
+    memcpy(&b, x->l2 + m * 24 + 8, 8);
+    memcpy(err, x->l2 + m * 24 + 16, 8);
+    double p = fma(b, (double)key, a);
+    if (*err >> 63) {
+        size_t st = (size_t)((*err >> 32) & 0x7fffffff);
+        double num = (double)(*err & 0xffffffffu);
+        m = st + fclamp(p, num - 1);
+        memcpy(&a, x->l1 + m * 24, 8);
+        memcpy(&b, x->l1 + m * 24 + 8, 8);
+        memcpy(err, x->l1 + m * 24 + 16, 8);
+        p = fma(b, (double)key, a);
+    }
+    return fclamp(p, (double)x->sa_num - 1.0);
+}
+
 static uint64_t rmi_lookup(rd_t *r, uint64_t key, uint64_t *err)
 {
     const oracle_index_t *x = r->ix;

@@ -261,3 +261,42 @@ print("OK")
         e.pop("MEME_FORCE_WIDE")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=900)
     assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-2000:]
+
+
+def test_rmi_inference_matches_reference_formula(oracle, pkg, golden_index, mid_index):
+    """A4 pinned: the device's P-RMI prediction and error word equal learned_index_lookup
+    (src/LearnedIndex_seeding.cpp:L186-210) for every key -- keys of real suffixes, random keys, the extremes.
+    (Seeding results are canonical whatever the prediction, so only a direct comparison can see a wrong model.)"""
+    from bwa_meme_b200 import capi
+    rng = np.random.default_rng(3)
+    for prefix in (golden_index, mid_index[0]):
+        ix = capi.MemeIndex(prefix, mode=3)
+        oix = oracle.OracleIndex(prefix, 3)
+        text = np.fromfile(prefix + ".0123", dtype=np.uint8)
+        starts = rng.integers(0, len(text) - 40, size=20000)
+        k = np.zeros(len(starts), np.uint64)
+        for r in range(32):                                   # first base in the most significant bits (Tokenization)
+            k |= text[starts + r].astype(np.uint64) << np.uint64(62 - 2 * r)
+        keys = np.concatenate([k, rng.integers(0, 1 << 63, size=20000, dtype=np.uint64) * np.uint64(2),
+                               np.array([0, 1, (1 << 64) - 1, (1 << 63), (1 << 63) - 1], dtype=np.uint64)])
+        gp, ge_ = ix.rmi_lookup(keys)
+        wp, we = oix.rmi_lookup(keys)
+        ix.close(); oix.close()
+        assert (gp == wp).all() and (ge_ == we).all()
+
+
+def test_probe_counts_stay_near_one_block_per_search(oracle, pkg, golden_index, golden_reads, monkeypatch):
+    """A3/A4 guarded from the other side: with a well-trained index a search needs about one 8-entry block probe and
+    hardly any k-ary narrowing round.  A wrong RMI key or prediction would not change the (canonical) results, but it
+    would show here as extra probes."""
+    from bwa_meme_b200 import capi
+    monkeypatch.setenv("MEME_SEED_STATS", "1")
+    codes, offs = golden_reads[150]
+    n = len(offs) - 1
+    ix = capi.MemeIndex(golden_index, mode=3)
+    ix.seed(codes, offs, capi.default_seed_opt(rounds=1))      # round 1: every search starts from the RMI
+    c = ix.seed_counters()
+    ix.close()
+    assert c["searches"] > 5 * n
+    assert c["block_probes"] <= 1.15 * c["searches"], c
+    assert c["kary_rounds"] <= 0.05 * c["searches"], c
