@@ -299,16 +299,28 @@ def main_ours(a):
     del os.environ["MEME_SEED_STATS"]
     for _ in range(a.warmup):
         ix.seed_run(opt)
+        if world > 1:                           # the record gather is part of a step: warm it up too (NCCL channels)
+            parts = mdist.device_results(ix, n, device)
+            gathered, _ = mdist.gather_records(parts, 0, device)
+            del parts, gathered
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ix.seed_counters()["launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seed_ms = []
+    gather_bytes = 0
     ev0.record()
     for _ in range(a.steps):
         ix.seed_run(opt)
         seed_ms.append(ix.seed_last_ms())
+        if world > 1:
+            # the one exchange step of the path, INSIDE the timed region: every rank's record lists, device-resident,
+            # travel over NCCL (NVLink) into one buffer on rank 0 -- exact sizes, no padding, no host bounce
+            parts = mdist.device_results(ix, n, device)
+            gathered, moved = mdist.gather_records(parts, 0, device)
+            gather_bytes = moved
+            del parts, gathered
     ev1.record()
     sync_all()
     dev_ms = ev0.elapsed_time(ev1)
@@ -359,8 +371,10 @@ def main_ours(a):
                 "how": "MEME_FORCE_WIDE=1: 5-byte positions / inverse SA and the WIDE kernel instantiations on the same index and reads"}
         wix.close()
 
-    # ---- final hit gather (the one collective of the path): per-rank totals + checksums over NCCL ----
+    # ---- totals per rank (counts only; the record gather itself ran inside the timed region above) ----
     summary = mdist.gather_summary(ix, n, world, device)
+    summary["record_gather"] = {"inside_timed_region": world > 1, "bytes_into_rank0_per_step": int(gather_bytes) if rank == 0 else None,
+                                "how": "all_gather of sizes + NCCL send/recv of device-resident lists into one buffer on rank 0"}
 
     # ---- max over ranks ----
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)

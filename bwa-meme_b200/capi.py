@@ -22,7 +22,7 @@ RESULT_FIELDS = ("score", "tle", "gtle", "qle", "gscore", "max_off")
 EXPORTS = [
     "meme_index_load", "meme_rmi_lookup", "meme_index_load_devices", "meme_seed_batch_multi", "meme_index_from_host", "meme_index_free", "meme_index_sa_num", "meme_index_device_bytes",
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
-    "meme_seed_warmup", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
+    "meme_seed_warmup", "meme_seed_copy_device", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_last_error", "meme_device_count", "meme_version",
@@ -205,6 +205,11 @@ class MemeIndex:
         if not copy:
             return {"n_reads": int(res.n_reads), "n_smems": int(res.n_smems), "n_hits": int(res.n_hits)}
         return self._wrap(res)
+
+    def seed_copy_device(self, d_smems: int, d_hits: int, d_smem_off: int, d_hit_off: int):
+        vp = C.c_void_p
+        lib().meme_seed_copy_device.argtypes = [vp, vp, vp, vp, vp]
+        _check(lib().meme_seed_copy_device(self.h, vp(d_smems), vp(d_hits), vp(d_smem_off), vp(d_hit_off)), "meme_seed_copy_device")
 
     def rmi_lookup(self, keys: np.ndarray):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

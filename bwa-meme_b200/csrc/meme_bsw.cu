@@ -47,7 +47,7 @@ struct meme_bsw {
     void *d_sort_tmp; size_t cap_sort_tmp;
     int64_t is_off[BSW_IS_NCLASS + 1]; int64_t n_is, n_ovf;
     int32_t *d_wused; size_t cap_wused;
-    int match_a;
+    int match_a; int attr_set;
     u64 *d_ctrl; u64 *h_ctrl;
     int64_t n_pairs, n_ref, n_qer;
     u64 launches;
@@ -629,10 +629,9 @@ extern "C" int meme_bsw_run_ext(meme_bsw_t *b, int32_t w, int32_t tries, int32_t
     // ---- inter-sequence classes ----
     {
         BswIsConst P = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->end_bonus, opt->a, opt->b};
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!b->attr_set) {                     // per device: function attributes belong to the device's context
             CUDA_TRY(cudaFuncSetAttribute(k_bsw_is, cudaFuncAttributeMaxDynamicSharedMemorySize, BSW_IS_WORDS[BSW_IS_NCLASS - 1] * BSW_IS_THREADS * 5));
-            attr_set = true;
+            b->attr_set = 1;
         }
         for (int c = BSW_IS_NCLASS - 1; c >= 0; c--) {
             const int64_t lo = b->is_off[c + 1], cn = b->is_off[c] - lo;

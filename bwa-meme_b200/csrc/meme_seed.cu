@@ -378,6 +378,21 @@ extern "C" int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_h
     return MEME_OK;
 }
 
+// Device-to-device copies of the lists of the last meme_seed_run (any pointer may be NULL): for callers that keep the
+// results in HBM, e.g. the NCCL gather of the multi-process bench.  Asynchronous on the handle's stream.
+extern "C" int meme_seed_copy_device(meme_index_t *ix, void *d_smems, void *d_hits, void *d_smem_off, void *d_hit_off)
+{
+    if (!ix || !ix->ran || ix->piped) { meme_set_error("no completed meme_seed_run on this handle"); return MEME_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const int64_t n = ix->n_reads, ns = n ? (int64_t)ix->h_ctrl[32] : 0, nh = n ? (int64_t)ix->h_ctrl[33] : 0;
+    cudaStream_t st = ix->stream;
+    if (d_smems && ns) CUDA_TRY(cudaMemcpyAsync(d_smems, ix->d_smems, (size_t)ns * sizeof(meme_smem_t), cudaMemcpyDeviceToDevice, st));
+    if (d_hits && nh) CUDA_TRY(cudaMemcpyAsync(d_hits, ix->d_hits, (size_t)nh * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_smem_off && n) CUDA_TRY(cudaMemcpyAsync(d_smem_off, ix->d_smem_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_hit_off && n) CUDA_TRY(cudaMemcpyAsync(d_hit_off, ix->d_hit_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    return MEME_OK;
+}
+
 extern "C" int meme_seed_last_ms(meme_index_t *ix, float ms[3])
 {
     if (!ix || !ms || !ix->ev_ready) { meme_set_error("no timed seeding run"); return MEME_E_ARG; }

@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             case P_D1_R:
             c_d1_r:
                 if (KIND != 1) { state = P_TASK; break; }
+                // progress guard (not in the reference, which loops forever here when the text ends with its longest
+                // T run and a match runs into the text end: DESIGN.md section 2): the zig-zag must move forward
+                if (pivot + lev <= sp) { pivot = L; goto d1_loop; }
                 sp = pivot + lev;
                 pivot = sp;
                 goto d1_zz;
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(TPR_THREADS, MINB) k_flat(IndexView ix, Args A
             case P_D2_R:
             c_d2_r:
                 if (KIND != 2) { state = P_TASK; break; }
+                if (pivot + lev <= sp) goto c_task;             // progress guard, as in the zig-zag of T1
                 sp = pivot + lev;
                 pivot = sp;
                 goto d2_loop;

@@ -361,6 +361,7 @@ __device__ __forceinline__ void ctl_pass(const IndexView &ix, const Args &A, uns
                 GO(L_AUTO_START);
             case L_C_D1_R:
                 if (KIND != 1) GO(L_C_TASK);
+                if (pivot + lev <= sp) { pivot = L_; GO(L_D1_LOOP); }   // progress guard (see meme_seed_flat.cuh)
                 sp = pivot + lev;
                 pivot = sp;
                 GO(L_D1_ZZ);
@@ -389,6 +390,7 @@ __device__ __forceinline__ void ctl_pass(const IndexView &ix, const Args &A, uns
                 GO(L_AUTO_START);
             case L_C_D2_R:
                 if (KIND != 2) GO(L_C_TASK);
+                if (pivot + lev <= sp) GO(L_C_TASK);                    // progress guard
                 sp = pivot + lev;
                 pivot = sp;
                 GO(L_D2_LOOP);

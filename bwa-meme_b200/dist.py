@@ -49,42 +49,78 @@ def gather_summary(ix, n_reads: int, world: int, device) -> dict:
             "per_rank": m.tolist()}
 
 
-def _gather_var(t: torch.Tensor, root: int, device) -> list[torch.Tensor] | None:
-    """Gather 1-D tensors of different lengths to `root` (all_gather of sizes + padded gather)."""
+def _gather_exact(t: torch.Tensor, root: int, device) -> tuple[torch.Tensor | None, np.ndarray]:
+    """Gather 1-D tensors of different lengths to `root` without padding: all_gather of the sizes, then every peer
+    sends its tensor straight into its slice of ONE buffer on the root (NCCL send/recv over NVLink on the GPU box, gloo
+    in the CPU tests).  Returns (concatenation on root | None, sizes per rank)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = _all_gather_i64([int(t.numel())], device)[:, 0]
-    mx = int(sizes.max())
-    pad = torch.zeros(mx, dtype=t.dtype, device=device)
-    pad[:t.numel()] = t.to(device)
-    bufs = [torch.empty(mx, dtype=t.dtype, device=device) for _ in range(world)] if rank == root else None
-    dist.gather(pad, bufs, dst=root)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    t = t.to(device)
+    if rank == root:
+        out = torch.empty(int(starts[-1]), dtype=t.dtype, device=device)
+        out[int(starts[root]):int(starts[root + 1])] = t
+        ops = [dist.P2POp(dist.irecv, out[int(starts[r]):int(starts[r + 1])], r) for r in range(world) if r != root and sizes[r] > 0]
+    else:
+        out = None
+        ops = [dist.P2POp(dist.isend, t, root)] if t.numel() > 0 else []
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out, sizes
+
+
+def gather_records(parts: dict, root: int = 0, device="cpu") -> tuple[dict | None, int]:
+    """The final hit gather: every rank's record arrays -- `smems` (raw bytes of the 24-byte records),
+    `hits` (int64), `smem_off`, `hit_off` (int64, n+1 entries) as 1-D torch tensors ALREADY ON `device` -- concatenated on
+    `root` in rank order = read order, offsets rebased there.  No host bounce and no padding: device-resident tensors
+    travel device to device.  Returns (dict of tensors on root | None, bytes this rank sent or received)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return parts, 0
+    rank = dist.get_rank()
+    moved = 0
+    out = {}
+    sizes = {}
+    for k in ("smems", "hits", "smem_off", "hit_off"):
+        out[k], sizes[k] = _gather_exact(parts[k], root, device)
+        esz = parts[k].element_size()
+        moved += int((sizes[k].sum() - sizes[k][root]) * esz) if rank == root else int(parts[k].numel() * esz)
     if rank != root:
-        return None
-    return [bufs[r][:int(sizes[r])] for r in range(world)]
+        return None, moved
+    # offsets: drop the leading 0 of every shard but the first, add the running totals
+    world = dist.get_world_size()
+    for k in ("smem_off", "hit_off"):
+        st = np.concatenate([[0], np.cumsum(sizes[k])])
+        pieces, base = [], 0
+        for r in range(world):
+            seg = out[k][int(st[r]):int(st[r + 1])]
+            pieces.append(seg + base if r == 0 else seg[1:] + base)
+            base = base + int(seg[-1]) if seg.numel() else base
+        out[k] = torch.cat(pieces)
+    return out, moved
+
+
+def device_results(ix, n_reads: int, device) -> dict:
+    """The lists of the last meme_seed_run as torch tensors on `device` (device-to-device copies, no host bounce)."""
+    ns, nh = ix.seed_totals()
+    parts = {"smems": torch.empty(ns * 24, dtype=torch.uint8, device=device), "hits": torch.empty(nh, dtype=torch.int64, device=device),
+             "smem_off": torch.empty(n_reads + 1, dtype=torch.int64, device=device),
+             "hit_off": torch.empty(n_reads + 1, dtype=torch.int64, device=device)}
+    ix.seed_copy_device(parts["smems"].data_ptr(), parts["hits"].data_ptr(), parts["smem_off"].data_ptr(), parts["hit_off"].data_ptr())
+    return parts
 
 
 def gather_seed_results(res: dict, root: int = 0, device="cpu") -> dict | None:
-    """Concatenate every rank's seeding result (the dict MemeIndex.seed returns, for that rank's
-    contiguous shard) on `root`, in rank order = read order.  Returns None on the other ranks.
-    Record layouts travel as raw bytes; offsets are rebased on the root."""
+    """Host-array form of gather_records (the dict MemeIndex.seed returns, for that rank's contiguous shard): used by
+    the CPU tests (gloo).  Returns None on the other ranks."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return res
     from . import capi
-    parts = {}
-    parts["smems"] = _gather_var(torch.from_numpy(res["smems"].view(np.uint8).reshape(-1).copy()), root, device)
-    parts["hits"] = _gather_var(torch.from_numpy(res["hits"].view(np.int64).copy()), root, device)
-    parts["smem_off"] = _gather_var(torch.from_numpy(res["smem_off"].copy()), root, device)
-    parts["hit_off"] = _gather_var(torch.from_numpy(res["hit_off"].copy()), root, device)
-    if dist.get_rank() != root:
+    parts = {"smems": torch.from_numpy(res["smems"].view(np.uint8).reshape(-1).copy()),
+             "hits": torch.from_numpy(res["hits"].view(np.int64).copy()),
+             "smem_off": torch.from_numpy(res["smem_off"].copy()), "hit_off": torch.from_numpy(res["hit_off"].copy())}
+    out, _ = gather_records(parts, root, device)
+    if out is None:
         return None
-    smems = np.concatenate([p.cpu().numpy().view(capi.SMEM_DTYPE) for p in parts["smems"]])
-    hits = np.concatenate([p.cpu().numpy().view(np.uint64) for p in parts["hits"]])
-    so, ho = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)]
-    sb = hb = 0
-    for a, b in zip(parts["smem_off"], parts["hit_off"]):
-        a, b = a.cpu().numpy(), b.cpu().numpy()
-        so.append(a[1:] + sb)
-        ho.append(b[1:] + hb)
-        sb += int(a[-1])
-        hb += int(b[-1])
-    return {"smems": smems, "hits": hits, "smem_off": np.concatenate(so), "hit_off": np.concatenate(ho)}
+    return {"smems": out["smems"].cpu().numpy().view(capi.SMEM_DTYPE), "hits": out["hits"].cpu().numpy().view(np.uint64),
+            "smem_off": out["smem_off"].cpu().numpy(), "hit_off": out["hit_off"].cpu().numpy()}

@@ -29,10 +29,6 @@ def make_genome(length: int, seed: int = 20261017, n_families: int = 5, copies: 
             mut = rng.random(rep_len) < divergence
             cp[mut] = (cp[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
             g[pos:pos + rep_len] = cp
-    # keep the text ends free of homopolymer corner cases (first base not A/T, last not A/T):
-    # the fwd+RC text then neither starts nor ends with a T/A run (see DESIGN.md "text end")
-    g[0] = 1
-    g[-1] = 2
     return g
 
 
@@ -157,8 +153,6 @@ def make_genome_large(length: int, seed: int = 20261017, n_families: int = 300, 
             mut = rng.random(rep_len) < div
             cp[mut] = (cp[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
             g[p:p + rep_len] = cp
-    g[0] = 1
-    g[-1] = 2
     return g
 
 
@@ -234,3 +228,50 @@ def make_pairs_torch(genome_t, n_pairs: int, read_len: int = 150, seed: int = 11
         r1[a:b] = torch.where(flip[:, None], right, left)
         r2[a:b] = torch.where(flip[:, None], left, right)
     return r1, r2
+
+
+def make_genome_textend(length: int = 30000, seed: int = 301, start_a_run: int = 6, end_t_run: int = 5) -> np.ndarray:
+    """Fixture genome whose fwd+RC text has homopolymer ends: the forward strand starts with `start_a_run` A's (so the
+    text ENDS with that many T's) and ends with `end_t_run` T's (the forward/reverse junction sits in a T|A run)."""
+    g = make_genome(length, seed=seed, n_families=3, copies=12, rep_len=400)
+    g[:start_a_run] = 0
+    g[start_a_run] = 1
+    g[-end_t_run:] = 3
+    g[-end_t_run - 1] = 2
+    return g
+
+
+def make_textend_reads(genome: np.ndarray, pad: int, start_a_run: int = 6, read_len: int = 150, seed: int = 1):
+    """Reads that run into the END of the fwd+RC text (the last k text bases followed by a tail: random bases, or a run
+    of T's shorter than / equal to / longer than the index's padding run `pad`, or T's to the read end), both strands;
+    reads spanning the forward/reverse junction; and reads whose tail is a long T (or A) run elsewhere.
+    Returns (codes, offsets)."""
+    rng = np.random.default_rng(seed)
+    text = np.concatenate([genome, (3 - genome[::-1]).astype(np.uint8)])
+    n = len(text)
+    reads = []
+
+    def add(r):
+        r = np.asarray(r, dtype=np.uint8)[:read_len]
+        reads.append(r)
+        reads.append(revcomp(r))
+
+    for k in list(range(1, 40)) + [50, 64, 65, 96, 100, 128, 140, 149]:
+        pre, m = text[n - k:], read_len - k
+        for c in (0, 1, pad - start_a_run - 1, pad - start_a_run, pad - 1, pad, pad + 1, pad + 5, m):
+            c = max(0, min(m, c))
+            rest = m - c
+            tail = [np.full(c, 3, np.uint8)]
+            if rest > 0:
+                tail.append(rng.integers(0, 3, 1).astype(np.uint8))          # the run ends with a non-T base
+                tail.append(rng.integers(0, 4, rest - 1).astype(np.uint8))
+            add(np.concatenate([pre] + tail))
+    L = len(genome)
+    for k in (20, 75, 130):
+        add(text[L - k:L - k + read_len])
+    for _ in range(40):
+        st, k = int(rng.integers(100, L - 200)), int(rng.integers(20, 140))
+        add(np.concatenate([genome[st:st + k], np.full(read_len - k, 3, np.uint8)]))
+    add(np.full(read_len, 3, np.uint8))
+    codes = np.concatenate(reads)
+    return codes, np.arange(len(reads) + 1, dtype=np.int64) * read_len

@@ -128,6 +128,9 @@ int meme_seed_warmup(meme_index_t *ix, int64_t n_reads, int32_t read_len);
 int meme_seed_upload(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n_reads);
 int meme_seed_run(meme_index_t *ix, const meme_seed_opt_t *opt);          /* synchronises between the task kinds; the final gather is asynchronous */
 int meme_seed_download(meme_index_t *ix, meme_seed_result_t *out);        /* synchronises               */
+/* Device-to-device copies of the lists of the last meme_seed_run (any pointer may be NULL; sizes from
+ * meme_seed_totals): for callers that keep the results in HBM (the NCCL gather of the multi-process bench). */
+int meme_seed_copy_device(meme_index_t *ix, void *d_smems, void *d_hits, void *d_smem_off, void *d_hit_off);
 /* Totals of the last run without copying the lists (synchronises). */
 int meme_seed_totals(meme_index_t *ix, int64_t *n_smems, int64_t *n_hits);
 /* Work counters of the last run: [0] searches, [1] contiguous SA block probes, [2] k-ary narrowing rounds,

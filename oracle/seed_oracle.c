@@ -491,6 +491,10 @@ static int seed_step1(rd_t *r, int pivot)
             pivot = pivot - l + 1;
             if (L - pivot < r->min_seed_len) break;
             int rr = do_search(r, pivot, 1, 1);
+            /* PROGRESS GUARD (not in the reference): when the text ends with its longest T run, a match into the text
+             * end can make the right search shorter than the left one and the reference loops here forever
+             * (tests/test_text_end_guard.py); the zig-zag of this segment ends instead. */
+            if (pivot + rr <= sp) break;
             sp = pivot + rr;
             pivot = sp;
         }
@@ -519,6 +523,7 @@ static void seed_onepos(rd_t *r, int pivot)
             pivot = pivot - l + 1;
             if (next - pivot < r->min_seed_len) break;
             int rr = do_search(r, pivot, 1, 1);
+            if (pivot + rr <= sp) break;            /* progress guard, as in seed_step1 */
             sp = pivot + rr;
             pivot = sp;
         }

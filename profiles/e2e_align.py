@@ -46,6 +46,8 @@ if os.environ.get("ARMS"):
 nreads = N * (2 if PE else 1)
 for name, exe, env in arms:
     e = dict(os.environ); e.update(env); e["MEME_B200_LIB"] = lib
+    if os.environ.get("DEVICES") and name != "reference_cpu":
+        e["MEME_B200_DEVICES"] = os.environ["DEVICES"]      # reads and extension pairs shard across these GPUs
     if name == "gpu_seed_bsw" and os.environ.get("DUMP"):
         e["MEME_B200_DUMP_PAIRS"] = os.environ["DUMP"]
     t0 = time.time()

@@ -71,6 +71,23 @@ def mid_index(pkg, tmp_path_factory):
     return prefix, g
 
 
+@pytest.fixture(scope="session")
+def textend_case(pkg, tmp_path_factory):
+    """Genome whose fwd+RC text ends in a T run, indexed by our builder, and the reads of tests/golden/smem_textend.txt
+    (reads running into the text end / across the forward-reverse junction / with long T tails)."""
+    import json
+    from bwa_meme_b200 import synth, index_build
+    meta = json.load(open(os.path.join(GOLDEN, "textend.json")))
+    g = synth.make_genome_textend(meta["length"], meta["seed"], meta["start_a_run"], meta["end_t_run"])
+    d = tmp_path_factory.mktemp("textend_index")
+    prefix = str(d / "textend.fa")
+    st = index_build.build_index(prefix, g, bits=meta["bits"])
+    assert st["pad"] == meta["pad"]
+    codes, offs = synth.make_textend_reads(g, meta["pad"], meta["start_a_run"], seed=meta["reads_seed"])
+    assert len(offs) - 1 == meta["n_reads"]
+    return prefix, codes, offs
+
+
 def has_gpu():
     try:
         import torch

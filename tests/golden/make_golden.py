@@ -10,6 +10,9 @@ The fixtures are small and committed; the GPU box only reads them.
   bsw_*.npy             {score,tle,gtle,qle,gscore,max_off} of BandedPairWiseSW::scalarBandedSWAWrapper
   mem7.sam              `bwa-meme mem -7` SAM (minus @PG) for the len150 reads  (end-to-end reference)
   pe_reads.npy, mem7_pe.sam   250 read pairs (codes) and the reference's paired-end SAM for them
+  smem_textend.txt      SMEM dump for reads that run into the END of the fwd+RC text of a genome with homopolymer ends
+                        (synth.make_genome_textend / make_textend_reads): compare_read_and_ref_binary's text-end branch,
+                        src/LearnedIndex_seeding.cpp:L266-273
 """
 import hashlib
 import json
@@ -37,6 +40,31 @@ BSW_SETS = [(0, 400, 150, 110, 120), (1, 300, 60, 200, 40), (2, 200, 300, 120, 2
 
 def sha(path):
     return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+TEXTEND = {"length": 30000, "seed": 301, "start_a_run": 6, "end_t_run": 5, "bits": 16, "reads_seed": 1}
+
+
+def make_textend(work):
+    """Reads crossing the end of the text (and the forward/reverse junction) of a genome whose text ends in a T run."""
+    g = synth.make_genome_textend(TEXTEND["length"], TEXTEND["seed"], TEXTEND["start_a_run"], TEXTEND["end_t_run"])
+    fa = os.path.join(work, "textend.fa")
+    synth.write_fasta(fa, g)
+    subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "index", "-a", "meme", "-t", "4", fa], check=True, capture_output=True,
+                   timeout=300)
+    mine = os.path.join(work, "textend_mine.fa")
+    st = index_build.build_index(mine, g, bits=TEXTEND["bits"])
+    for ext in ("_L0_PARAMETERS", "_L1_PARAMETERS", "_L2_PARAMETERS"):
+        open(fa + ".suffixarray_uint64" + ext, "wb").write(open(mine + ".suffixarray_uint64" + ext, "rb").read())
+    codes, offs = synth.make_textend_reads(g, st["pad"], TEXTEND["start_a_run"], seed=TEXTEND["reads_seed"])
+    fq = os.path.join(work, "textend.fq")
+    synth.write_fastq(fq, codes, offs)
+    out = os.path.join(HERE, "smem_textend.txt")
+    with open(out, "w") as fo:
+        # (a hard limit: with longer homopolymer ends the reference's own search does not terminate, DESIGN.md section 2)
+        subprocess.run(["timeout", "-s", "KILL", "120", os.path.join(REF, f"learned_seeding_mode3.{ISA}"), fa, fq, "512", "1", "4"],
+                       stdout=fo, stderr=subprocess.DEVNULL, check=True)
+    json.dump({**TEXTEND, "pad": int(st["pad"]), "n_reads": int(len(offs) - 1)}, open(os.path.join(HERE, "textend.json"), "w"), indent=1)
 
 
 def main():
@@ -95,6 +123,7 @@ def main():
     sam = subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "mem", "-7", "-t", "1", fa, os.path.join(work, "pe_1.fq"),
                           os.path.join(work, "pe_2.fq")], capture_output=True, text=True, check=True).stdout
     open(os.path.join(HERE, "mem7_pe.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
+    make_textend(work)
     shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
     for seed, n, mq, mx, h0m in BSW_SETS:
         pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)

@@ -99,3 +99,24 @@ def test_high_copy_repeats_sampled_hits_sam_identical(pkg, tmp_path):
     r = ix.seed(codes, offs)
     ix.close()
     assert int(r["smems"]["hitcount"].max()) > 500
+
+
+def test_two_gpus_sam_identical(pkg, golden_index, tmp_path):
+    """Reads (pair-aligned) and extension pairs shard across two GPUs through the C ABI (meme_index_load_devices,
+    meme_seed_batch_multi, segments dealt to one kernel-B handle per device): SAM must not depend on the GPU count."""
+    import torch
+    from bwa_meme_b200 import synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = _binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/bwa-meme-b200_* not built (needs the reference sources)")
+    pe = np.load(os.path.join(GOLDEN, "pe_reads.npy"))
+    n = pe.shape[1] // 150
+    offs = np.arange(n + 1, dtype=np.int64) * 150
+    f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+    synth.write_fastq(f1, pe[0], offs, prefix="p")
+    synth.write_fastq(f2, pe[1], offs, prefix="p")
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1", "MEME_B200_DEVICES": "0,1"})
+    assert "resident on 2 GPU(s)" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()

@@ -26,8 +26,8 @@ def _cuda_include():
     return None
 
 
-@pytest.fixture(scope="module", params=["grp", "flat"])
-def sim(pkg, request):
+def make_sim(which: str):
+    """Build (if stale) and bind the host simulation of one kernel: "flat" or "grp"."""
     inc = _cuda_include()
     if not shutil.which("g++") or not inc:
         pytest.skip("g++ or the CUDA headers are missing")
@@ -42,7 +42,7 @@ def sim(pkg, request):
                         os.path.join(SIM_DIR, "flat_host.cpp")], check=True)
     L = C.CDLL(lib)
     L.flat_sim_seed.restype = C.c_int
-    impl = 1 if request.param == "grp" else 0
+    impl = 1 if which == "grp" else 0
     from bwa_meme_b200 import capi
 
     def seed(prefix, mode, codes, offs, opt=None, wide=False):
@@ -65,6 +65,11 @@ def sim(pkg, request):
         return r
 
     return seed
+
+
+@pytest.fixture(scope="module", params=["grp", "flat"])
+def sim(pkg, request):
+    return make_sim(request.param)
 
 
 def _canon(O, r, n):
@@ -140,3 +145,14 @@ def test_max_occ_sampling_on_cpu(sim, pkg, mid_index):
             sh = samp["hits"][samp["hit_off"][r] + samp["smems"]["hitbeg"][k]:][:len(idx)]
             assert sh.tolist() == fh[idx].tolist()
     assert saw_big
+
+
+def test_text_end_reads_on_cpu(oracle, sim, textend_case):
+    """The kernels' control code on reads that run into the end of the text (tests/golden/smem_textend.txt)."""
+    prefix, codes, offs = textend_case
+    n = len(offs) - 1
+    want = oracle.parse_ref_dump(os.path.join(GOLDEN, "smem_textend.txt"), n)
+    for mode in (3, 1):
+        got = _canon(oracle, sim(prefix, mode, codes, offs), n)
+        bad = [i for i in range(n) if got[i] != want[i]]
+        assert not bad, f"mode {mode}: {len(bad)} reads differ, first {bad[:5]}"

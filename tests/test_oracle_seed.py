@@ -81,3 +81,19 @@ def test_oracle_vs_live_reference(oracle, pkg, tmp_path):
     ix.close()
     got = oracle.canon_lines(r["smems"], r["smem_off"], r["hit_off"], r["hits"], n)
     assert got == want
+
+
+def test_oracle_matches_reference_at_the_text_end(oracle, textend_case):
+    """Reads that run into the end of the fwd+RC text (homopolymer T end), across the forward/reverse junction, and with
+    T tails longer than the index's padding run: compare_read_and_ref_binary's text-end branch
+    (src/LearnedIndex_seeding.cpp:L266-273).  Fixture = the reference's own dump (tests/golden/make_golden.py)."""
+    prefix, codes, offs = textend_case
+    n = len(offs) - 1
+    want = oracle.parse_ref_dump(os.path.join(GOLDEN, "smem_textend.txt"), n)
+    for mode in (3, 1):
+        oix = oracle.OracleIndex(prefix, mode)
+        got = oix.seed(codes, offs)
+        oix.close()
+        a = oracle.canon_lines(got["smems"], got["smem_off"], got["hit_off"], got["hits"], n)
+        bad = [i for i in range(n) if a[i] != want[i]]
+        assert not bad, f"mode {mode}: {len(bad)} reads differ, first {bad[:5]}"

@@ -300,3 +300,18 @@ def test_probe_counts_stay_near_one_block_per_search(oracle, pkg, golden_index, 
     assert c["searches"] > 5 * n
     assert c["block_probes"] <= 1.15 * c["searches"], c
     assert c["kary_rounds"] <= 0.05 * c["searches"], c
+
+
+def test_text_end_reads_match_reference_dump(oracle, pkg, textend_case):
+    """Reads running into the end of the fwd+RC text (T-run end), across the forward/reverse junction and with T tails
+    longer than the padding run: the CUDA kernel equals the reference's dump (src/LearnedIndex_seeding.cpp:L266-273)."""
+    from bwa_meme_b200 import capi
+    prefix, codes, offs = textend_case
+    n = len(offs) - 1
+    want = oracle.parse_ref_dump(os.path.join(GOLDEN, "smem_textend.txt"), n)
+    for mode in (3, 2, 1):
+        ix = capi.MemeIndex(prefix, mode=mode)
+        got = _canon(oracle, ix.seed(codes, offs), n)
+        ix.close()
+        bad = [i for i in range(n) if got[i] != want[i]]
+        assert not bad, f"mode {mode}: {len(bad)} reads differ, first {bad[:5]}"
