@@ -167,13 +167,8 @@ static int launch_seed(meme_index_t *ix, const Args &A)
         return lng ? launch_grp<KIND, false, true>(ix, A, stats) : launch_grp<KIND, false, false>(ix, A, stats);
     }
     const size_t sm = (size_t)TPR_THREADS * flat_sw<KIND>() * sizeof(u32);
-    if (ix->v.pos_wide) {
-        // 64-bit suffix-array indices: at 128 registers the reseed kernel spills 172 bytes; MEME_SEED_WIDE_MINB=1 compiles
-        // for one CTA per SM (255 registers, no spills, half the resident warps) -- profiles/r2 has the measurement
-        static int wminb = getenv("MEME_SEED_WIDE_MINB") ? atoi(getenv("MEME_SEED_WIDE_MINB")) : 2;
-        if (wminb == 1 && !stats) return launch_kernel(ix, A, k_flat<KIND, true, 1, true, false>, sm);
+    if (ix->v.pos_wide)
         return stats ? launch_kernel(ix, A, k_flat<KIND, true, 2, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, true, 2, true, false>, sm);
-    }
     return stats ? launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, true>, sm) : launch_kernel(ix, A, k_flat<KIND, false, FLAT_MINB, true, false>, sm);
 }
 

