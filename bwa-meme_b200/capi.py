@@ -24,7 +24,7 @@ EXPORTS = [
     "meme_index_set_stream", "meme_index_download", "meme_seed_batch", "meme_seed_upload", "meme_seed_run",
     "meme_seed_warmup", "meme_seed_copy_device", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
-    "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
+    "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -277,6 +277,24 @@ class MemeBsw:
         _check(lib().meme_bsw_batch_ext(self.h, out.ctypes.data, len(out), ref.ctypes.data, len(ref), qer.ctypes.data, len(qer), w,
                                         tries, int(prev_is_h0), C.byref(self.opt), wu.ctypes.data), "meme_bsw_batch_ext")
         return out, wu
+
+    def get_scores_text(self, ix: "MemeIndex", pairs: np.ndarray, qer: np.ndarray, w: int, tries: int = 1, prev_is_h0: bool = False):
+        """Reference by position: pairs carry (id, idr) = position in ix's text (id < 0: backwards); no reference upload."""
+        out = np.ascontiguousarray(pairs.copy())
+        qer = np.ascontiguousarray(qer, dtype=np.uint8)
+        vp = C.c_void_p
+        L = lib()
+        L.meme_bsw_attach_text.argtypes = [vp, vp]
+        _check(L.meme_bsw_attach_text(self.h, ix.h), "meme_bsw_attach_text")
+        _check(L.meme_bsw_set_match(self.h, self.opt.a), "meme_bsw_set_match")
+        pp = (vp * 1)(out.ctypes.data); np_ = (C.c_int64 * 1)(len(out)); pr = (vp * 1)(None); nr = (C.c_int64 * 1)(0)
+        pq = (vp * 1)(qer.ctypes.data); nq = (C.c_int64 * 1)(len(qer))
+        L.meme_bsw_upload_segments.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+        _check(L.meme_bsw_upload_segments(self.h, 1, pp, np_, pr, nr, pq, nq), "meme_bsw_upload_segments")
+        _check(L.meme_bsw_run_ext(self.h, w, tries, int(prev_is_h0), C.byref(self.opt)), "meme_bsw_run_ext")
+        _check(L.meme_bsw_download(self.h, out.ctypes.data), "meme_bsw_download")
+        _check(L.meme_bsw_attach_text(self.h, None), "meme_bsw_attach_text")
+        return out
 
     def upload(self, pairs, ref, qer):
         _check(lib().meme_bsw_set_match(self.h, self.opt.a), "meme_bsw_set_match")

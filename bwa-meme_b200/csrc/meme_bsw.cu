@@ -21,6 +21,8 @@
 // (L218-221) comes from two ballots.  All per-row control (z-drop, band, gscore) is warp-uniform.
 // Slots outside the current band keep their old contents, exactly like the reference's eh[] array.
 #include <vector>
+#include <algorithm>
+#include <climits>
 #include <cub/device/device_radix_sort.cuh>
 #include "meme_common.cuh"
 #include "meme_bsw_is.cuh"
@@ -48,6 +50,9 @@ struct meme_bsw {
     int64_t is_off[BSW_IS_NCLASS + 1]; int64_t n_is, n_ovf;
     int32_t *d_wused; size_t cap_wused;
     int match_a; int attr_set;
+    // reference by position: the 2-bit text of an index on the same device, and whether the uploaded batch uses it
+    const u64 *text_pac; u64 text_len; int text_mode;
+    int64_t *d_ovf_off; size_t cap_ovf_off;
     u64 *d_ctrl; u64 *h_ctrl;
     int64_t n_pairs, n_ref, n_qer;
     u64 launches;
@@ -368,8 +373,8 @@ static inline int bsw_is_class_of(int qlen)
 
 __global__ void __launch_bounds__(BSW_IS_THREADS)
 k_bsw_is(BswIsConst P, int words, int w, int tries, int prev_is_h0, meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order,
-         int64_t n_work, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ qer, int32_t *__restrict__ w_used,
-         u64 *__restrict__ ctrl)
+         int64_t n_work, const uint8_t *__restrict__ ref, const u64 *__restrict__ text_pac, const uint8_t *__restrict__ qer,
+         int32_t *__restrict__ w_used, u64 *__restrict__ ctrl)
 {
     extern __shared__ u32 bsw_rows[];
     u32 *row = bsw_rows + threadIdx.x;
@@ -381,7 +386,12 @@ k_bsw_is(BswIsConst P, int words, int w, int tries, int prev_is_h0, meme_seqpair
         meme_seqpair_t *p = pairs + pi;
         const int h0 = p->h0;
         BswIsOut o;
-        const int wu = bsw_is_retry(P, w, tries, prev_is_h0 ? h0 : -1, qer + p->idq, p->len2, ref + p->idr, p->len1, h0, row,
+        BswTarget T;
+        if (text_pac) {                         // (id, idr) = position in the 2-bit text, sign of id = direction
+            T.bytes = nullptr; T.pac = text_pac; T.dir = p->id < 0 ? -1 : +1;
+            T.pos = ((u64)((u32)p->id & 0x7fffffffu) << 32) | (u32)p->idr;
+        } else { T.bytes = ref + p->idr; T.pac = nullptr; T.pos = 0; T.dir = 1; }
+        const int wu = bsw_is_retry(P, w, tries, prev_is_h0 ? h0 : -1, qer + p->idq, p->len2, T, p->len1, h0, row,
                                     qrow, BSW_IS_THREADS, o, cells);
         p->score = o.score; p->tle = o.tle; p->gtle = o.gtle; p->qle = o.qle; p->gscore = o.gscore; p->max_off = o.max_off;
         if (w_used) w_used[pi] = wu;
@@ -434,7 +444,7 @@ extern "C" void meme_bsw_free(meme_bsw_t *b)
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     void *dev[] = {b->d_pairs, b->d_ref, b->d_qer, b->d_scratch, b->d_scratch_off, b->d_ctrl, b->d_order, b->d_keys, b->d_keys2,
-                   b->d_idx, b->d_idx2, b->d_sort_tmp, b->d_wused};
+                   b->d_idx, b->d_idx2, b->d_sort_tmp, b->d_wused, b->d_ovf_off};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_ctrl) cudaFreeHost(b->h_ctrl);
     cudaStreamDestroy(b->own_stream);
@@ -458,6 +468,37 @@ extern "C" int meme_bsw_set_match(meme_bsw_t *b, int32_t a)
     return MEME_OK;
 }
 
+// reference by position, overflow classes: their (few) pairs get their reference bytes written out, so that the
+// warp-per-pair and generic kernels run unchanged
+__global__ void k_bsw_materialise(meme_seqpair_t *__restrict__ pairs, const u32 *__restrict__ order, const int64_t *__restrict__ off,
+                                  int64_t n_work, const u64 *__restrict__ pac, uint8_t *__restrict__ ref)
+{
+    int64_t k = blockIdx.x;
+    if (k >= n_work) return;
+    meme_seqpair_t *p = pairs + order[k];
+    const int dir = p->id < 0 ? -1 : +1;
+    const u64 pos = ((u64)((u32)p->id & 0x7fffffffu) << 32) | (u32)p->idr;
+    uint8_t *dst = ref + off[k];
+    for (int i = threadIdx.x; i < p->len1; i += blockDim.x) {
+        const u64 q = dir > 0 ? pos + (u64)i : pos - (u64)i;
+        dst[i] = (uint8_t)((pac[q >> 5] >> (2 * (q & 31))) & 3);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { p->idr = (int32_t)off[k]; p->id = 0; }
+}
+
+// Lets the handle read pair references from the 2-bit text of `ix` (same device) instead of uploaded bytes: pairs of a
+// batch uploaded with ref == NULL carry a text position in (id, idr) -- idr = low 32 bits, id = bits 32..62, id < 0 for a
+// pair that walks the text backwards (left extensions).  NULL detaches.
+extern "C" int meme_bsw_attach_text(meme_bsw_t *b, const meme_index_t *ix)
+{
+    if (!b) return MEME_E_ARG;
+    if (ix && ix->device != b->device) { meme_set_error("index and banded-SW handle live on different devices"); return MEME_E_ARG; }
+    b->text_pac = ix ? ix->v.pac : nullptr;
+    b->text_len = ix ? ix->v.sa_num : 0;
+    return MEME_OK;
+}
+
 __global__ void k_bsw_rebase(meme_seqpair_t *__restrict__ pairs, int64_t n, int32_t ref_base, int32_t qer_base)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,8 +514,11 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
 {
     if (!b || nseg < 0 || (nseg && (!pairs || !n_pairs || !ref || !n_ref || !qer || !n_qer))) { meme_set_error("bad argument"); return MEME_E_ARG; }
     int64_t tot_p = 0, tot_r = 0, tot_q = 0;
+    // reference by position: no reference bytes at all, and a text is attached
+    bool text_mode = b->text_pac != nullptr;
+    for (int s = 0; s < nseg && text_mode; s++) if (ref[s] || n_ref[s]) text_mode = false;
     for (int s = 0; s < nseg; s++) {
-        if (n_pairs[s] < 0 || n_ref[s] < 0 || n_qer[s] < 0 || (n_pairs[s] && (!pairs[s] || !ref[s] || !qer[s]))) {
+        if (n_pairs[s] < 0 || n_ref[s] < 0 || n_qer[s] < 0 || (n_pairs[s] && (!pairs[s] || (!text_mode && !ref[s]) || !qer[s]))) {
             meme_set_error("bad segment %d", s);
             return MEME_E_ARG;
         }
@@ -487,20 +531,24 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
     // validation, class counts of the inter-sequence kernel, and the (few) pairs of the overflow classes
     int64_t is_cnt[BSW_IS_NCLASS] = {0};
     std::vector<u32> ovf;
-    std::vector<int32_t> ovf_len2;
+    std::vector<int32_t> ovf_len2, ovf_len1;
     {
         int64_t base = 0;
         for (int s = 0; s < nseg; s++) {
             const meme_seqpair_t *ps = pairs[s];
             for (int64_t i = 0; i < n_pairs[s]; i++) {
                 const meme_seqpair_t &p = ps[i];
-                if (p.len1 < 0 || p.len2 < 0 || p.idr < 0 || p.idq < 0 || (int64_t)p.idr + p.len1 > n_ref[s] ||
-                    (int64_t)p.idq + p.len2 > n_qer[s]) {
+                bool bad = p.len1 < 0 || p.len2 < 0 || p.idq < 0 || (int64_t)p.idq + p.len2 > n_qer[s];
+                if (!bad && text_mode) {
+                    const u64 pos = ((u64)((u32)p.id & 0x7fffffffu) << 32) | (u32)p.idr;
+                    bad = p.len1 > 0 && (p.id < 0 ? (pos >= b->text_len || pos + 1 < (u64)p.len1) : pos + (u64)p.len1 > b->text_len);
+                } else if (!bad) bad = p.idr < 0 || (int64_t)p.idr + p.len1 > n_ref[s];
+                if (bad) {
                     meme_set_error("pair %lld of segment %d points outside the sequence buffers", (long long)i, s);
                     return MEME_E_ARG;
                 }
                 const bool o = p.len2 > BSW_IS_MAX_QLEN || (long long)p.h0 + (long long)p.len2 * b->match_a >= BSW_IS_MAX_SCORE || p.h0 < 0;
-                if (o) { ovf.push_back((u32)(base + i)); ovf_len2.push_back(p.len2); }
+                if (o) { ovf.push_back((u32)(base + i)); ovf_len2.push_back(p.len2); ovf_len1.push_back(p.len1); }
                 else is_cnt[bsw_is_class_of(p.len2)]++;
             }
             base += n_pairs[s];
@@ -520,13 +568,15 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
                 CUDA_TRY(cudaMemcpyAsync(b->d_pairs + pb, pairs[s], (size_t)n_pairs[s] * sizeof(meme_seqpair_t), cudaMemcpyHostToDevice, st));
                 if (n_ref[s]) CUDA_TRY(cudaMemcpyAsync(b->d_ref + rb, ref[s], (size_t)n_ref[s], cudaMemcpyHostToDevice, st));
                 if (n_qer[s]) CUDA_TRY(cudaMemcpyAsync(b->d_qer + qb, qer[s], (size_t)n_qer[s], cudaMemcpyHostToDevice, st));
-                if (rb || qb) k_bsw_rebase<<<(unsigned)((n_pairs[s] + 255) / 256), 256, 0, st>>>(b->d_pairs + pb, n_pairs[s], (int32_t)rb, (int32_t)qb);
+                if ((rb && !text_mode) || qb)
+                    k_bsw_rebase<<<(unsigned)((n_pairs[s] + 255) / 256), 256, 0, st>>>(b->d_pairs + pb, n_pairs[s], text_mode ? 0 : (int32_t)rb, (int32_t)qb);
             }
             pb += n_pairs[s]; rb += n_ref[s]; qb += n_qer[s];
         }
     }
     b->n_pairs = n_all; b->n_ref = tot_r; b->n_qer = tot_q;
     b->n_ovf = (int64_t)ovf.size(); b->n_is = n_all - b->n_ovf;
+    b->text_mode = text_mode ? 1 : 0;
     // ---- inter-sequence order: device radix sort by (query length, reference length), longest first ----
     // sorted descending, the overflow pairs (key 0xffffffff) come first, then the classes from the widest rows down
     b->is_off[BSW_IS_NCLASS] = b->n_ovf;
@@ -556,10 +606,10 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
         b->cls_off[0] = 0;
         for (int c = 0; c < BSW_NCLASS; c++) b->cls_off[c + 1] = b->cls_off[c] + cnt[c];
         std::vector<u32> order(ovf.size() + 1);
-        std::vector<int32_t> olen(ovf.size() + 1);
+        std::vector<int32_t> olen(ovf.size() + 1), olen1(ovf.size() + 1);
         int64_t cur[BSW_NCLASS];
         for (int c = 0; c < BSW_NCLASS; c++) cur[c] = b->cls_off[c];
-        for (size_t k = 0; k < ovf.size(); k++) { int64_t d = cur[bsw_class_of(ovf_len2[k])]++; order[(size_t)d] = ovf[k]; olen[(size_t)d] = ovf_len2[k]; }
+        for (size_t k = 0; k < ovf.size(); k++) { int64_t d = cur[bsw_class_of(ovf_len2[k])]++; order[(size_t)d] = ovf[k]; olen[(size_t)d] = ovf_len2[k]; olen1[(size_t)d] = ovf_len1[k]; }
         if ((rc = meme_grow_device((void **)&b->d_order, &b->cap_order, ovf.size() + 1, 4, st))) return rc;
         // rows of the generic kernel (queries beyond the register kernel): 2 * (len2 + 2) int32 per pair
         const int64_t l0 = b->cls_off[BSW_NCLASS - 1], n_long = b->cls_off[BSW_NCLASS] - l0;
@@ -572,9 +622,22 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
             if ((rc = meme_grow_device((void **)&b->d_scratch, &b->cap_scratch, (size_t)acc + 16, 4, st))) return rc;
             CUDA_TRY(cudaMemcpyAsync(b->d_scratch_off, off.data(), (size_t)(n_long + 1) * 8, cudaMemcpyHostToDevice, st));
         }
+        std::vector<int64_t> roff;
         if (!ovf.empty()) {
             CUDA_TRY(cudaMemcpyAsync(b->d_order, order.data(), ovf.size() * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));       // `order` and `off` are temporaries
+            if (text_mode) {
+                // the overflow kernels read bytes: write these pairs' reference out of the text (class order = `order`)
+                roff.resize(ovf.size() + 1);
+                int64_t racc = 0;
+                for (size_t k = 0; k < ovf.size(); k++) { roff[k] = racc; racc += olen1[k]; }
+                roff[ovf.size()] = racc;
+                if ((rc = meme_grow_device((void **)&b->d_ref, &b->cap_ref, (size_t)racc + 64, 1, st))) return rc;
+                if ((rc = meme_grow_device((void **)&b->d_ovf_off, &b->cap_ovf_off, ovf.size() + 1, 8, st))) return rc;
+                CUDA_TRY(cudaMemcpyAsync(b->d_ovf_off, roff.data(), (ovf.size() + 1) * 8, cudaMemcpyHostToDevice, st));
+                k_bsw_materialise<<<(unsigned)ovf.size(), 128, 0, st>>>(b->d_pairs, b->d_order, b->d_ovf_off, (int64_t)ovf.size(), b->text_pac, b->d_ref);
+                CUDA_TRY(cudaGetLastError());
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));       // `order`, `off`, `roff` are temporaries
         }
     }
     return MEME_OK;
@@ -642,7 +705,8 @@ extern "C" int meme_bsw_run_ext(meme_bsw_t *b, int32_t w, int32_t tries, int32_t
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sms * per_sm, need = (cn + BSW_IS_THREADS - 1) / BSW_IS_THREADS;
             if (grid > need) grid = need;
-            k_bsw_is<<<(unsigned)grid, BSW_IS_THREADS, sm, st>>>(P, BSW_IS_WORDS[c], w, tries, prev_is_h0, b->d_pairs, b->d_idx2 + lo, cn, b->d_ref, b->d_qer,
+            k_bsw_is<<<(unsigned)grid, BSW_IS_THREADS, sm, st>>>(P, BSW_IS_WORDS[c], w, tries, prev_is_h0, b->d_pairs, b->d_idx2 + lo, cn, b->d_ref,
+                                                              b->text_mode ? b->text_pac : nullptr, b->d_qer,
                                                               b->d_wused, b->d_ctrl);
             CUDA_TRY(cudaGetLastError());
             b->launches++;

@@ -62,9 +62,24 @@ struct BswIsConst {
 
 struct BswIsOut { int score, tle, gtle, qle, gscore, max_off; };
 
+// The reference side of a pair: bytes uploaded by the caller (codes 0..4), or -- when the caller's reference is the
+// indexed text that already sits in HBM -- a position in the 2-bit fwd+RC text and a direction (left extensions walk the
+// text backwards: src/bwamem.cpp:L2798 copies rseq reversed).  The text carries no N (bntseq randomises them at index
+// time, src/bntseq.cpp:L299), so both forms give the same codes.
+struct BswTarget {
+    const uint8_t *bytes;
+    const u64 *pac; u64 pos; int dir;
+};
+BSW_HD int bsw_target_at(const BswTarget &T, int i)
+{
+    if (T.bytes) return T.bytes[i];
+    const u64 p = T.dir > 0 ? T.pos + (u64)i : T.pos - (u64)i;
+    return (int)((T.pac[p >> 5] >> (2 * (p & 31))) & 3);
+}
+
 // One pair.  row: the thread's score row, word j at row[j * stride], j in [0, qlen]; qrow: its query bases, byte j at
 // qrow[j * stride]; the caller has NOT initialised either.
-BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qlen, const uint8_t *target, int tlen, int h0,
+BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qlen, const BswTarget &target, int tlen, int h0,
                        u32 *row, uint8_t *qrow, const int stride, BswIsOut &out, u64 &cells)
 {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins, e_del = P.e_del, e_ins = P.e_ins;
@@ -102,10 +117,10 @@ BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qle
     }
     int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen;
-    int tc_next = tlen > 0 ? target[0] : 0;
+    int tc_next = tlen > 0 ? bsw_target_at(target, 0) : 0;
     for (int i = 0; i < tlen; i++) {
         const int tc = tc_next;
-        if (i + 1 < tlen) tc_next = target[i + 1];                 // the next row's base arrives while this row is computed
+        if (i + 1 < tlen) tc_next = bsw_target_at(target, i + 1);  // the next row's base arrives while this row is computed
         int f = 0, h1, key = -1;
         if (beg < i - w) beg = i - w;
         if (end > i + w + 1) end = i + w + 1;
@@ -173,7 +188,7 @@ BSW_HD void bsw_is_one(const BswIsConst &P, int w, const uint8_t *query, int qle
 // One pair with the extension driver's band retries (reference src/bwamem.cpp:L2968-3000): up to `tries` widths
 // w, 2w, ...; a result is final when the score equals `prev` (the region's score before this extension), when the best
 // cell stayed within 3/4 of the band, or on the last try.  Returns the width that produced the final result.
-BSW_HD int bsw_is_retry(const BswIsConst &P, int w, int tries, int prev, const uint8_t *query, int qlen, const uint8_t *target,
+BSW_HD int bsw_is_retry(const BswIsConst &P, int w, int tries, int prev, const uint8_t *query, int qlen, const BswTarget &target,
                         int tlen, int h0, u32 *row, uint8_t *qrow, const int stride, BswIsOut &out, u64 &cells)
 {
     int wt = w;

@@ -40,7 +40,7 @@ def run_mem(exe: str, prefix: str, fastqs: list[str], out_sam: str, threads: int
     proc = [l for l in p.stderr.splitlines() if "Processed" in l and "real sec" in l]
     real = sum(float(l.split("CPU sec,")[1].split("real sec")[0]) for l in proc)
     logs = [l for l in p.stderr.splitlines() if l.startswith("[meme_b200]")]
-    return {"real_s": real, "wall_s": wall, "chunks": len(proc), "log": logs}
+    return {"real_s": real, "wall_s": wall, "chunks": len(proc), "log": logs, "stderr_tail": p.stderr[-6000:]}
 
 
 def sam_body(path: str) -> bytes:

@@ -7,6 +7,8 @@
 //   1. every host thread walks its share of the reads and writes the left / right extension pairs of all their seeds
 //      into its own pinned arena (alignment-region bookkeeping as in L2612-2934: reference window per chain, seeds in
 //      score order, reversed copies for the left side);
+//      (with the index resident on the GPU the reference side of a pair is just a position in that text: no bytes copied
+//      or uploaded);
 //   2. ONE device call per side (meme_glue_bsw_segments -> meme_bsw_upload_segments / meme_bsw_run_ext): the band
 //      retries (MAX_BAND_TRY, w then 2w, L2968-3376) are decided by the kernel, the right side starts from the scores
 //      the left side produced (h0 = region score, L3168-3173);
@@ -71,7 +73,7 @@ static inline void seed_coverage(mem_alnreg_t *a)
 
 // step 1 for one read: regions and extension pairs of all seeds of all chains
 static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *ref_string, const bseq1_t *seq,
-                         int l, mem_chain_v *chn, mem_alnreg_v *av, ThreadState &T)
+                         int l, mem_chain_v *chn, mem_alnreg_v *av, ThreadState &T, const bool by_position)
 {
     const int64_t l_pac = bns->l_pac;
     const uint8_t *query = (const uint8_t *)seq->seq;
@@ -125,11 +127,17 @@ static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_
                 sp->h0 = s->len * opt->a;
                 sp->seqid = l; sp->regid = (int)av->n - 1;
                 sp->len2 = s->qbeg; sp->len1 = (int32_t)tl;
-                sp->idq = (int32_t)T.left.n_qer; sp->idr = (int32_t)T.left.n_ref;
+                sp->idq = (int32_t)T.left.n_qer;
                 uint8_t *qs = T.left.take_qer(s->qbeg);
                 for (int i = 0; i < s->qbeg; ++i) qs[i] = query[s->qbeg - 1 - i];
-                uint8_t *rs = T.left.take_ref(tl);
-                for (int64_t i = 0; i < tl; ++i) rs[i] = rseq[tl - 1 - i];
+                if (by_position) {                      // the reversed reference = the text read backwards from rbeg - 1
+                    const uint64_t p = tl > 0 ? (uint64_t)(s->rbeg - 1) : 0;
+                    sp->idr = (int32_t)(uint32_t)p; sp->id = (int32_t)((uint32_t)(p >> 32) | 0x80000000u);
+                } else {
+                    sp->idr = (int32_t)T.left.n_ref;
+                    uint8_t *rs = T.left.take_ref(tl);
+                    for (int64_t i = 0; i < tl; ++i) rs[i] = rseq[tl - 1 - i];
+                }
                 a->qb = s->qbeg; a->rb = s->rbeg;
             } else {
                 a->score = a->truesc = s->len * opt->a; a->qb = 0; a->rb = s->rbeg;
@@ -142,9 +150,15 @@ static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_
                 sp->h0 = H0_;                           // known after the left side
                 sp->seqid = l; sp->regid = (int)av->n - 1;
                 sp->len2 = (int32_t)(l_query - qe); sp->len1 = (int32_t)(rmax1 - rmax0 - re);
-                sp->idq = (int32_t)T.right.n_qer; sp->idr = (int32_t)T.right.n_ref;
+                sp->idq = (int32_t)T.right.n_qer;
                 memcpy(T.right.take_qer(sp->len2), query + qe, (size_t)sp->len2);
-                memcpy(T.right.take_ref(sp->len1), rseq + re, (size_t)sp->len1);
+                if (by_position) {
+                    const uint64_t p = (uint64_t)(rmax0 + re);
+                    sp->idr = (int32_t)(uint32_t)p; sp->id = (int32_t)(uint32_t)(p >> 32);
+                } else {
+                    sp->idr = (int32_t)T.right.n_ref;
+                    memcpy(T.right.take_ref(sp->len1), rseq + re, (size_t)sp->len1);
+                }
                 a->qe = (int)qe; a->re = rmax0 + re;
             } else {
                 a->qe = l_query; a->re = s->rbeg + s->len;
@@ -248,6 +262,7 @@ bool meme_extend_chunk(worker_t &w, int n)
     const bntseq_t *bns = w.fmi->idx->bns;
     const uint8_t *pac = w.fmi->idx->pac;
     const int T = std::max(1, (int)w.nthreads);
+    const bool by_position = meme_glue_bsw_text_mode();     // the reference side of the pairs is read from the resident text
     if ((int)g_ts.size() < T) g_ts.resize((size_t)T);
     g_srt_off.resize((size_t)n + 1);
     double t0 = omp_get_wtime();
@@ -262,13 +277,13 @@ bool meme_extend_chunk(worker_t &w, int n)
             // from the blocks the glue page-locked at index load when it could
             const int64_t est = (int64_t)(r1 - r0) * 6;
             for (Arena *A : {&S.left, &S.right}) {
-                Arena::reserve(A->pairs, A->cap, est); Arena::reserve(A->ref, A->cap_ref, est * 200); Arena::reserve(A->qer, A->cap_qer, est * 100);
+                Arena::reserve(A->pairs, A->cap, est); if (!by_position) Arena::reserve(A->ref, A->cap_ref, est * 200); Arena::reserve(A->qer, A->cap_qer, est * 100);
                 Arena::reserve(A->w_used, A->cap_w, est);
             }
         }
         for (int l = r0; l < r1; l++) {
             g_srt_off[(size_t)l] = (int64_t)S.srt.size();
-            collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S);
+            collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S, by_position);
         }
     }
     double t1 = omp_get_wtime();
@@ -281,8 +296,8 @@ bool meme_extend_chunk(worker_t &w, int n)
     for (int t = 0; t < T; t++) {
         Arena &A = g_ts[(size_t)t].left;
         Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
-        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer; nq[(size_t)t] = A.n_qer;
-        pw[(size_t)t] = A.w_used; tot_left += A.n;
+        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = by_position ? nullptr : A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer;
+        nq[(size_t)t] = A.n_qer; pw[(size_t)t] = A.w_used; tot_left += A.n;
     }
     meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 0, opt->o_del,
                            opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->pen_clip5, opt->a, opt->b, pw.data());
@@ -309,8 +324,8 @@ bool meme_extend_chunk(worker_t &w, int n)
     for (int t = 0; t < T; t++) {
         Arena &A = g_ts[(size_t)t].right;
         Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
-        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer; nq[(size_t)t] = A.n_qer;
-        pw[(size_t)t] = A.w_used; tot_right += A.n;
+        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = by_position ? nullptr : A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer;
+        nq[(size_t)t] = A.n_qer; pw[(size_t)t] = A.w_used; tot_right += A.n;
     }
     double t3 = omp_get_wtime();
     meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 1, opt->o_del,

@@ -29,6 +29,7 @@ struct Api {
     decltype(&meme_bsw_download_segments) bsw_download_segments = nullptr;
     decltype(&meme_bsw_run_ext) bsw_run_ext = nullptr;
     decltype(&meme_bsw_set_match) bsw_set_match = nullptr;
+    decltype(&meme_bsw_attach_text) bsw_attach_text = nullptr;
     decltype(&meme_pinned_alloc) pinned_alloc = nullptr;
     decltype(&meme_pinned_free) pinned_free = nullptr;
     bool ok = false;
@@ -54,10 +55,11 @@ Api &api()
         a.bsw_download_segments = (decltype(a.bsw_download_segments))dlsym(a.so, "meme_bsw_download_segments");
         a.bsw_run_ext = (decltype(a.bsw_run_ext))dlsym(a.so, "meme_bsw_run_ext");
         a.bsw_set_match = (decltype(a.bsw_set_match))dlsym(a.so, "meme_bsw_set_match");
+        a.bsw_attach_text = (decltype(a.bsw_attach_text))dlsym(a.so, "meme_bsw_attach_text");
         a.pinned_alloc = (decltype(a.pinned_alloc))dlsym(a.so, "meme_pinned_alloc");
         a.pinned_free = (decltype(a.pinned_free))dlsym(a.so, "meme_pinned_free");
         a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
-               a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
+               a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
     });
@@ -275,6 +277,14 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
 // ---- chunk-level seed extension (meme_extend.inl, included by the patched bwamem.cpp) ----
 bool meme_glue_bsw_enabled() { return env_on("MEME_B200_BSW"); }
 
+// Reference by position: with the index resident on the GPUs (MEME_B200=1) the extension pairs name their reference side
+// as a position in that text and nothing of it is uploaded.  Off when pairs are dumped (the dump carries bytes) or when
+// MEME_B200_BSW_BYTES=1 asks for the byte form.
+bool meme_glue_bsw_text_mode()
+{
+    return !g_index.empty() && !getenv("MEME_B200_DUMP_PAIRS") && !env_on("MEME_B200_BSW_BYTES");
+}
+
 // Pinned blocks reserved where the index is loaded (outside the aligner's per-chunk timers): page-locking the ~2 GB of
 // pair arenas a chunk needs costs about a second, which the first chunk would otherwise pay.
 namespace {
@@ -293,6 +303,7 @@ void meme_glue_pinned_reserve(int threads, long reads_per_chunk)
     size_t total = 0;
     for (int t = 0; t < threads * 2; t++)
         for (size_t b : sizes) {
+            if (b == est * 200 && meme_glue_bsw_text_mode()) continue;     // no reference bytes: pairs name text positions
             void *p = nullptr;
             if (api().pinned_alloc(b, &p)) return;          // not fatal: the arenas fall back to allocating on demand
             std::lock_guard<std::mutex> lk(g_pin_mu);
@@ -309,8 +320,7 @@ void *meme_glue_pinned_alloc(size_t bytes)
         std::lock_guard<std::mutex> lk(g_pin_mu);
         size_t best = (size_t)-1;
         for (size_t i = 0; i < g_pin_cache.size(); i++)
-            if (g_pin_cache[i].bytes >= bytes && g_pin_cache[i].bytes <= bytes + bytes / 2 + (1 << 20) &&
-                (best == (size_t)-1 || g_pin_cache[i].bytes < g_pin_cache[best].bytes)) best = i;
+            if (g_pin_cache[i].bytes >= bytes && (best == (size_t)-1 || g_pin_cache[i].bytes < g_pin_cache[best].bytes)) best = i;   // best fit
         if (best != (size_t)-1) { void *p = g_pin_cache[best].p; g_pin_cache.erase(g_pin_cache.begin() + (long)best); return p; }
     }
     void *p = nullptr;
@@ -335,6 +345,10 @@ void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t
             meme_bsw_t *h = nullptr;
             int rc = A.bsw_create(dev, &h);
             if (rc) die("meme_bsw_create", rc);
+            if (meme_glue_bsw_text_mode()) {
+                rc = A.bsw_attach_text(h, g_index[hs.size()]);
+                if (rc) die("meme_bsw_attach_text", rc);
+            }
             hs.push_back(h);
         }
     }

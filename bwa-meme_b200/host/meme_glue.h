@@ -28,6 +28,7 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
 
 // used by meme_extend.inl
 bool meme_glue_bsw_enabled();
+bool meme_glue_bsw_text_mode();
 void meme_glue_pinned_reserve(int threads, long reads_per_chunk);
 void *meme_glue_pinned_alloc(size_t bytes);
 void meme_glue_pinned_free(void *p);

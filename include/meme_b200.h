@@ -195,6 +195,12 @@ int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_seqpair_t *
                              const uint8_t *const *ref, const int64_t *n_ref, const uint8_t *const *qer, const int64_t *n_qer);
 int meme_bsw_download_segments(meme_bsw_t *b, int32_t nseg, meme_seqpair_t *const *pairs, const int64_t *n_pairs,
                                int32_t *const *w_used);
+/* Reference by position: when the reference side of the pairs IS the indexed text that already sits in HBM (the
+ * extension driver reads it from ref_string = the .0123 file, src/bwamem.cpp:L2670-2681), nothing of it needs uploading.
+ * After meme_bsw_attach_text(b, ix) (same device), a batch uploaded with ref == NULL / n_ref == 0 in every segment is
+ * read as: (id, idr) of a pair = position in the fwd+RC text (idr = low 32 bits, id = bits 32..62), id < 0 = the pair
+ * walks the text backwards from that position (left extensions).  ix == NULL detaches. */
+int meme_bsw_attach_text(meme_bsw_t *b, const meme_index_t *ix);
 /* DP cells evaluated by the last run (band-limited, retries included), for GCUPS accounting. */
 int meme_bsw_cells(meme_bsw_t *b, uint64_t *cells);
 

@@ -65,4 +65,6 @@ for name, exe, env in arms:
     if ext_lines: out["gpu_extend_log"] = ext_lines[-1]
     if os.environ.get("E2E_VERBOSE"):
         print("\n".join(l for l in p.stderr.splitlines() if "[meme" in l), file=sys.stderr)
+    if os.environ.get("E2E_PROFILE"):      # the aligner's own profile table (src/profiling.cpp)
+        print(f"---- {name}\n" + p.stderr[-5000:], file=sys.stderr)
     print(json.dumps(out), flush=True)

@@ -113,3 +113,46 @@ def test_sorted_launch_order_covers_every_pair(oracle, bsw):
     got = bsw.get_scores(pairs, ref, qer, 100)
     for f in oracle.RESULT_FIELDS:
         assert (got[f] == want[f]).all(), f
+
+
+def test_reference_by_position_in_the_resident_text(oracle, pkg, golden_index):
+    """Pairs whose reference side is a position in the index's HBM-resident 2-bit text (no reference upload;
+    meme_bsw_attach_text): forwards and backwards, inter-sequence kernel and overflow classes (a long query, a huge h0),
+    with the band retries.  Equal to the oracle on the bytes those positions spell."""
+    from bwa_meme_b200 import capi
+    rng = np.random.default_rng(19)
+    text = np.fromfile(golden_index + ".0123", dtype=np.uint8)
+    n = 6000
+    pairs = np.zeros(n, capi.SEQPAIR_DTYPE)
+    byte_pairs = np.zeros(n, capi.SEQPAIR_DTYPE)
+    refs, qers = [], []
+    ro = qo = 0
+    for i in range(n):
+        ql = int(rng.integers(1, 151)) if i % 500 else int(rng.integers(330, 420))
+        tl = ql + int(rng.integers(0, 100))
+        d = 1 if rng.random() < 0.5 else -1
+        p = int(rng.integers(600, len(text) - 600))
+        t = text[p:p + tl] if d > 0 else text[p - tl + 1:p + 1][::-1]
+        q = t[:ql].copy()
+        m = rng.random(ql) < 0.04
+        q[m] = (q[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+        h0 = int(rng.integers(19, 120)) if i % 333 else 70000
+        pairs[i] = (p & 0xffffffff, qo, (p >> 32) | (-(1 << 31) if d < 0 else 0), tl, ql, h0, 0, 0, 0, 0, 0, 0, 0, 0)
+        byte_pairs[i] = (ro, qo, 0, tl, ql, h0, 0, 0, 0, 0, 0, 0, 0, 0)
+        refs.append(t); qers.append(q); ro += tl; qo += ql
+    ref, qer = np.concatenate(refs), np.concatenate(qers)
+    ix = capi.MemeIndex(golden_index, mode=3)
+    b = capi.MemeBsw()
+    try:
+        for w, tries in ((100, 1), (3, 2)):
+            a = oracle.bsw_batch(byte_pairs, ref, qer, w)
+            if tries == 2:
+                a2 = oracle.bsw_batch(byte_pairs, ref, qer, 2 * w)
+                final = (a["score"] == -1) | (a["max_off"] < (w >> 1) + (w >> 2))
+            got = b.get_scores_text(ix, pairs, qer, w, tries=tries)
+            for f in oracle.RESULT_FIELDS:
+                want = a[f] if tries == 1 else np.where(final, a[f], a2[f])
+                bad = np.nonzero(got[f] != want)[0]
+                assert len(bad) == 0, (w, tries, f, bad[:3], pairs[bad[0]])
+    finally:
+        b.close(); ix.close()

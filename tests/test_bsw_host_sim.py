@@ -91,3 +91,40 @@ def test_non_default_penalties(oracle, sim, pkg):
     got, _, _ = sim(pairs, ref, qer, 60, opt=capi.BswOpt(5, 2, 7, 3, 50, 3, 2, 5))
     for f in oracle.RESULT_FIELDS:
         assert (got[f] == want[f]).all(), f
+
+
+def test_reference_by_position_equals_reference_bytes(oracle, sim, pkg):
+    """The pair function reading its reference side from a 2-bit text by position (forwards for right extensions,
+    backwards for left ones) gives what the byte form gives."""
+    import ctypes as C
+    from bwa_meme_b200 import capi
+    rng = np.random.default_rng(9)
+    text = rng.integers(0, 4, size=60000, dtype=np.uint8)
+    n = 3000
+    pairs = np.zeros(n, capi.SEQPAIR_DTYPE)
+    pos = np.zeros(n, np.int64); dirs = np.zeros(n, np.int32)
+    refs, qers = [], []
+    ro = qo = 0
+    for i in range(n):
+        ql, tl = int(rng.integers(1, 151)), 0
+        tl = ql + int(rng.integers(0, 100))
+        d = 1 if rng.random() < 0.5 else -1
+        p = int(rng.integers(400, len(text) - 400))
+        t = text[p:p + tl] if d > 0 else text[p - tl + 1:p + 1][::-1]
+        q = t[:ql].copy()
+        m = rng.random(ql) < 0.04
+        q[m] = (q[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+        pairs[i] = (ro, qo, 0, tl, ql, int(rng.integers(19, 120)), 0, 0, 0, 0, 0, 0, 0, 0)
+        pos[i], dirs[i] = p, d
+        refs.append(t); qers.append(q); ro += tl; qo += ql
+    ref, qer = np.concatenate(refs), np.concatenate(qers)
+    want = oracle.bsw_batch(pairs, ref, qer, 100)
+    L = C.CDLL(os.path.join(SIM_DIR, "_build", "libbsw_host.so"))
+    out = pairs.copy()
+    opt = capi.default_bsw_opt()
+    rc = L.bsw_is_sim_text(C.c_void_p(out.ctypes.data), C.c_int64(n), C.c_void_p(text.ctypes.data), C.c_int64(len(text)),
+                           C.c_void_p(pos.ctypes.data), C.c_void_p(dirs.ctypes.data), C.c_void_p(qer.ctypes.data), C.c_int(100),
+                           C.c_int(1), C.c_int(0), C.byref(opt), None)
+    assert rc == 0
+    for f in oracle.RESULT_FIELDS:
+        assert (out[f] == want[f]).all(), f
