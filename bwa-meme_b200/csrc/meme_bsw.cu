@@ -21,6 +21,7 @@
 // (L218-221) comes from two ballots.  All per-row control (z-drop, band, gscore) is warp-uniform.
 // Slots outside the current band keep their old contents, exactly like the reference's eh[] array.
 #include <vector>
+#include <thread>
 #include <algorithm>
 #include <climits>
 #include <cub/device/device_radix_sort.cuh>
@@ -528,30 +529,52 @@ extern "C" int meme_bsw_upload_segments(meme_bsw_t *b, int32_t nseg, const meme_
         meme_set_error("batch too large for 32-bit pair offsets (%lld pairs, %lld + %lld sequence bytes)", (long long)tot_p, (long long)tot_r, (long long)tot_q);
         return MEME_E_ARG;
     }
-    // validation, class counts of the inter-sequence kernel, and the (few) pairs of the overflow classes
+    // validation, class counts of the inter-sequence kernel, and the (few) pairs of the overflow classes: one host thread
+    // per segment (the segments are the arenas of the caller's threads, a few hundred thousand pairs each)
     int64_t is_cnt[BSW_IS_NCLASS] = {0};
     std::vector<u32> ovf;
     std::vector<int32_t> ovf_len2, ovf_len1;
     {
-        int64_t base = 0;
-        for (int s = 0; s < nseg; s++) {
+        struct SegScan { int64_t cnt[BSW_IS_NCLASS] = {0}; std::vector<u32> ovf; std::vector<int32_t> l2, l1; int64_t bad = -1; };
+        std::vector<SegScan> scan((size_t)nseg);
+        std::vector<int64_t> seg_base((size_t)nseg + 1, 0);
+        for (int s = 0; s < nseg; s++) seg_base[(size_t)s + 1] = seg_base[(size_t)s] + n_pairs[s];
+        const int match_a = b->match_a;
+        const u64 text_len = b->text_len;
+        auto scan_seg = [&](int s) {
+            SegScan &S = scan[(size_t)s];
             const meme_seqpair_t *ps = pairs[s];
+            const int64_t base = seg_base[(size_t)s];
             for (int64_t i = 0; i < n_pairs[s]; i++) {
                 const meme_seqpair_t &p = ps[i];
                 bool bad = p.len1 < 0 || p.len2 < 0 || p.idq < 0 || (int64_t)p.idq + p.len2 > n_qer[s];
                 if (!bad && text_mode) {
                     const u64 pos = ((u64)((u32)p.id & 0x7fffffffu) << 32) | (u32)p.idr;
-                    bad = p.len1 > 0 && (p.id < 0 ? (pos >= b->text_len || pos + 1 < (u64)p.len1) : pos + (u64)p.len1 > b->text_len);
+                    bad = p.len1 > 0 && (p.id < 0 ? (pos >= text_len || pos + 1 < (u64)p.len1) : pos + (u64)p.len1 > text_len);
                 } else if (!bad) bad = p.idr < 0 || (int64_t)p.idr + p.len1 > n_ref[s];
-                if (bad) {
-                    meme_set_error("pair %lld of segment %d points outside the sequence buffers", (long long)i, s);
-                    return MEME_E_ARG;
-                }
-                const bool o = p.len2 > BSW_IS_MAX_QLEN || (long long)p.h0 + (long long)p.len2 * b->match_a >= BSW_IS_MAX_SCORE || p.h0 < 0;
-                if (o) { ovf.push_back((u32)(base + i)); ovf_len2.push_back(p.len2); ovf_len1.push_back(p.len1); }
-                else is_cnt[bsw_is_class_of(p.len2)]++;
+                if (bad) { S.bad = i; return; }
+                const bool o = p.len2 > BSW_IS_MAX_QLEN || (long long)p.h0 + (long long)p.len2 * match_a >= BSW_IS_MAX_SCORE || p.h0 < 0;
+                if (o) { S.ovf.push_back((u32)(base + i)); S.l2.push_back(p.len2); S.l1.push_back(p.len1); }
+                else S.cnt[bsw_is_class_of(p.len2)]++;
             }
-            base += n_pairs[s];
+        };
+        if (nseg > 1 && tot_p > 100000) {
+            std::vector<std::thread> th;
+            for (int s = 0; s < nseg; s++) th.emplace_back(scan_seg, s);
+            for (auto &t : th) t.join();
+        } else {
+            for (int s = 0; s < nseg; s++) scan_seg(s);
+        }
+        for (int s = 0; s < nseg; s++) {
+            const SegScan &S = scan[(size_t)s];
+            if (S.bad >= 0) {
+                meme_set_error("pair %lld of segment %d points outside the sequence buffers", (long long)S.bad, s);
+                return MEME_E_ARG;
+            }
+            for (int c = 0; c < BSW_IS_NCLASS; c++) is_cnt[c] += S.cnt[c];
+            ovf.insert(ovf.end(), S.ovf.begin(), S.ovf.end());
+            ovf_len2.insert(ovf_len2.end(), S.l2.begin(), S.l2.end());
+            ovf_len1.insert(ovf_len1.end(), S.l1.begin(), S.l1.end());
         }
     }
     CUDA_TRY(cudaSetDevice(b->device));

@@ -95,7 +95,10 @@ struct meme_index {
     cudaStream_t copy_stream;
     cudaEvent_t pe[6];                    // per buffer set: input arrived [0,1], run finished [2,3], lists drained [4,5]
     int piped; int64_t piped_reads;
+    // ---- chaining (meme_chain.cu) ----
+    struct ChainWork *chain;
 };
+void meme_chain_free(struct ChainWork *c);
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);
 int meme_grow_pinned(void **p, size_t *cap, size_t need, size_t elem);

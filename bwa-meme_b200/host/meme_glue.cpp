@@ -32,6 +32,8 @@ struct Api {
     decltype(&meme_bsw_attach_text) bsw_attach_text = nullptr;
     decltype(&meme_pinned_alloc) pinned_alloc = nullptr;
     decltype(&meme_pinned_free) pinned_free = nullptr;
+    decltype(&meme_chain_set_contigs) chain_set_contigs = nullptr;
+    decltype(&meme_chain_batch_multi) chain_batch_multi = nullptr;
     bool ok = false;
 };
 
@@ -58,7 +60,9 @@ Api &api()
         a.bsw_attach_text = (decltype(a.bsw_attach_text))dlsym(a.so, "meme_bsw_attach_text");
         a.pinned_alloc = (decltype(a.pinned_alloc))dlsym(a.so, "meme_pinned_alloc");
         a.pinned_free = (decltype(a.pinned_free))dlsym(a.so, "meme_pinned_free");
-        a.ok = a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+        a.chain_set_contigs = (decltype(a.chain_set_contigs))dlsym(a.so, "meme_chain_set_contigs");
+        a.chain_batch_multi = (decltype(a.chain_batch_multi))dlsym(a.so, "meme_chain_batch_multi");
+        a.ok = a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
                a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
@@ -83,6 +87,14 @@ const bseq1_t *g_base = nullptr;
 int g_n = 0;
 bool g_have = false;
 int g_max_occ = 0;
+// MEME_B200_CHAIN=1: chains instead of SMEM/hit lists (meme_chain_batch_multi); the seeds of the chunk's chains live in one
+// arena of mem_seed_t that the chain records handed to the aligner point into (valid until the next chunk)
+std::vector<meme_chain_result_t> g_cshard;
+std::vector<int64_t> g_cseed_base;
+bool g_have_chains = false;
+bool g_contigs_set = false;
+mem_seed_t *g_seed_arena = nullptr;
+size_t g_seed_arena_cap = 0;
 double g_seed_s = 0;
 long g_seed_reads = 0;
 
@@ -140,9 +152,10 @@ void meme_glue_set_prefix(const char *idx_prefix)
 }
 
 // One GPU seeding call for the whole chunk (the reference seeds 512 reads at a time per thread).
-void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_learned)
+void meme_glue_seed_chunk(const mem_opt_t *opt, const bntseq_t *bns, bseq1_t *seqs, int n, int use_learned)
 {
     g_have = false;
+    g_have_chains = false;
     if (!use_learned || !env_on("MEME_B200") || n <= 0) return;
     Api &a = api();
     ensure_index();
@@ -173,6 +186,47 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_le
     // src/bwamem.cpp:L1154-1155): a repeat SMEM with 1e5 occurrences costs max_occ positions, not 1e5
     so.max_occ = opt->max_occ > 0 ? opt->max_occ : 0;
     g_max_occ = so.max_occ;
+    if (env_on("MEME_B200_CHAIN") && so.max_occ > 0 && bns) {
+        // seeding AND chaining on the GPU: mem_chain_Learned + mem_chain_flt run on the device-resident lists, only the
+        // filtered chains and their seeds come back (src/bwamem.cpp:L1398-1407 for every read of the chunk)
+        if (!g_contigs_set) {
+            std::vector<meme_contig_t> ct((size_t)bns->n_seqs);
+            for (int i = 0; i < bns->n_seqs; i++) { ct[(size_t)i].offset = bns->anns[i].offset; ct[(size_t)i].len = bns->anns[i].len; ct[(size_t)i].is_alt = bns->anns[i].is_alt; }
+            for (auto ix : g_index) {
+                int rc = a.chain_set_contigs(ix, ct.data(), bns->n_seqs, bns->l_pac);
+                if (rc) die("meme_chain_set_contigs", rc);
+            }
+            g_contigs_set = true;
+        }
+        meme_chain_opt_t co;
+        co.w = opt->w; co.max_chain_gap = opt->max_chain_gap; co.max_occ = opt->max_occ; co.min_seed_len = opt->min_seed_len;
+        co.min_chain_weight = opt->min_chain_weight; co.max_chain_extend = opt->max_chain_extend;
+        co.mask_level = opt->mask_level; co.drop_ratio = opt->drop_ratio;
+        g_cshard.resize(g_index.size());
+        int rc = a.chain_batch_multi(g_index.data(), (int)g_index.size(), codes.data(), off.data(), n, (opt->flag & MEM_F_PE) ? 1 : 0, &so, &co,
+                                     g_cshard.data(), g_shard_begin.data());
+        if (rc) die("meme_chain_batch_multi", rc);
+        long tot_chains = 0, tot_seeds = 0;
+        g_cseed_base.assign(g_cshard.size() + 1, 0);
+        for (size_t d = 0; d < g_cshard.size(); d++) {
+            tot_chains += (long)g_cshard[d].n_chains; tot_seeds += (long)g_cshard[d].n_seeds;
+            g_cseed_base[d + 1] = g_cseed_base[d] + g_cshard[d].n_seeds;
+        }
+        if ((size_t)tot_seeds + 1 > g_seed_arena_cap) {
+            free(g_seed_arena);
+            g_seed_arena_cap = (size_t)tot_seeds + (size_t)tot_seeds / 4 + 1024;
+            g_seed_arena = (mem_seed_t *)malloc(g_seed_arena_cap * sizeof(mem_seed_t));
+            if (!g_seed_arena) { fprintf(stderr, "[meme_b200] out of memory (seed arena)\n"); exit(EXIT_FAILURE); }
+        }
+        g_base = seqs; g_n = n; g_have_chains = true;
+        g_seed_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        g_seed_reads += n;
+        auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[meme_b200] seeded and chained %d reads on the GPU: %ld chains, %ld seeds (cumulative %.3f s for %ld reads; this chunk: "
+                "codes %.1f ms, meme_chain_batch %.1f ms)\n", n, tot_chains, tot_seeds, g_seed_s, g_seed_reads,
+                std::chrono::duration<double>(t1 - t0).count() * 1e3, std::chrono::duration<double>(t2 - t1).count() * 1e3);
+        return;
+    }
     // pairs stay together: with paired-end input consecutive reads are mates (the chunk holds whole pairs)
     int rc = a.seed_batch_multi(g_index.data(), (int)g_index.size(), codes.data(), off.data(), n, (opt->flag & MEM_F_PE) ? 1 : 0, &so,
                                 g_shard.data(), g_shard_begin.data());
@@ -234,6 +288,76 @@ bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits)
     }
     hits->n = full;
     return true;
+}
+
+// The read's chains exactly as mem_chain_Learned + mem_chain_flt would leave them in chain_ar[l] (src/bwamem.cpp:L1398-1407);
+// true = done, the caller skips its own seeding and chaining of this read.
+bool meme_glue_take_chains(bseq1_t *s, int l, mem_chain_v *chn)
+{
+    if (!g_have_chains) return false;
+    long idx = (long)(s - g_base);
+    if (idx < 0 || idx >= g_n) return false;
+    size_t sh = 0;
+    while (sh + 1 < g_cshard.size() && idx >= g_shard_begin[sh + 1]) sh++;
+    const meme_chain_result_t &R = g_cshard[sh];
+    idx -= (long)g_shard_begin[sh];
+    // base codes in place, which the caller's loop does before seeding and later stages rely on (L1277-1280)
+    for (int i = 0; i < s->l_seq; ++i) s->seq[i] = s->seq[i] < 4 ? s->seq[i] : nst_nt4_table[(int)s->seq[i]];
+    const int64_t c0 = R.chain_off[idx], n = R.chain_off[idx + 1] - c0;
+    chn->n = (size_t)n; chn->m = (size_t)n;
+    chn->a = n ? (mem_chain_t *)malloc((size_t)n * sizeof(mem_chain_t)) : nullptr;
+    if (n && !chn->a) { fprintf(stderr, "[meme_b200] out of memory (chains)\n"); exit(EXIT_FAILURE); }
+    const float frac = R.frac_rep[idx];
+    for (int64_t i = 0; i < n; i++) {
+        const meme_chain_t &g = R.chains[c0 + i];
+        mem_chain_t &c = chn->a[i];
+        memset(&c, 0, sizeof c);
+        c.seqid = l; c.n = g.n; c.m = SEEDS_PER_CHAIN; c.first = g.first; c.rid = g.rid;
+        c.w = (uint32_t)g.w; c.kept = (uint32_t)g.kept; c.is_alt = (uint32_t)g.is_alt;
+        c.frac_rep = frac; c.pos = g.pos;
+        mem_seed_t *dst = g_seed_arena + g_cseed_base[sh] + g.seed_beg;
+        const meme_chain_seed_t *src = R.seeds + g.seed_beg;
+        for (int j = 0; j < g.n; j++) {
+            dst[j].rbeg = src[j].rbeg; dst[j].qbeg = src[j].qbeg; dst[j].len = src[j].len; dst[j].score = src[j].len;
+            dst[j].done = 0; dst[j].aln = 0;
+        }
+        c.seeds = dst;
+    }
+    return true;
+}
+
+// MEME_B200_DUMP_CHAINS=path: one line per read with chain_ar as the chaining stage leaves it -- whichever code produced it
+// (with every hook off: the reference's own mem_chain_Learned + mem_chain_flt).  Test instrumentation.
+void meme_glue_dump_chains(const bseq1_t *seq, int nseq, const mem_chain_v *chain_ar)
+{
+    static const char *path = getenv("MEME_B200_DUMP_CHAINS");
+    if (!path) return;
+    static std::mutex mu;
+    static FILE *f = nullptr;
+    std::string buf;
+    char tmp[256];
+    for (int l = 0; l < nseq; l++) {
+        const mem_chain_v &v = chain_ar[l];
+        snprintf(tmp, sizeof tmp, "%s %zu", seq[l].name, v.n);
+        buf += tmp;
+        for (size_t i = 0; i < v.n; i++) {
+            const mem_chain_t &c = v.a[i];
+            snprintf(tmp, sizeof tmp, " [pos=%ld rid=%d n=%d w=%d kept=%d alt=%d first=%d frac=%.6f", (long)c.pos, c.rid, c.n, (int)c.w, (int)c.kept,
+                     (int)c.is_alt, c.first, c.frac_rep);
+            buf += tmp;
+            for (int j = 0; j < c.n; j++) {
+                snprintf(tmp, sizeof tmp, " %d,%d,%ld", c.seeds[j].qbeg, c.seeds[j].len, (long)c.seeds[j].rbeg);
+                buf += tmp;
+            }
+            buf += "]";
+        }
+        buf += "\n";
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!f) f = fopen(path, "w");
+    if (!f) { fprintf(stderr, "[meme_b200] cannot write %s\n", path); exit(EXIT_FAILURE); }
+    fwrite(buf.data(), 1, buf.size(), f);
+    fflush(f);
 }
 
 // Seed extension through the GPU: same contract as getScores8/16 / scalarBandedSWAWrapper (fills the six

@@ -6,13 +6,16 @@
 //   meme_glue_set_prefix   in memoryAllocLearned()            src/fastmap.cpp:L351   (index prefix)
 //   meme_glue_seed_chunk   in mem_process_seqs(), before kt_for(worker_bwt)  src/bwamem.cpp:L1941
 //   meme_glue_take         in mem_kernel1_core_Learned(), around the seeding calls  src/bwamem.cpp:L1366-1397
+//   meme_glue_take_chains  first line of that function's per-read loop: with MEME_B200_CHAIN=1 the read's filtered chains
+//                          come from the GPU and the loop body (seeding, mem_chain_Learned, mem_chain_flt) is skipped  L1249
+//   meme_glue_dump_chains  after that loop (test instrumentation, MEME_B200_DUMP_CHAINS=path)          L1410
 //   meme_glue_bsw          first line of BandedPairWiseSW::getScores8/16 and scalarBandedSWAWrapper
 //                                                             src/bandedSWA.cpp:L242, L412, L1117, L1970, L2664, L3469, L4198
 //                          (per-call seam; reached only by callers other than the chunk-level driver below)
 //   meme_extend_chunk      in mem_process_seqs(), instead of kt_for(worker_aln)     src/bwamem.cpp:L1945
 //                          (defined in meme_extend.inl, which the patched bwamem.cpp includes at its end)
 //
-// Everything is off unless the environment says MEME_B200=1 (seeding) / MEME_B200_BSW=1 (extension), so the
+// Everything is off unless the environment says MEME_B200=1 (seeding) / MEME_B200_CHAIN=1 (+ chaining) / MEME_B200_BSW=1 (extension), so the
 // patched binary is byte-for-byte the reference's behaviour by default.
 #pragma once
 #include <stdint.h>
@@ -21,8 +24,10 @@
 #include "LearnedIndex_seeding.h"
 
 void meme_glue_set_prefix(const char *idx_prefix);
-void meme_glue_seed_chunk(const mem_opt_t *opt, bseq1_t *seqs, int n, int use_learned);
+void meme_glue_seed_chunk(const mem_opt_t *opt, const bntseq_t *bns, bseq1_t *seqs, int n, int use_learned);
 bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits);
+bool meme_glue_take_chains(bseq1_t *s, int l, mem_chain_v *chn);
+void meme_glue_dump_chains(const bseq1_t *seq, int nseq, const mem_chain_v *chain_ar);
 bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
                    int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b);
 

@@ -141,6 +141,67 @@ int meme_seed_counters(meme_index_t *ix, uint64_t counters[8]);
  * [1] offset scans, [2] the hit-materialisation kernel. */
 int meme_seed_last_ms(meme_index_t *ix, float ms[3]);
 
+/* ---- chaining: seeds -> chains -> filtered chains, on the device ---------------- */
+
+/* What the path reads of bntann1_t (src/bntseq.h:L41-49). */
+typedef struct {
+    int64_t offset;
+    int32_t len;
+    int32_t is_alt;
+} meme_contig_t;
+
+/* mem_opt_t fields read by mem_chain_Learned / test_and_merge / mem_chain_flt (defaults of src/bwamem.cpp:L126-162). */
+typedef struct {
+    int32_t w;                  /* [100] band width: seeds join a chain within w of its diagonal   */
+    int32_t max_chain_gap;      /* [10000]                                                         */
+    int32_t max_occ;            /* [500]; must equal the max_occ the seeding run sampled with       */
+    int32_t min_seed_len;       /* [19]                                                            */
+    int32_t min_chain_weight;   /* [0]                                                             */
+    int32_t max_chain_extend;   /* [1<<30]                                                         */
+    float   mask_level;         /* [0.50]                                                          */
+    float   drop_ratio;         /* [0.50]                                                          */
+} meme_chain_opt_t;
+
+/* A seed of a chain: the fields of mem_seed_t that chaining sets (src/bwamem.h:L124-127); score == len. */
+typedef struct {
+    int64_t rbeg;
+    int32_t qbeg, len;
+} meme_chain_seed_t;
+
+/* A chain as mem_chain_flt leaves it (mem_chain_t, src/bwamem.h:L132-139). */
+typedef struct {
+    int64_t pos;                /* rbeg of the first seed (the B-tree key)                         */
+    int64_t seed_beg;           /* its seeds: seeds[seed_beg .. seed_beg + n)                      */
+    int32_t n, rid;
+    int32_t w, first;           /* weight; first shadowed chain (index in the sorted list) or -1   */
+    int32_t kept, is_alt;
+} meme_chain_t;
+
+typedef struct {
+    int64_t n_reads, n_chains, n_seeds;
+    const int64_t           *chain_off;   /* n_reads+1: chains of read r = chains[chain_off[r] .. chain_off[r+1]), in the
+                                             order mem_kernel1_core_Learned leaves them in chain_ar[r]                 */
+    const float             *frac_rep;    /* n_reads                                                               */
+    const meme_chain_t      *chains;
+    const meme_chain_seed_t *seeds;
+} meme_chain_result_t;
+
+/* The contig table (bns->anns, bns->l_pac): seeds bridging two contigs or the forward/reverse boundary are dropped
+ * (bns_intv2rid, src/bntseq.cpp:L408-416), chains never cross contigs, ALT contigs are treated as the filter treats them. */
+int meme_chain_set_contigs(meme_index_t *ix, const meme_contig_t *contigs, int32_t n_contigs, int64_t l_pac);
+/* mem_chain_Learned + mem_chain_flt (src/bwamem.cpp:L1122-1204, L599-717; mem_flt_chained_seeds, L565-597, does nothing
+ * for reads shorter than about 700 bases and is outside this path's 320-base limit) for every read of the last
+ * meme_seed_run, from its device-resident SMEM and hit lists.  That run must have sampled hits with the same max_occ. */
+int meme_chain_run(meme_index_t *ix, const meme_chain_opt_t *opt);
+int meme_chain_download(meme_index_t *ix, meme_chain_result_t *out);        /* synchronises; pinned, owned by the handle */
+/* CUDA-event duration (ms) of the last meme_chain_run. */
+int meme_chain_last_ms(meme_index_t *ix, float *ms);
+/* Seeding + chaining of a chunk across ndev devices (same sharding as meme_seed_batch_multi); only chains and their seeds
+ * travel to the host -- the SMEM and hit lists stay in HBM. */
+int meme_chain_batch_multi(meme_index_t *const *ixs, int ndev, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,
+                           int pair_aligned, const meme_seed_opt_t *seed_opt, const meme_chain_opt_t *chain_opt,
+                           meme_chain_result_t *outs, int64_t *shard_begin);
+
 /* ---- kernel B: banded Smith-Waterman seed extension ------------------------------------------ */
 
 /* Byte-identical to the reference's SeqPair (src/bandedSWA.h:L90-99). */

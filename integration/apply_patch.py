@@ -15,8 +15,17 @@ HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_d
 
 
 def patch_bwamem(src: str) -> str:
-    out, n_seed, n_close, n_chunk, n_inc, n_aln = [], 0, 0, 0, 0, 0
+    out, n_seed, n_close, n_chunk, n_inc, n_aln, n_take, n_dump, in_k1 = [], 0, 0, 0, 0, 0, 0, 0, False
     for line in src.splitlines(keepends=True):
+        if line.startswith("int mem_kernel1_core_Learned("):
+            in_k1 = True
+        if in_k1 and line.strip() == "smems->n = 0;" and not n_take:
+            out.append("        if (meme_glue_take_chains(&seq_[l], l, &chain_ar[l])) continue;   // meme_b200: GPU chains for this read, if any\n")
+            n_take += 1
+        if in_k1 and "tprof[LEARNED_SEED_CHAIN][tid] += __rdtsc() - tim;" in line:
+            out.append("    meme_glue_dump_chains(seq_, nseq, chain_ar);   // meme_b200: test instrumentation (MEME_B200_DUMP_CHAINS)\n")
+            n_dump += 1
+            in_k1 = False
         if line.startswith('#include "bwamem.h"') and not n_inc:
             out.append(line)
             out.append('#include "meme_glue.h"\n')
@@ -33,7 +42,7 @@ def patch_bwamem(src: str) -> str:
             n_close += 1
             continue
         if re.match(r"\s*kt_for\(worker_bwt, &w, n_\);", line):
-            out.append("    meme_glue_seed_chunk(opt, seqs, n_, w.useLearned);   // meme_b200: whole-chunk GPU seeding\n")
+            out.append("    meme_glue_seed_chunk(opt, w.fmi->idx->bns, seqs, n_, w.useLearned);   // meme_b200: whole-chunk GPU seeding (+ chaining)\n")
             out.append(line)
             n_chunk += 1
             continue
@@ -45,7 +54,7 @@ def patch_bwamem(src: str) -> str:
         if line.startswith("void mem_process_seqs(") and not n_aln:
             out.append("bool meme_extend_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
         out.append(line)
-    assert (n_inc, n_seed, n_close, n_chunk, n_aln) == (1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln)
+    assert (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump) == (1, 1, 1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump)
     return "".join(out) + '\n#include "meme_extend.inl"   // meme_b200: chunk-level seed extension\n'
 
 

@@ -1,4 +1,4 @@
-"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c).
+"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c, oracle/chain_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline leg -- never by the product package.
@@ -16,7 +16,7 @@ BUILD = os.path.join(HERE, "_build")
 
 def build(force: bool = False) -> None:
     os.makedirs(BUILD, exist_ok=True)
-    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so")):
+    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so"), ("chain_oracle.c", "liboracle_chain.so")):
         s, o = os.path.join(HERE, src), os.path.join(BUILD, lib)
         if not os.path.exists(s):
             continue
@@ -262,4 +262,85 @@ def run_ref_bsw_shim(binary: str, pairs: np.ndarray, ref: np.ndarray, qer: np.nd
     for k, name in enumerate(RESULT_FIELDS):
         out[name] = res[:, k]
     os.remove(fin); os.remove(fout)
+    return out
+
+
+# ---- chaining oracle (oracle/chain_oracle.c) ----------------------------------------------------------------------------------
+class ChainOpt(C.Structure):
+    _fields_ = [("w", C.c_int32), ("max_chain_gap", C.c_int32), ("max_occ", C.c_int32), ("min_seed_len", C.c_int32),
+                ("min_chain_weight", C.c_int32), ("max_chain_extend", C.c_int32), ("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+class ChainResult(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_chains", C.c_int64), ("n_seeds", C.c_int64), ("chain_off", C.POINTER(C.c_int64)),
+                ("frac_rep", C.POINTER(C.c_float)), ("chains", C.c_void_p), ("seeds", C.c_void_p)]
+
+
+CONTIG_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("is_alt", "<i4")])
+CHAIN_DTYPE = np.dtype([("pos", "<i8"), ("seed_beg", "<i8"), ("n", "<i4"), ("rid", "<i4"), ("w", "<i4"), ("first", "<i4"),
+                        ("kept", "<i4"), ("is_alt", "<i4")])
+CHAIN_SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
+
+
+def default_chain_opt(w: int = 100, max_chain_gap: int = 10000, max_occ: int = 500, min_seed_len: int = 19, min_chain_weight: int = 0,
+                      max_chain_extend: int = 1 << 30, mask_level: float = 0.5, drop_ratio: float = 0.5) -> ChainOpt:
+    """mem_opt_init defaults (src/bwamem.cpp:L126-162)."""
+    return ChainOpt(w, max_chain_gap, max_occ, min_seed_len, min_chain_weight, max_chain_extend, mask_level, drop_ratio)
+
+
+_chain_lib = None
+
+
+def chain_lib():
+    global _chain_lib
+    if _chain_lib is None:
+        build()
+        L = C.CDLL(os.path.join(BUILD, "liboracle_chain.so"))
+        L.oracle_chain_reads.restype = C.POINTER(ChainResult)
+        L.oracle_chain_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                         C.c_int64, C.POINTER(ChainOpt)]
+        L.oracle_chain_result_free.argtypes = [C.POINTER(ChainResult)]
+        _chain_lib = L
+    return _chain_lib
+
+
+def chain_reads(seed_res: dict, read_len: np.ndarray, contigs: np.ndarray, l_pac: int, opt: ChainOpt | None = None) -> dict:
+    """mem_chain_Learned + mem_chain_flt for every read of a seeding result with FULL hit lists (the dict OracleIndex.seed
+    returns; hitbeg relative to the read's list)."""
+    opt = opt or default_chain_opt()
+    L = chain_lib()
+    sm = np.ascontiguousarray(seed_res["smems"])
+    so = np.ascontiguousarray(seed_res["smem_off"], dtype=np.int64)
+    hi = np.ascontiguousarray(seed_res["hits"], dtype=np.uint64)
+    ho = np.ascontiguousarray(seed_res["hit_off"], dtype=np.int64)
+    rl = np.ascontiguousarray(read_len, dtype=np.int32)
+    ct = np.ascontiguousarray(contigs, dtype=CONTIG_DTYPE)
+    assert sm.dtype.itemsize == 24
+    n = len(rl)
+    r = L.oracle_chain_reads(sm.ctypes.data, so.ctypes.data, hi.ctypes.data, ho.ctypes.data, rl.ctypes.data, n, ct.ctypes.data, len(ct),
+                             int(l_pac), C.byref(opt))
+    R = r.contents
+    nc, nsd = int(R.n_chains), int(R.n_seeds)
+    out = {"chain_off": np.ctypeslib.as_array(R.chain_off, shape=(n + 1,)).copy(),
+           "frac_rep": np.ctypeslib.as_array(R.frac_rep, shape=(max(n, 1),))[:n].copy(),
+           "chains": np.frombuffer(C.string_at(R.chains, nc * CHAIN_DTYPE.itemsize), dtype=CHAIN_DTYPE).copy() if nc else np.zeros(0, CHAIN_DTYPE),
+           "seeds": np.frombuffer(C.string_at(R.seeds, nsd * CHAIN_SEED_DTYPE.itemsize), dtype=CHAIN_SEED_DTYPE).copy() if nsd else np.zeros(0, CHAIN_SEED_DTYPE)}
+    L.oracle_chain_result_free(r)
+    return out
+
+
+def chain_lines(res: dict, names=None) -> list[str]:
+    """Canonical text form of a chaining result, one line per read -- the format MEME_B200_DUMP_CHAINS writes
+    (bwa-meme_b200/host/meme_glue.cpp: meme_glue_dump_chains)."""
+    out = []
+    co, ch, sd, fr = res["chain_off"], res["chains"], res["seeds"], res["frac_rep"]
+    for r in range(len(co) - 1):
+        parts = [names[r] if names is not None else str(r), f"{len(range(int(co[r]), int(co[r + 1])))}"]
+        for c in ch[int(co[r]):int(co[r + 1])]:
+            seeds = sd[int(c["seed_beg"]):int(c["seed_beg"]) + int(c["n"])]
+            frac = fr[r]
+            parts.append(f"[pos={int(c['pos'])} rid={int(c['rid'])} n={int(c['n'])} w={int(c['w'])} kept={int(c['kept'])} alt={int(c['is_alt'])} "
+                         f"first={int(c['first'])} frac={float(frac):.6f} " +
+                         " ".join(f"{int(s['qbeg'])},{int(s['len'])},{int(s['rbeg'])}" for s in seeds) + "]")
+        out.append(" ".join(parts))
     return out

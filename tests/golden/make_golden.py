@@ -10,6 +10,9 @@ The fixtures are small and committed; the GPU box only reads them.
   bsw_*.npy             {score,tle,gtle,qle,gscore,max_off} of BandedPairWiseSW::scalarBandedSWAWrapper
   mem7.sam              `bwa-meme mem -7` SAM (minus @PG) for the len150 reads  (end-to-end reference)
   pe_reads.npy, mem7_pe.sam   250 read pairs (codes) and the reference's paired-end SAM for them
+  chains_len*.txt, chains_rep*.txt   chain_ar after mem_chain_Learned + mem_chain_flt (the patched aligner with every hook off runs
+                        the reference's own code; MEME_B200_DUMP_CHAINS prints it): golden read sets, and a repeat-rich
+                        three-contig genome (chains_rep.json) with default options and with -c 8 -W 40 -N 3
   smem_textend.txt      SMEM dump for reads that run into the END of the fwd+RC text of a genome with homopolymer ends
                         (synth.make_genome_textend / make_textend_reads): compare_read_and_ref_binary's text-end branch,
                         src/LearnedIndex_seeding.cpp:L266-273
@@ -65,6 +68,71 @@ def make_textend(work):
         subprocess.run(["timeout", "-s", "KILL", "120", os.path.join(REF, f"learned_seeding_mode3.{ISA}"), fa, fq, "512", "1", "4"],
                        stdout=fo, stderr=subprocess.DEVNULL, check=True)
     json.dump({**TEXTEND, "pad": int(st["pad"]), "n_reads": int(len(offs) - 1)}, open(os.path.join(HERE, "textend.json"), "w"), indent=1)
+
+
+CHAINS_REP = {"length": 120000, "seed": 909, "n_families": 4, "copies": 150, "rep_len": 200, "divergence": 0.02,
+              "tandem_unit": 37, "tandem_copies": 60, "tandem_at": 70000, "contigs": [["c0", 0, 40000, 0], ["c1", 40000, 35000, 1], ["c2", 75000, 45000, 0]],
+              "n_reads": 500, "read_len": 150, "reads_seed": 31, "bits": 14}
+
+
+def chains_rep_genome():
+    """Repeat-rich three-contig genome (the middle contig ALT) for the chaining fixtures: 150-copy dispersed repeats and a
+    tandem array, so that reads carry tens to hundreds of chains (B-tree splits, equal positions, ties in the weight sort)."""
+    m = CHAINS_REP
+    g = synth.make_genome(m["length"], seed=m["seed"], n_families=m["n_families"], copies=m["copies"], rep_len=m["rep_len"],
+                          divergence=m["divergence"])
+    rng = np.random.default_rng(m["seed"] + 1)
+    unit = rng.integers(0, 4, size=m["tandem_unit"], dtype=np.uint8)
+    arr = np.tile(unit, m["tandem_copies"])
+    mut = rng.random(arr.size) < 0.01
+    arr[mut] = (arr[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    g[m["tandem_at"]:m["tandem_at"] + arr.size] = arr
+    return g
+
+
+def chains_rep_reads(g):
+    m = CHAINS_REP
+    codes, offs = synth.make_reads(g, m["n_reads"], m["read_len"], seed=m["reads_seed"], n_frac=0.02)
+    return codes, offs
+
+
+def dump_chains(prefix, fq, out, extra=()):
+    """chain_ar of every read as the UNMODIFIED reference code leaves it: the patched aligner with every hook off."""
+    env = dict(os.environ, MEME_B200_DUMP_CHAINS=out)
+    for k in ("MEME_B200", "MEME_B200_BSW", "MEME_B200_CHAIN"):
+        env.pop(k, None)
+    subprocess.run([os.path.join(REF, f"bwa-meme-b200_mode3.{ISA}"), "mem", "-7", "-t", "1", *extra, prefix, fq, "-o", "/dev/null"], check=True,
+                   capture_output=True, env=env, timeout=600)
+    lines = sorted(open(out).read().splitlines(), key=lambda l: int(l.split()[0][1:]))
+    open(out, "w").write("".join(l + "\n" for l in lines))
+
+
+def make_chains(work, fa, g):
+    """Chain dumps (mem_chain_Learned + mem_chain_flt of the reference) for the golden read sets and the repeat-rich genome."""
+    for rl, n, nf, seed in READ_SETS:
+        dump_chains(fa, os.path.join(work, f"r{rl}.fq"), os.path.join(HERE, f"chains_len{rl}.txt"))
+    m = CHAINS_REP
+    gr = chains_rep_genome()
+    far = os.path.join(work, "rep.fa")
+    with open(far, "wb") as f:
+        for name, off, ln, alt in m["contigs"]:
+            tmp = os.path.join(work, "_c.fa")
+            synth.write_fasta(tmp, gr[off:off + ln], name=name)
+            f.write(open(tmp, "rb").read())
+    subprocess.run([os.path.join(REF, f"bwa-meme_mode3.{ISA}"), "index", "-a", "meme", "-t", "4", far], check=True, capture_output=True, timeout=600)
+    open(far + ".alt", "w").write("".join(f"{name}\t0\t*\t0\t0\t*\t*\t0\t0\t*\t*\n" for name, off, ln, alt in m["contigs"] if alt))
+    mine = os.path.join(work, "rep_mine.fa")
+    index_build.build_index(mine, gr, bits=m["bits"])
+    assert open(mine + ".pos_packed", "rb").read() == open(far + ".pos_packed", "rb").read()
+    for ext in ("_L0_PARAMETERS", "_L1_PARAMETERS", "_L2_PARAMETERS"):
+        open(far + ".suffixarray_uint64" + ext, "wb").write(open(mine + ".suffixarray_uint64" + ext, "rb").read())
+    codes, offs = chains_rep_reads(gr)
+    fq = os.path.join(work, "rep.fq")
+    synth.write_fastq(fq, codes, offs)
+    dump_chains(far, fq, os.path.join(HERE, "chains_rep.txt"))
+    # the same reads with a small max_occ (hit sampling), a chain-weight floor and a chain-extension cap
+    dump_chains(far, fq, os.path.join(HERE, "chains_rep_c8_W40_N3.txt"), extra=("-c", "8", "-W", "40", "-N", "3"))
+    json.dump(m, open(os.path.join(HERE, "chains_rep.json"), "w"), indent=1)
 
 
 def main():
@@ -124,6 +192,7 @@ def main():
                           os.path.join(work, "pe_2.fq")], capture_output=True, text=True, check=True).stdout
     open(os.path.join(HERE, "mem7_pe.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
     make_textend(work)
+    make_chains(work, fa, g)
     shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
     for seed, n, mq, mx, h0m in BSW_SETS:
         pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)
