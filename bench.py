@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the 64-bit-index sub-record")
+    ap.add_argument("--no-chain", action="store_true", help="skip the GPU chaining sub-record")
     ap.add_argument("--no-align", action="store_true", help="skip the end-to-end `mem -7` and kernel-B records")
     ap.add_argument("--align-genome", type=int, default=int(os.environ.get("MEME_BENCH_ALIGN_GENOME", 20_000_000)))
     ap.add_argument("--align-reads", type=int, default=int(os.environ.get("MEME_BENCH_ALIGN_READS", 2_000_000)))
@@ -371,6 +372,35 @@ def main_ours(a):
                 "how": "MEME_FORCE_WIDE=1: 5-byte positions / inverse SA and the WIDE kernel instantiations on the same index and reads"}
         wix.close()
 
+    # ---- chaining + chain filtering on the device-resident lists: seeds -> filtered chains ----
+    chain = None
+    if rank == 0 and world == 1 and not a.no_chain:
+        copt = capi.default_chain_opt()
+        sopt = capi.default_seed_opt(max_occ=copt.max_occ)
+        l_pac = int(ix.sa_num // 2)
+        ix.chain_set_contigs(np.array([(0, l_pac, 0)], dtype=capi.CONTIG_DTYPE), l_pac)     # the synthetic reference is one contig
+        ix.seed_upload_ptr(host.data_ptr(), offs_pinned.data_ptr(), n)
+        ix.seed_run(sopt)
+        ix.chain_run(copt)
+        torch.cuda.synchronize()
+        cms = []
+        c0e, c1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0e.record()
+        for _ in range(3):
+            ix.seed_run(sopt)
+            ix.chain_run(copt)
+            cms.append(ix.chain_last_ms())
+        c1e.record()
+        torch.cuda.synchronize()
+        ctot = ix.chain_download(copy=False)
+        ls, lh = ix.seed_totals()
+        chain = {"k_chain_ms": float(np.mean(cms)), "chained_reads_per_s": n / (float(np.mean(cms)) / 1e3), "seed_plus_chain_reads_per_s": n * 3 / (c0e.elapsed_time(c1e) / 1e3),
+                 "chains": ctot["n_chains"], "chain_seeds": ctot["n_seeds"],
+                 "d2h_bytes_chains": ctot["n_chains"] * 40 + ctot["n_seeds"] * 16 + (n + 1) * 8 + n * 4,
+                 "d2h_bytes_lists_it_replaces": ls * 24 + lh * 8 + 2 * (n + 1) * 8,
+                 "what": "mem_chain_Learned + mem_chain_flt (max_occ 500 sampling) for every read of the batch, one thread per read, on the "
+                         "SMEM / hit lists meme_seed_run left in HBM; only chains and their seeds would travel to the host"}
+
     # ---- totals per rank (counts only; the record gather itself ran inside the timed region above) ----
     summary = mdist.gather_summary(ix, n, world, device)
     summary["record_gather"] = {"inside_timed_region": world > 1, "bytes_into_rank0_per_step": int(gather_bytes) if rank == 0 else None,
@@ -427,6 +457,12 @@ def main_ours(a):
             bytes_per_read = O.bytes_seed(want["counters"], ns * L, a.mode) / ns
             line["parity_sample"] = {"reads": ns, "identical_to_oracle": bool(same), "oracle_s": time.time() - t0,
                                      "oracle_counters_per_read": {k: v / ns for k, v in want["counters"].items()}}
+            if chain is not None:        # chains of the same sample: C ABI vs the chaining oracle on the seeding oracle's lists
+                l_pac = int(ix.sa_num // 2)
+                ct = np.array([(0, l_pac, 0)], dtype=O.CONTIG_DTYPE)
+                cw = O.chain_lines(O.chain_reads(want, np.full(ns, L, np.int32), ct, l_pac))
+                cg = O.chain_lines(ix.chain(sample.reshape(-1), soffs, capi.default_seed_opt(max_occ=500), capi.default_chain_opt()))
+                chain["parity_sample"] = {"reads": ns, "identical_to_oracle": bool(cw == cg)}
             # (b) the reference's own CPU seeding on all host cores, bounded sample
             n_cpu = a.cpu_sample or min(n, max(200_000, 60_000 * cores))
             res = run_reference_cpu(a, prefix, host[:n_cpu].numpy(), 1, 2)
@@ -464,6 +500,7 @@ def main_ours(a):
         else:
             line["roofline"] = None
         line["wide"] = wide
+        line["chain"] = chain
         if world == 1 and not a.no_align:
             try:
                 line["align_e2e"], line["bsw"] = bench_align_and_bsw(a, device, local)

@@ -25,8 +25,14 @@ EXPORTS = [
     "meme_seed_warmup", "meme_seed_copy_device", "meme_seed_download", "meme_seed_totals", "meme_seed_counters", "meme_seed_last_ms", "meme_bsw_create", "meme_bsw_free",
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
+    "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
+
+CONTIG_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("is_alt", "<i4")])
+CHAIN_DTYPE = np.dtype([("pos", "<i8"), ("seed_beg", "<i8"), ("n", "<i4"), ("rid", "<i4"), ("w", "<i4"), ("first", "<i4"),
+                        ("kept", "<i4"), ("is_alt", "<i4")])
+CHAIN_SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
 
 
 class SeedOpt(C.Structure):
@@ -42,6 +48,22 @@ class SeedResult(C.Structure):
 class BswOpt(C.Structure):
     _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
                 ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+class ChainOpt(C.Structure):
+    _fields_ = [("w", C.c_int32), ("max_chain_gap", C.c_int32), ("max_occ", C.c_int32), ("min_seed_len", C.c_int32),
+                ("min_chain_weight", C.c_int32), ("max_chain_extend", C.c_int32), ("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+class ChainResult(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_chains", C.c_int64), ("n_seeds", C.c_int64), ("chain_off", C.c_void_p),
+                ("frac_rep", C.c_void_p), ("chains", C.c_void_p), ("seeds", C.c_void_p)]
+
+
+def default_chain_opt(w: int = 100, max_chain_gap: int = 10000, max_occ: int = 500, min_seed_len: int = 19, min_chain_weight: int = 0,
+                      max_chain_extend: int = 1 << 30, mask_level: float = 0.5, drop_ratio: float = 0.5) -> ChainOpt:
+    """mem_opt_init defaults (reference src/bwamem.cpp:L126-162)."""
+    return ChainOpt(w, max_chain_gap, max_occ, min_seed_len, min_chain_weight, max_chain_extend, mask_level, drop_ratio)
 
 
 def default_seed_opt(rounds: int = 3, min_seed_len: int = 19, split_factor: float = 1.5, split_width: int = 10,
@@ -102,6 +124,11 @@ def lib():
         L.meme_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.meme_pinned_free.argtypes = [vp]
         L.meme_pinned_free.restype = None
+        L.meme_chain_set_contigs.argtypes = [vp, vp, i32, i64]
+        L.meme_chain_run.argtypes = [vp, C.POINTER(ChainOpt)]
+        L.meme_chain_download.argtypes = [vp, C.POINTER(ChainResult)]
+        L.meme_chain_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.meme_chain_batch_multi.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.POINTER(SeedOpt), C.POINTER(ChainOpt), vp, vp]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -234,6 +261,55 @@ class MemeIndex:
         _check(lib().meme_seed_counters(self.h, C.byref(c)), "meme_seed_counters")
         return {"searches": int(c[0]), "block_probes": int(c[1]), "kary_rounds": int(c[2]), "ext_rounds": int(c[3]),
                 "pac_rounds": int(c[4]), "launches": int(c[5]), "reseed_tasks": int(c[6]), "round_trips": int(c[7])}
+
+
+    # ---- chaining (mem_chain_Learned + mem_chain_flt on the device-resident lists of the last seed_run) ----
+    def chain_set_contigs(self, contigs: np.ndarray, l_pac: int):
+        ct = np.ascontiguousarray(contigs, dtype=CONTIG_DTYPE)
+        _check(lib().meme_chain_set_contigs(self.h, ct.ctypes.data, len(ct), int(l_pac)), "meme_chain_set_contigs")
+
+    def chain_run(self, opt: ChainOpt):
+        _check(lib().meme_chain_run(self.h, C.byref(opt)), "meme_chain_run")
+
+    @staticmethod
+    def _wrap_chains(res: ChainResult) -> dict:
+        n, nc, ns = int(res.n_reads), int(res.n_chains), int(res.n_seeds)
+
+        def arr(ptr, count, dt):
+            if count == 0 or not ptr:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer(C.string_at(ptr, count * np.dtype(dt).itemsize), dtype=dt).copy()
+        return {"chain_off": arr(res.chain_off, n + 1, np.int64) if n else np.zeros(1, np.int64), "frac_rep": arr(res.frac_rep, n, np.float32),
+                "chains": arr(res.chains, nc, CHAIN_DTYPE), "seeds": arr(res.seeds, ns, CHAIN_SEED_DTYPE)}
+
+    def chain_download(self, copy: bool = True) -> dict:
+        res = ChainResult()
+        _check(lib().meme_chain_download(self.h, C.byref(res)), "meme_chain_download")
+        if not copy:
+            return {"n_reads": int(res.n_reads), "n_chains": int(res.n_chains), "n_seeds": int(res.n_seeds)}
+        return self._wrap_chains(res)
+
+    def chain_last_ms(self) -> float:
+        ms = C.c_float()
+        _check(lib().meme_chain_last_ms(self.h, C.byref(ms)), "meme_chain_last_ms")
+        return float(ms.value)
+
+    def chain(self, codes: np.ndarray, offsets: np.ndarray, seed_opt: SeedOpt, chain_opt: ChainOpt) -> dict:
+        """Seeding + chaining of a batch through meme_chain_batch_multi on this one device."""
+        return chain_batch_multi([self], codes, offsets, seed_opt, chain_opt)[0][0]
+
+
+def chain_batch_multi(indexes: list, codes: np.ndarray, offsets: np.ndarray, seed_opt: SeedOpt, chain_opt: ChainOpt, pair_aligned: bool = False):
+    """meme_chain_batch_multi: returns ([result dict per device], shard_begin)."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    nd = len(indexes)
+    hs = (C.c_void_p * nd)(*[ix.h for ix in indexes])
+    outs = (ChainResult * nd)()
+    sb = (C.c_int64 * (nd + 1))()
+    _check(lib().meme_chain_batch_multi(hs, nd, codes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, 1 if pair_aligned else 0,
+                                        C.byref(seed_opt), C.byref(chain_opt), outs, sb), "meme_chain_batch_multi")
+    return [MemeIndex._wrap_chains(outs[d]) for d in range(nd)], [int(x) for x in sb]
 
 
 class MemeBsw:

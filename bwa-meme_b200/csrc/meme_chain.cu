@@ -266,6 +266,27 @@ extern "C" int meme_chain_download(meme_index_t *ix, meme_chain_result_t *out)
     return MEME_OK;
 }
 
+// Chains the lists the last meme_seed_warmup left in HBM once and throws the result away: kernels loaded, scratch, output
+// and pinned arrays sized for a chunk of that size.  A one-contig table stands in when none has been set yet.
+extern "C" int meme_chain_warmup(meme_index_t *ix)
+{
+    if (!ix) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    if (!ix->ran || ix->piped || ix->last_opt.max_occ <= 0) return MEME_OK;      // nothing resident to warm up on
+    int rc;
+    ChainWork *c;
+    if ((rc = chain_work(ix, &c))) return rc;
+    const bool dummy = !c->d_contigs;
+    if (dummy) {
+        meme_contig_t one = {0, (int32_t)(ix->v.sa_num / 2 > 0x7fffffff ? 0x7fffffff : ix->v.sa_num / 2), 0};
+        if ((rc = meme_chain_set_contigs(ix, &one, 1, (int64_t)(ix->v.sa_num / 2)))) return rc;
+    }
+    meme_chain_opt_t o = {100, 10000, ix->last_opt.max_occ, 19, 0, 1 << 30, 0.5f, 0.5f};
+    if ((rc = meme_chain_run(ix, &o))) return rc;
+    rc = chain_append(ix, 0, 0, 0);
+    if (dummy) { cudaFree(c->d_contigs); c->d_contigs = nullptr; c->n_contigs = 0; }
+    return rc;
+}
+
 // one device's share of a chunk: sub-batches of MEME_SEED_CHUNK reads, each seeded and chained in HBM; only chains travel
 static int chain_batch_one(meme_index_t *ix, const uint8_t *codes, const int64_t *read_off, int64_t n, const meme_seed_opt_t *so,
                            const meme_chain_opt_t *co, meme_chain_result_t *out)

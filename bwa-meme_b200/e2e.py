@@ -50,9 +50,9 @@ def sam_body(path: str) -> bytes:
 
 def compare_arms(prefix: str, fastqs: list[str], n_reads: int, read_len: int, threads: int, workdir: str, mode: int = 3,
                  gpu_env: dict | None = None, tag: str = "se") -> dict:
-    """reference CPU vs patched aligner with GPU seeding + GPU seed extension on the same FASTQ."""
+    """reference CPU vs patched aligner with GPU seeding + chaining + seed extension on the same FASTQ."""
     ref, b200, _ = binaries(mode)
-    gpu_env = gpu_env or {"MEME_B200": "1", "MEME_B200_BSW": "1"}
+    gpu_env = gpu_env or {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}
     out = {}
     r = run_mem(ref, prefix, fastqs, os.path.join(workdir, f"{tag}_ref.sam"), threads)
     g = run_mem(b200, prefix, fastqs, os.path.join(workdir, f"{tag}_gpu.sam"), threads, gpu_env)

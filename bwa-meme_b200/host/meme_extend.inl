@@ -58,6 +58,7 @@ struct ThreadState {
 
 static std::vector<ThreadState> g_ts;
 static std::vector<int64_t> g_srt_off;  // per read: offset of its first chain in its thread's srt
+static std::vector<int> g_blk_owner;    // per block of reads: the host thread that built its pairs (owner of its srt slice)
 
 static inline void seed_coverage(mem_alnreg_t *a)
 {   // seeds of the chain fully inside the region (L3003-3013)
@@ -266,24 +267,31 @@ bool meme_extend_chunk(worker_t &w, int n)
     if ((int)g_ts.size() < T) g_ts.resize((size_t)T);
     g_srt_off.resize((size_t)n + 1);
     double t0 = omp_get_wtime();
-    // ---- 1. regions + pairs: contiguous shares of the reads, one arena pair per host thread ----
+    // ---- 1. regions + pairs: blocks of reads handed out dynamically (a host thread that shares its core with the aligner's
+    //         reader / writer threads takes fewer), one arena pair per host thread ----
+    const int BLK = 1024, n_blk = (n + BLK - 1) / BLK;
+    g_blk_owner.resize((size_t)n_blk);
 #pragma omp parallel num_threads(T)
     {
         const int t = omp_get_thread_num();
         ThreadState &S = g_ts[(size_t)t];
         S.left.reset(); S.right.reset(); S.srt.clear();
-        const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
         {   // first chunk: the arenas take their typical share (up to 6 pairs per read, 200 + 100 sequence bytes per pair),
             // from the blocks the glue page-locked at index load when it could
-            const int64_t est = (int64_t)(r1 - r0) * 6;
+            const int64_t est = (int64_t)(n / T + 1) * 6;
             for (Arena *A : {&S.left, &S.right}) {
                 Arena::reserve(A->pairs, A->cap, est); if (!by_position) Arena::reserve(A->ref, A->cap_ref, est * 200); Arena::reserve(A->qer, A->cap_qer, est * 100);
                 Arena::reserve(A->w_used, A->cap_w, est);
             }
         }
-        for (int l = r0; l < r1; l++) {
-            g_srt_off[(size_t)l] = (int64_t)S.srt.size();
-            collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S, by_position);
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < n_blk; b++) {
+            g_blk_owner[(size_t)b] = t;
+            const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
+            for (int l = r0; l < r1; l++) {
+                g_srt_off[(size_t)l] = (int64_t)S.srt.size();
+                collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S, by_position);
+            }
         }
     }
     double t1 = omp_get_wtime();
@@ -345,10 +353,17 @@ bool meme_extend_chunk(worker_t &w, int n)
             a->w = max_(a->w, S.right.w_used[k]);
             seed_coverage(a);
         }
-        const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
-        for (int l = r0; l < r1; l++) {
-            purge_contained(opt, &w.seqs[l], &w.chain_ar[l], &w.regs[l], S.srt.data() + g_srt_off[(size_t)l]);
-            finish_read(opt, bns, pac, &w.seqs[l], &w.chain_ar[l], &w.regs[l]);
+        // every region has both sides folded before any read is finished (a block may be finished by another thread than
+        // the one that built its pairs)
+#pragma omp barrier
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < n_blk; b++) {
+            uint32_t *srt = g_ts[(size_t)g_blk_owner[(size_t)b]].srt.data();
+            const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
+            for (int l = r0; l < r1; l++) {
+                purge_contained(opt, &w.seqs[l], &w.chain_ar[l], &w.regs[l], srt + g_srt_off[(size_t)l]);
+                finish_read(opt, bns, pac, &w.seqs[l], &w.chain_ar[l], &w.regs[l]);
+            }
         }
     }
     double t5 = omp_get_wtime();

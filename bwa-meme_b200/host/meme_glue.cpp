@@ -34,6 +34,7 @@ struct Api {
     decltype(&meme_pinned_free) pinned_free = nullptr;
     decltype(&meme_chain_set_contigs) chain_set_contigs = nullptr;
     decltype(&meme_chain_batch_multi) chain_batch_multi = nullptr;
+    decltype(&meme_chain_warmup) chain_warmup = nullptr;
     bool ok = false;
 };
 
@@ -62,7 +63,8 @@ Api &api()
         a.pinned_free = (decltype(a.pinned_free))dlsym(a.so, "meme_pinned_free");
         a.chain_set_contigs = (decltype(a.chain_set_contigs))dlsym(a.so, "meme_chain_set_contigs");
         a.chain_batch_multi = (decltype(a.chain_batch_multi))dlsym(a.so, "meme_chain_batch_multi");
-        a.ok = a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+        a.chain_warmup = (decltype(a.chain_warmup))dlsym(a.so, "meme_chain_warmup");
+        a.ok = a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
                a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
@@ -131,6 +133,7 @@ static void ensure_index()
         for (int d = 0; d < nd; d++) {
             rc = a.seed_warmup(g_index[(size_t)d], warm / nd + 1, 150);
             if (rc) die("meme_seed_warmup", rc);
+            if (env_on("MEME_B200_CHAIN") && (rc = a.chain_warmup(g_index[(size_t)d]))) die("meme_chain_warmup", rc);
         }
         fprintf(stderr, "[meme_b200] warm-up batch of %ld reads in %.2f s\n", warm,
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());

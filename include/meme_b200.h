@@ -196,6 +196,8 @@ int meme_chain_run(meme_index_t *ix, const meme_chain_opt_t *opt);
 int meme_chain_download(meme_index_t *ix, meme_chain_result_t *out);        /* synchronises; pinned, owned by the handle */
 /* CUDA-event duration (ms) of the last meme_chain_run. */
 int meme_chain_last_ms(meme_index_t *ix, float *ms);
+/* After meme_seed_warmup: chains that batch once, so that the first real chunk does not pay for module load and pool sizing. */
+int meme_chain_warmup(meme_index_t *ix);
 /* Seeding + chaining of a chunk across ndev devices (same sharding as meme_seed_batch_multi); only chains and their seeds
  * travel to the host -- the SMEM and hit lists stay in HBM. */
 int meme_chain_batch_multi(meme_index_t *const *ixs, int ndev, const uint8_t *codes, const int64_t *read_off, int64_t n_reads,

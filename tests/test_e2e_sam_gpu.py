@@ -32,7 +32,8 @@ def _run(exe, args, env_extra):
     return sam, p.stderr
 
 
-@pytest.mark.parametrize("hooks", [{"MEME_B200": "1"}, {"MEME_B200": "1", "MEME_B200_BSW": "1"}])
+@pytest.mark.parametrize("hooks", [{"MEME_B200": "1"}, {"MEME_B200": "1", "MEME_B200_BSW": "1"}, {"MEME_B200": "1", "MEME_B200_CHAIN": "1"},
+                                   {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}])
 def test_single_end_sam_identical(pkg, golden_index, golden_reads, tmp_path, hooks):
     from bwa_meme_b200 import synth
     exe = _binary()
@@ -42,7 +43,7 @@ def test_single_end_sam_identical(pkg, golden_index, golden_reads, tmp_path, hoo
     fq = str(tmp_path / "r.fq")
     synth.write_fastq(fq, codes, offs)
     sam, err = _run(exe, [golden_index, fq], hooks)
-    assert "seeded 300 reads on the GPU" in err
+    assert ("seeded and chained 300 reads on the GPU" if "MEME_B200_CHAIN" in hooks else "seeded 300 reads on the GPU") in err
     assert sam == open(os.path.join(GOLDEN, "mem7.sam")).read()
 
 
@@ -59,6 +60,9 @@ def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
     synth.write_fastq(f2, pe[1], offs, prefix="p")
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1"})
     assert "on the GPU" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"})
+    assert "seeded and chained" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
 
 
@@ -93,6 +97,9 @@ def test_high_copy_repeats_sampled_hits_sam_identical(pkg, tmp_path):
     got, err = _run(exe, [prefix, fq], {"MEME_B200": "1"})
     assert "seeded 400 reads on the GPU" in err
     assert got == want
+    got, err = _run(exe, [prefix, fq], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"})
+    assert "seeded and chained 400 reads on the GPU" in err
+    assert got == want
     # the case is really exercised: some SMEM has more than 500 hits
     from bwa_meme_b200 import capi
     ix = capi.MemeIndex(prefix, mode=3)
@@ -120,3 +127,46 @@ def test_two_gpus_sam_identical(pkg, golden_index, tmp_path):
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1", "MEME_B200_DEVICES": "0,1"})
     assert "resident on 2 GPU(s)" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_DEVICES": "0,1"})
+    assert "seeded and chained" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+
+
+def test_chain_dumps_identical_to_reference_code(pkg, tmp_path):
+    """chain_ar after the chaining stage, printed by the same binary: GPU chains (MEME_B200_CHAIN=1) against the reference's
+    own mem_chain_Learned + mem_chain_flt (every hook off), on the repeat-rich three-contig genome of the chaining
+    fixtures, with default options and with -c 8 -W 40 -N 3; and both against the committed dump of the reference."""
+    from bwa_meme_b200 import synth, index_build
+    from chain_util import rep_genome, rep_reads, rep_meta, read_dump
+    exe = _binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/bwa-meme-b200_* not built (needs the reference sources)")
+    m = rep_meta()
+    g = rep_genome(synth)
+    prefix = str(tmp_path / "rep.fa")
+    index_build.build_index(prefix, g, bits=m["bits"])
+    # our builder writes one contig; the fixture has three (the middle one ALT): rewrite .ann / .alt as bwa index would
+    with open(prefix + ".ann", "w") as f:
+        f.write(f"{len(g)} {len(m['contigs'])} 11\n")
+        for name, off, ln, alt in m["contigs"]:
+            f.write(f"0 {name} (null)\n{off} {ln} 0\n")
+    open(prefix + ".amb", "w").write(f"{len(g)} {len(m['contigs'])} 0\n")
+    open(prefix + ".alt", "w").write("".join(f"{name}\t0\t*\t0\t0\t*\t*\t0\t0\t*\t*\n" for name, off, ln, alt in m["contigs"] if alt))
+    codes, offs = rep_reads(synth, g)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, codes, offs)
+
+    def dump(hooks, extra, tag):
+        out = str(tmp_path / f"chains_{tag}.txt")
+        env = dict(hooks, MEME_B200_DUMP_CHAINS=out)
+        sam, err = _run(exe, [*extra, prefix, fq], env)
+        lines = sorted(open(out).read().splitlines(), key=lambda l: int(l.split()[0][1:]))
+        return lines, sam, err
+
+    for extra, golden in (([], "chains_rep.txt"), (["-c", "8", "-W", "40", "-N", "3"], "chains_rep_c8_W40_N3.txt")):
+        cpu, sam_cpu, _ = dump({}, extra, "cpu")
+        gpu, sam_gpu, err = dump({"MEME_B200": "1", "MEME_B200_CHAIN": "1"}, extra, "gpu")
+        assert "seeded and chained 500 reads on the GPU" in err
+        assert cpu == read_dump(golden)
+        assert gpu == cpu
+        assert sam_gpu == sam_cpu
