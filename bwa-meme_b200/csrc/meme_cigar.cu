@@ -1,0 +1,268 @@
+// meme_cigar.cu -- the global alignments of the SAM stage on the device, behind
+// meme_cigar_batch of include/meme_b200.h.
+//
+// Replaces, for all regions of a chunk at once, what mem_reg2aln computes per region when the SAM stage asks for it: the
+// band-doubling loop (src/bwamem.cpp:L2339-2348) around bwa_gen_cigar2 (src/bwa.cpp:L274-361) = ksw_global2
+// (src/ksw.cpp:L560-670) + NM + MD.  meme_cigar_core.cuh has the per-region procedure.
+//
+// One thread per region.  Most regions (three quarters on 150 bp reads) need no matrix at all (equal lengths and an inferred
+// band of 0: the score is a sum over the diagonal); the others fill a banded matrix of a few thousand cells with a byte of
+// backtrack per cell.  Regions are therefore ordered by the size of that matrix before the alignment kernel runs (device
+// radix sort of an 8-bit cost class), so that the 32 regions of a warp do similar work.  Per-region scratch (DP row, backtrack
+// matrix) is carved out of two slice-sized arrays by exclusive scans of the per-region needs; tasks are processed in slices
+// of 2^18 so that the worst case (301 x 301 matrices for every region) stays bounded.  Three kernels per slice:
+// k_cigar_size (needs + cost class), k_cigar_align (alignment, CIGAR length, NM, MD length), k_cigar_emit (compact CIGAR
+// and MD strings at the offsets of a scan).
+#include <cub/cub.cuh>
+#include <vector>
+#include "meme_common.cuh"
+#include "meme_cigar_core.cuh"
+
+using namespace cig;
+
+struct CigarWork {
+    meme_cigar_task_t *d_tasks; size_t cap_tasks;
+    uint8_t *d_codes; size_t cap_codes;
+    int64_t *d_z_off, *d_eh_off, *d_op_off, *d_md_off; size_t cap_z_off, cap_eh_off, cap_op_off, cap_md_off;
+    uint8_t *d_key, *d_key2; gu32 *d_idx, *d_idx2; size_t cap_key, cap_key2, cap_idx, cap_idx2;
+    uint8_t *d_z; size_t cap_z;
+    EH *d_eh; size_t cap_eh;
+    meme_cigar_rec_t *d_recs; size_t cap_recs;
+    gu32 *d_ops; size_t cap_ops;
+    char *d_md; size_t cap_md;
+    u64 *d_ctl;                 // [0] error flag, [1] DP cells
+    meme_cigar_rec_t *h_recs; gu32 *h_ops; char *h_md; size_t hcap_recs, hcap_ops, hcap_md;
+    cudaEvent_t ev[2];
+    float ms; u64 cells;
+    int ran;
+};
+
+void meme_cigar_free(CigarWork *c)
+{
+    if (!c) return;
+    void *dev[] = {c->d_tasks, c->d_codes, c->d_z_off, c->d_eh_off, c->d_op_off, c->d_md_off, c->d_key, c->d_key2, c->d_idx, c->d_idx2,
+                   c->d_z, c->d_eh, c->d_recs, c->d_ops, c->d_md, c->d_ctl};
+    for (void *p : dev) if (p) cudaFree(p);
+    void *host[] = {c->h_recs, c->h_ops, c->h_md};
+    for (void *p : host) if (p) cudaFreeHost(p);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    free(c);
+}
+
+struct CigarArgs {
+    const meme_cigar_task_t *tasks; int64_t n;
+    const uint8_t *codes; int64_t n_codes;
+    const u64 *pac; u64 sa_num; int64_t l_pac;
+    meme_cigar_opt_t opt;
+};
+
+__device__ __forceinline__ bool task_valid(const CigarArgs &A, const meme_cigar_task_t &t)
+{
+    // bwa_gen_cigar2 L285 (empty / bridging the strands) and L287 (bns_get_seq clipped the range); plus what would read
+    // outside the arrays
+    if (t.qlen <= 0 || t.rb >= t.re || (t.rb < A.l_pac && t.re > A.l_pac)) return false;
+    if (t.rb < 0 || t.re > (A.l_pac << 1) || (u64)t.re > A.sa_num) return false;
+    if (t.q_off < 0 || t.q_off + t.qlen > A.n_codes || t.qlen > MEME_MAX_READ_LEN || t.re - t.rb > (1 << 20)) return false;
+    return true;
+}
+
+__device__ __forceinline__ Seqs task_seqs(const CigarArgs &A, const meme_cigar_task_t &t)
+{
+    Seqs S;
+    S.codes = A.codes; S.pac = (const gu64 *)A.pac; S.q_off = t.q_off; S.rb = t.rb; S.qlen = t.qlen; S.tlen = (int)(t.re - t.rb);
+    S.rev = t.rb >= A.l_pac;
+    return S;
+}
+
+__global__ void k_cigar_size(CigarArgs A, int64_t *__restrict__ z_need, int64_t *__restrict__ eh_need, uint8_t *__restrict__ key, gu32 *__restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > A.n) return;
+    if (i == A.n) { z_need[i] = 0; eh_need[i] = 0; return; }
+    const meme_cigar_task_t t = A.tasks[i];
+    int64_t zb = 0, eb = 0;
+    if (task_valid(A, t)) {
+        zb = z_bytes(A.opt, t.qlen, (int)(t.re - t.rb), t.w);
+        eb = t.qlen + 1;
+    }
+    z_need[i] = zb; eh_need[i] = eb;
+    // cost class: heavier first.  0 bytes (no matrix) last; otherwise by log2 of the matrix size
+    int cls = zb == 0 ? 0 : 64 - __clzll((unsigned long long)zb);
+    key[i] = (uint8_t)(255 - cls);
+    idx[i] = (gu32)i;
+}
+
+__global__ void __launch_bounds__(128) k_cigar_align(CigarArgs A, const gu32 *__restrict__ perm, const int64_t *__restrict__ z_off,
+                                                     const int64_t *__restrict__ eh_off, uint8_t *__restrict__ z, EH *__restrict__ eh,
+                                                     meme_cigar_rec_t *__restrict__ recs, int64_t *__restrict__ op_cnt,
+                                                     int64_t *__restrict__ md_cnt, u64 *__restrict__ ctl)
+{
+    const int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix > A.n) return;
+    if (tix == A.n) { op_cnt[A.n] = 0; md_cnt[A.n] = 0; return; }
+    const int64_t i = perm[tix];
+    const meme_cigar_task_t t = A.tasks[i];
+    meme_cigar_rec_t r;
+    r.score = 0; r.nm = -1; r.n_cigar = -1; r.md_len = 0; r.cigar_off = 0; r.md_off = 0;
+    if (task_valid(A, t)) {
+        const Seqs S = task_seqs(A, t);
+        EH *e = eh + eh_off[i];
+        uint8_t *zz = z + z_off[i];
+        int n_ops = 0;
+        gu64 cells = 0;
+        r.score = region_cigar(A.opt, S, t.w, t.truesc, e, zz, &n_ops, &cells);
+        r.n_cigar = n_ops;
+        r.md_len = nm_md(S, reinterpret_cast<const gu32 *>(e), n_ops, nullptr, &r.nm);
+        if (cells) atomicAdd((unsigned long long *)&ctl[1], (unsigned long long)cells);
+    }
+    recs[i] = r;
+    op_cnt[i] = r.n_cigar > 0 ? r.n_cigar : 0;
+    md_cnt[i] = r.md_len;
+}
+
+__global__ void __launch_bounds__(128) k_cigar_emit(CigarArgs A, const int64_t *__restrict__ eh_off, const EH *__restrict__ eh,
+                                                    const int64_t *__restrict__ op_off, const int64_t *__restrict__ md_off,
+                                                    int64_t op_base, int64_t md_base, meme_cigar_rec_t *__restrict__ recs,
+                                                    gu32 *__restrict__ ops_out, char *__restrict__ md_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    meme_cigar_rec_t r = recs[i];
+    r.cigar_off = op_base + op_off[i];
+    r.md_off = md_base + md_off[i];
+    recs[i] = r;
+    if (r.n_cigar <= 0) return;
+    const gu32 *rev = reinterpret_cast<const gu32 *>(eh + eh_off[i]);
+    gu32 *dst = ops_out + op_off[i];
+    for (int k = 0; k < r.n_cigar; k++) dst[k] = rev[r.n_cigar - 1 - k];
+    const Seqs S = task_seqs(A, A.tasks[i]);
+    int nm;
+    nm_md(S, rev, r.n_cigar, md_out + md_off[i], &nm);
+}
+
+static int cigar_work(meme_index_t *ix, CigarWork **out)
+{
+    if (!ix->cigar) {
+        CigarWork *c = (CigarWork *)calloc(1, sizeof(CigarWork));
+        if (!c) return MEME_E_NOMEM;
+        ix->cigar = c;
+        CUDA_TRY(cudaSetDevice(ix->device));
+        CUDA_TRY(cudaMalloc((void **)&c->d_ctl, 16));
+        for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    *out = ix->cigar;
+    return MEME_OK;
+}
+
+static int cigar_grow_pinned(void **p, size_t *cap, size_t need, size_t elem, size_t keep)
+{
+    if (need <= *cap && *p) return MEME_OK;
+    size_t ncap = need + need / 2 + 1024;
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, ncap * elem);
+    if (e != cudaSuccess) { meme_set_error("cudaMallocHost(%zu bytes): %s", ncap * elem, cudaGetErrorString(e)); return MEME_E_NOMEM; }
+    if (*p) { if (keep) memcpy(q, *p, keep * elem); cudaFreeHost(*p); }
+    *p = q; *cap = ncap;
+    return MEME_OK;
+}
+
+static int scan_i64(meme_index_t *ix, int64_t *d, int64_t n, cudaStream_t st)
+{
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d, d, (int)n, st);
+    int rc;
+    if ((rc = meme_grow_device(&ix->d_scan_tmp, &ix->cap_scan_tmp, tmp + 256, 1, st))) return rc;
+    size_t t2 = ix->cap_scan_tmp;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ix->d_scan_tmp, t2, d, d, (int)n, st));
+    return MEME_OK;
+}
+
+extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks, int64_t n_tasks, const uint8_t *codes, int64_t n_codes,
+                                int64_t l_pac, const meme_cigar_opt_t *opt, meme_cigar_result_t *out)
+{
+    if (!ix || !opt || !out || n_tasks < 0 || n_codes < 0 || (n_tasks > 0 && (!tasks || !codes)) || l_pac < 1) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    if ((u64)l_pac * 2 > ix->v.sa_num) { meme_set_error("l_pac %lld does not fit an index of %llu suffixes", (long long)l_pac, ix->v.sa_num); return MEME_E_ARG; }
+    if (opt->e_del <= 0 || opt->e_ins <= 0 || opt->w < 0) { meme_set_error("bad gap extension penalty / band"); return MEME_E_ARG; }
+    CigarWork *c; int rc;
+    if ((rc = cigar_work(ix, &c))) return rc;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    c->ran = 0; c->ms = 0; c->cells = 0;
+    if ((rc = meme_grow_device((void **)&c->d_codes, &c->cap_codes, (size_t)n_codes + 64, 1, st))) return rc;
+    if (n_codes) CUDA_TRY(cudaMemcpyAsync(c->d_codes, codes, (size_t)n_codes, cudaMemcpyHostToDevice, st));
+    if ((rc = cigar_grow_pinned((void **)&c->h_recs, &c->hcap_recs, (size_t)n_tasks + 1, sizeof(meme_cigar_rec_t), 0))) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_ctl, 0, 16, st));
+    const int64_t SLICE = 1 << 18;
+    int64_t op_base = 0, md_base = 0;
+    CUDA_TRY(cudaEventRecord(c->ev[0], st));
+    for (int64_t s0 = 0; s0 < n_tasks; s0 += SLICE) {
+        const int64_t n = n_tasks - s0 < SLICE ? n_tasks - s0 : SLICE;
+        void **grow[] = {(void **)&c->d_tasks, (void **)&c->d_z_off, (void **)&c->d_eh_off, (void **)&c->d_op_off, (void **)&c->d_md_off, (void **)&c->d_key,
+                         (void **)&c->d_key2, (void **)&c->d_idx, (void **)&c->d_idx2, (void **)&c->d_recs};
+        size_t *caps[] = {&c->cap_tasks, &c->cap_z_off, &c->cap_eh_off, &c->cap_op_off, &c->cap_md_off, &c->cap_key, &c->cap_key2, &c->cap_idx, &c->cap_idx2,
+                          &c->cap_recs};
+        size_t elem[] = {sizeof(meme_cigar_task_t), 8, 8, 8, 8, 1, 1, 4, 4, sizeof(meme_cigar_rec_t)};
+        for (int k = 0; k < 10; k++)
+            if ((rc = meme_grow_device(grow[k], caps[k], (size_t)n + 2, elem[k], st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->d_tasks, tasks + s0, (size_t)n * sizeof(meme_cigar_task_t), cudaMemcpyHostToDevice, st));
+        CigarArgs A;
+        A.tasks = c->d_tasks; A.n = n; A.codes = c->d_codes; A.n_codes = n_codes; A.pac = ix->v.pac; A.sa_num = ix->v.sa_num; A.l_pac = l_pac;
+        A.opt = *opt;
+        const unsigned blocks = (unsigned)((n + 1 + 127) / 128);
+        k_cigar_size<<<blocks, 128, 0, st>>>(A, c->d_z_off, c->d_eh_off, c->d_key, c->d_idx);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = scan_i64(ix, c->d_z_off, n + 1, st))) return rc;
+        if ((rc = scan_i64(ix, c->d_eh_off, n + 1, st))) return rc;
+        {
+            size_t tmp = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 8, st);
+            if ((rc = meme_grow_device(&ix->d_scan_tmp, &ix->cap_scan_tmp, tmp + 256, 1, st))) return rc;
+            size_t t2 = ix->cap_scan_tmp;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix->d_scan_tmp, t2, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 8, st));
+        }
+        int64_t tot[2];
+        CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_z_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&tot[1], c->d_eh_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = meme_grow_device((void **)&c->d_z, &c->cap_z, (size_t)tot[0] + 64, 1, st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_eh, &c->cap_eh, (size_t)tot[1] + 8, sizeof(EH), st))) return rc;
+        k_cigar_align<<<blocks, 128, 0, st>>>(A, c->d_idx2, c->d_z_off, c->d_eh_off, c->d_z, c->d_eh, c->d_recs, c->d_op_off, c->d_md_off, c->d_ctl);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = scan_i64(ix, c->d_op_off, n + 1, st))) return rc;
+        if ((rc = scan_i64(ix, c->d_md_off, n + 1, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_op_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&tot[1], c->d_md_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = meme_grow_device((void **)&c->d_ops, &c->cap_ops, (size_t)tot[0] + 8, 4, st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_md, &c->cap_md, (size_t)tot[1] + 8, 1, st))) return rc;
+        k_cigar_emit<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, c->d_eh_off, c->d_eh, c->d_op_off, c->d_md_off, op_base, md_base, c->d_recs,
+                                                               c->d_ops, c->d_md);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = cigar_grow_pinned((void **)&c->h_ops, &c->hcap_ops, (size_t)(op_base + tot[0]) + 1, 4, (size_t)op_base))) return rc;
+        if ((rc = cigar_grow_pinned((void **)&c->h_md, &c->hcap_md, (size_t)(md_base + tot[1]) + 1, 1, (size_t)md_base))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->h_recs + s0, c->d_recs, (size_t)n * sizeof(meme_cigar_rec_t), cudaMemcpyDeviceToHost, st));
+        if (tot[0]) CUDA_TRY(cudaMemcpyAsync(c->h_ops + op_base, c->d_ops, (size_t)tot[0] * 4, cudaMemcpyDeviceToHost, st));
+        if (tot[1]) CUDA_TRY(cudaMemcpyAsync(c->h_md + md_base, c->d_md, (size_t)tot[1], cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        op_base += tot[0]; md_base += tot[1];
+        ix->launches += 3;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[1], st));
+    u64 ctl[2];
+    CUDA_TRY(cudaMemcpyAsync(ctl, c->d_ctl, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventElapsedTime(&c->ms, c->ev[0], c->ev[1]));
+    c->cells = ctl[1];
+    c->ran = 1;
+    out->n_tasks = n_tasks; out->n_ops = op_base; out->n_md = md_base;
+    out->recs = c->h_recs; out->cigars = c->h_ops; out->md = c->h_md;
+    return MEME_OK;
+}
+
+extern "C" int meme_cigar_last(meme_index_t *ix, float *ms, uint64_t *cells)
+{
+    if (!ix || !ix->cigar || !ix->cigar->ran) { meme_set_error("no completed meme_cigar_batch"); return MEME_E_ARG; }
+    if (ms) *ms = ix->cigar->ms;
+    if (cells) *cells = ix->cigar->cells;
+    return MEME_OK;
+}

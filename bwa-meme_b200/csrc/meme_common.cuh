@@ -97,8 +97,11 @@ struct meme_index {
     int piped; int64_t piped_reads;
     // ---- chaining (meme_chain.cu) ----
     struct ChainWork *chain;
+    // ---- global alignment of the SAM stage (meme_cigar.cu) ----
+    struct CigarWork *cigar;
 };
 void meme_chain_free(struct ChainWork *c);
+void meme_cigar_free(struct CigarWork *c);
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);
 int meme_grow_pinned(void **p, size_t *cap, size_t need, size_t elem);

@@ -204,6 +204,51 @@ int meme_chain_batch_multi(meme_index_t *const *ixs, int ndev, const uint8_t *co
                            int pair_aligned, const meme_seed_opt_t *seed_opt, const meme_chain_opt_t *chain_opt,
                            meme_chain_result_t *outs, int64_t *shard_begin);
 
+/* ---- global alignment of the SAM stage: score, CIGAR, NM, MD of every region -------- */
+
+/* One region: what mem_reg2aln hands to bwa_gen_cigar2 (src/bwamem.cpp:L2326-2343). */
+typedef struct {
+    int64_t rb, re;         /* the region on the fwd+RC text                                            */
+    int64_t q_off;          /* first base of the query segment in `codes` (read start + qb)             */
+    int32_t qlen;           /* qe - qb                                                                  */
+    int32_t w;              /* band to start with: max of the two infer_bw values, limited as L2338 does */
+    int32_t truesc;         /* the region's local score (the loop stops once the global score is within a of it) */
+    int32_t pad;
+} meme_cigar_task_t;
+
+typedef struct {
+    int8_t  mat[25];        /* opt->mat (bwa_fill_scmat)                                                */
+    int8_t  pad[3];
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t w;              /* opt->w: the loop never goes beyond a band of 4w                          */
+    int32_t a;              /* opt->a                                                                   */
+} meme_cigar_opt_t;
+
+typedef struct {
+    int32_t score;          /* global alignment score of the final try                                  */
+    int32_t nm;             /* NM                                                                       */
+    int32_t n_cigar;        /* number of CIGAR operations; -1: rejected as bwa_gen_cigar2 rejects it (src/bwa.cpp:L285-287) */
+    int32_t md_len;         /* bytes of the MD string including its NUL                                 */
+    int64_t cigar_off;      /* cigars[cigar_off .. + n_cigar): len << 4 | op, op 0 = M, 1 = I, 2 = D     */
+    int64_t md_off;         /* md + md_off: the MD string                                               */
+} meme_cigar_rec_t;
+
+typedef struct {
+    int64_t n_tasks, n_ops, n_md;
+    const meme_cigar_rec_t *recs;
+    const uint32_t         *cigars;
+    const char             *md;
+} meme_cigar_result_t;
+
+/* For every task: the band-doubling loop of mem_reg2aln (src/bwamem.cpp:L2339-2348) around bwa_gen_cigar2
+ * (src/bwa.cpp:L274-361) = ksw_global2 (src/ksw.cpp:L560-670) + NM/MD.  The reference bases are read from the indexed text
+ * in HBM (l_pac = bns->l_pac), the query bases from `codes` (0..3, 4 = N).  Results are pinned host arrays owned by the
+ * handle, valid until the next call. */
+int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks, int64_t n_tasks, const uint8_t *codes, int64_t n_codes,
+                     int64_t l_pac, const meme_cigar_opt_t *opt, meme_cigar_result_t *out);
+/* CUDA-event duration (ms) of the kernels of the last meme_cigar_batch, and the DP cells they evaluated. */
+int meme_cigar_last(meme_index_t *ix, float *ms, uint64_t *cells);
+
 /* ---- kernel B: banded Smith-Waterman seed extension ------------------------------------------ */
 
 /* Byte-identical to the reference's SeqPair (src/bandedSWA.h:L90-99). */

@@ -1,4 +1,4 @@
-"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c, oracle/chain_oracle.c).
+"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c, oracle/chain_oracle.c, oracle/cigar_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline leg -- never by the product package.
@@ -16,7 +16,7 @@ BUILD = os.path.join(HERE, "_build")
 
 def build(force: bool = False) -> None:
     os.makedirs(BUILD, exist_ok=True)
-    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so"), ("chain_oracle.c", "liboracle_chain.so")):
+    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so"), ("chain_oracle.c", "liboracle_chain.so"), ("cigar_oracle.c", "liboracle_cigar.so")):
         s, o = os.path.join(HERE, src), os.path.join(BUILD, lib)
         if not os.path.exists(s):
             continue
@@ -344,3 +344,108 @@ def chain_lines(res: dict, names=None) -> list[str]:
                          " ".join(f"{int(s['qbeg'])},{int(s['len'])},{int(s['rbeg'])}" for s in seeds) + "]")
         out.append(" ".join(parts))
     return out
+
+
+# ---- SAM-stage alignment oracle (oracle/cigar_oracle.c) -------------------------------------------------------------------------
+class CigarOpt(C.Structure):
+    _fields_ = [("mat", C.c_int8 * 25), ("pad", C.c_int8 * 3), ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32),
+                ("e_ins", C.c_int32), ("w", C.c_int32), ("a", C.c_int32)]
+
+
+class CigarResult(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("n_ops", C.c_int64), ("n_md", C.c_int64), ("recs", C.c_void_p), ("cigars", C.c_void_p),
+                ("md", C.c_void_p)]
+
+
+CIGAR_TASK_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("q_off", "<i8"), ("qlen", "<i4"), ("w", "<i4"), ("truesc", "<i4"), ("pad", "<i4")])
+CIGAR_REC_DTYPE = np.dtype([("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("md_len", "<i4"), ("cigar_off", "<i8"), ("md_off", "<i8")])
+
+
+def default_cigar_opt(a: int = 1, b: int = 4, o_del: int = 6, e_del: int = 1, o_ins: int = 6, e_ins: int = 1, w: int = 100) -> CigarOpt:
+    """bwa_fill_scmat (src/bwa.cpp) + mem_opt_init defaults."""
+    o = CigarOpt()
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            o.mat[k] = a if i == j else -b
+            k += 1
+        o.mat[k] = -1
+        k += 1
+    for j in range(5):
+        o.mat[k] = -1
+        k += 1
+    o.o_del, o.e_del, o.o_ins, o.e_ins, o.w, o.a = o_del, e_del, o_ins, e_ins, w, a
+    return o
+
+
+_cigar_lib = None
+
+
+def cigar_lib():
+    global _cigar_lib
+    if _cigar_lib is None:
+        build()
+        L = C.CDLL(os.path.join(BUILD, "liboracle_cigar.so"))
+        L.oracle_cigar_regions.restype = C.POINTER(CigarResult)
+        L.oracle_cigar_regions.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(CigarOpt)]
+        L.oracle_cigar_result_free.argtypes = [C.POINTER(CigarResult)]
+        L.oracle_infer_w.restype = C.c_int
+        L.oracle_infer_w.argtypes = [C.c_int] * 10
+        _cigar_lib = L
+    return _cigar_lib
+
+
+def infer_w(qlen: int, tlen: int, truesc: int, reg_w: int, opt: CigarOpt | None = None) -> int:
+    opt = opt or default_cigar_opt()
+    return int(cigar_lib().oracle_infer_w(qlen, tlen, truesc, opt.a, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, opt.w, reg_w))
+
+
+def unpack_cigar_result(recs: np.ndarray, cigars: np.ndarray, md: bytes) -> list[dict]:
+    out = []
+    for r in recs:
+        n = int(r["n_cigar"])
+        if n < 0:
+            out.append({"n_cigar": -1})
+            continue
+        c0, m0 = int(r["cigar_off"]), int(r["md_off"])
+        out.append({"score": int(r["score"]), "nm": int(r["nm"]), "n_cigar": n, "cigar": [int(x) for x in cigars[c0:c0 + n]],
+                    "md": md[m0:m0 + int(r["md_len"]) - 1].decode()})
+    return out
+
+
+def cigar_regions(text: np.ndarray, l_pac: int, codes: np.ndarray, tasks: np.ndarray, opt: CigarOpt | None = None) -> list[dict]:
+    """The band-doubling loop of mem_reg2aln around bwa_gen_cigar2 for every task; text = the .0123 codes."""
+    opt = opt or default_cigar_opt()
+    L = cigar_lib()
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    tasks = np.ascontiguousarray(tasks, dtype=CIGAR_TASK_DTYPE)
+    r = L.oracle_cigar_regions(text.ctypes.data, int(l_pac), codes.ctypes.data, tasks.ctypes.data, len(tasks), C.byref(opt))
+    R = r.contents
+    n, no, nm = int(R.n_tasks), int(R.n_ops), int(R.n_md)
+    recs = np.frombuffer(C.string_at(R.recs, n * CIGAR_REC_DTYPE.itemsize), dtype=CIGAR_REC_DTYPE).copy() if n else np.zeros(0, CIGAR_REC_DTYPE)
+    cig = np.frombuffer(C.string_at(R.cigars, no * 4), dtype=np.uint32).copy() if no else np.zeros(0, np.uint32)
+    md = C.string_at(R.md, nm) if nm else b""
+    L.oracle_cigar_result_free(r)
+    return unpack_cigar_result(recs, cig, md)
+
+
+def sam_cigar(raw: dict, qb: int, qe: int, l_query: int, rev: bool) -> dict:
+    """What mem_reg2aln does to bwa_gen_cigar2's CIGAR before it is printed (src/bwamem.cpp:L2354-2379): squeeze a leading or
+    trailing deletion, add the soft clips.  Returns {"cigar", "md", "nm", "pos_shift"}."""
+    cig = list(raw["cigar"])
+    shift = 0
+    if cig:
+        if (cig[0] & 0xf) == 2:
+            shift = cig[0] >> 4
+            cig = cig[1:]
+        elif (cig[-1] & 0xf) == 2:
+            cig = cig[:-1]
+    if qb != 0 or qe != l_query:
+        clip5 = l_query - qe if rev else qb
+        clip3 = qb if rev else l_query - qe
+        if clip5:
+            cig = [clip5 << 4 | 3] + cig
+        if clip3:
+            cig = cig + [clip3 << 4 | 3]
+    return {"cigar": cig, "md": raw["md"], "nm": raw["nm"], "pos_shift": shift}

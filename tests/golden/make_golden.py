@@ -13,6 +13,8 @@ The fixtures are small and committed; the GPU box only reads them.
   chains_len*.txt, chains_rep*.txt   chain_ar after mem_chain_Learned + mem_chain_flt (the patched aligner with every hook off runs
                         the reference's own code; MEME_B200_DUMP_CHAINS prints it): golden read sets, and a repeat-rich
                         three-contig genome (chains_rep.json) with default options and with -c 8 -W 40 -N 3
+  cigar_ref.json        CIGAR / NM / MD / position of the reference's mem_reg2aln (oracle/ref_cigar_shim.cpp) for 1500 regions of the
+                        repeat-rich genome (tests/chain_util.py: make_cigar_cases)
   smem_textend.txt      SMEM dump for reads that run into the END of the fwd+RC text of a genome with homopolymer ends
                         (synth.make_genome_textend / make_textend_reads): compare_read_and_ref_binary's text-end branch,
                         src/LearnedIndex_seeding.cpp:L266-273
@@ -135,6 +137,17 @@ def make_chains(work, fa, g):
     json.dump(m, open(os.path.join(HERE, "chains_rep.json"), "w"), indent=1)
 
 
+def make_cigar(work):
+    """mem_reg2aln of the reference (oracle/ref_cigar_shim.cpp) on regions of the repeat-rich genome of the chaining fixtures."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import chain_util as U
+    gr = chains_rep_genome()
+    codes, cases = U.make_cigar_cases(gr, CHAINS_REP["contigs"], 1500, 4)
+    out = U.run_cigar_shim(os.path.join(REF, f"cigar_shim_mode3.{ISA}"), os.path.join(work, "rep.fa"), codes, cases, work)
+    assert len(out) == len(cases)
+    json.dump(out, open(os.path.join(HERE, "cigar_ref.json"), "w"))
+
+
 def main():
     work = "/tmp/meme_golden"
     os.makedirs(work, exist_ok=True)
@@ -193,6 +206,7 @@ def main():
     open(os.path.join(HERE, "mem7_pe.sam"), "w").write("".join(l + "\n" for l in sam.splitlines() if not l.startswith("@PG")))
     make_textend(work)
     make_chains(work, fa, g)
+    make_cigar(work)
     shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
     for seed, n, mq, mx, h0m in BSW_SETS:
         pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)
