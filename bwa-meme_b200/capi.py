@@ -26,6 +26,7 @@ EXPORTS = [
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
+    "meme_cigar_batch", "meme_cigar_last",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -33,6 +34,8 @@ CONTIG_DTYPE = np.dtype([("offset", "<i8"), ("len", "<i4"), ("is_alt", "<i4")])
 CHAIN_DTYPE = np.dtype([("pos", "<i8"), ("seed_beg", "<i8"), ("n", "<i4"), ("rid", "<i4"), ("w", "<i4"), ("first", "<i4"),
                         ("kept", "<i4"), ("is_alt", "<i4")])
 CHAIN_SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
+CIGAR_TASK_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("q_off", "<i8"), ("qlen", "<i4"), ("w", "<i4"), ("truesc", "<i4"), ("pad", "<i4")])
+CIGAR_REC_DTYPE = np.dtype([("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("md_len", "<i4"), ("cigar_off", "<i8"), ("md_off", "<i8")])
 
 
 class SeedOpt(C.Structure):
@@ -48,6 +51,33 @@ class SeedResult(C.Structure):
 class BswOpt(C.Structure):
     _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
                 ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+class CigarOpt(C.Structure):
+    _fields_ = [("mat", C.c_int8 * 25), ("pad", C.c_int8 * 3), ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32),
+                ("e_ins", C.c_int32), ("w", C.c_int32), ("a", C.c_int32)]
+
+
+class CigarResult(C.Structure):
+    _fields_ = [("n_tasks", C.c_int64), ("n_ops", C.c_int64), ("n_md", C.c_int64), ("recs", C.c_void_p), ("cigars", C.c_void_p),
+                ("md", C.c_void_p)]
+
+
+def default_cigar_opt(a: int = 1, b: int = 4, o_del: int = 6, e_del: int = 1, o_ins: int = 6, e_ins: int = 1, w: int = 100) -> CigarOpt:
+    """bwa_fill_scmat (reference src/bwa.cpp) + mem_opt_init defaults."""
+    o = CigarOpt()
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            o.mat[k] = a if i == j else -b
+            k += 1
+        o.mat[k] = -1
+        k += 1
+    for j in range(5):
+        o.mat[k] = -1
+        k += 1
+    o.o_del, o.e_del, o.o_ins, o.e_ins, o.w, o.a = o_del, e_del, o_ins, e_ins, w, a
+    return o
 
 
 class ChainOpt(C.Structure):
@@ -129,6 +159,8 @@ def lib():
         L.meme_chain_download.argtypes = [vp, C.POINTER(ChainResult)]
         L.meme_chain_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.meme_chain_batch_multi.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.POINTER(SeedOpt), C.POINTER(ChainOpt), vp, vp]
+        L.meme_cigar_batch.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(CigarOpt), C.POINTER(CigarResult)]
+        L.meme_cigar_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -293,6 +325,21 @@ class MemeIndex:
         ms = C.c_float()
         _check(lib().meme_chain_last_ms(self.h, C.byref(ms)), "meme_chain_last_ms")
         return float(ms.value)
+
+    # ---- global alignment of the SAM stage (mem_reg2aln's loop around bwa_gen_cigar2) ----
+    def cigar_batch(self, tasks: np.ndarray, codes: np.ndarray, l_pac: int, opt: CigarOpt | None = None) -> dict:
+        opt = opt or default_cigar_opt()
+        tasks = np.ascontiguousarray(tasks, dtype=CIGAR_TASK_DTYPE)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        res = CigarResult()
+        _check(lib().meme_cigar_batch(self.h, tasks.ctypes.data, len(tasks), codes.ctypes.data, len(codes), int(l_pac), C.byref(opt), C.byref(res)),
+               "meme_cigar_batch")
+        n, no, nm = int(res.n_tasks), int(res.n_ops), int(res.n_md)
+        ms, cells = C.c_float(), C.c_uint64()
+        _check(lib().meme_cigar_last(self.h, C.byref(ms), C.byref(cells)), "meme_cigar_last")
+        return {"recs": np.frombuffer(C.string_at(res.recs, n * CIGAR_REC_DTYPE.itemsize), dtype=CIGAR_REC_DTYPE).copy() if n else np.zeros(0, CIGAR_REC_DTYPE),
+                "cigars": np.frombuffer(C.string_at(res.cigars, no * 4), dtype=np.uint32).copy() if no else np.zeros(0, np.uint32),
+                "md": C.string_at(res.md, nm) if nm else b"", "ms": float(ms.value), "cells": int(cells.value)}
 
     def chain(self, codes: np.ndarray, offsets: np.ndarray, seed_opt: SeedOpt, chain_opt: ChainOpt) -> dict:
         """Seeding + chaining of a batch through meme_chain_batch_multi on this one device."""

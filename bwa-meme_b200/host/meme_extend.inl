@@ -372,3 +372,43 @@ bool meme_extend_chunk(worker_t &w, int n)
             (t4 - t3) * 1e3, (t5 - t4) * 1e3);
     return true;
 }
+
+
+// Called in front of kt_for(worker_sam) in mem_process_seqs: the band-doubling loop of mem_reg2aln around bwa_gen_cigar2
+// (L2339-2348) for EVERY region of the chunk in one device call per GPU.  worker_sam then finds the results through
+// meme_glue_take_cigar; which regions it actually prints (primary, supplementary, XA) is its own business, so all are done.
+void meme_cigar_chunk(worker_t &w, int n)
+{
+    if (!meme_glue_cigar_enabled() || n <= 0) return;
+    const mem_opt_t *opt = w.opt;
+    const int64_t l_pac = w.fmi->idx->bns->l_pac;
+    std::vector<int64_t> task_off((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        int c = 0;
+        const mem_alnreg_v &v = w.regs[i];
+        for (size_t k = 0; k < v.n; k++) if (v.a[k].rb >= 0 && v.a[k].re >= 0) c++;
+        task_off[(size_t)i + 1] = task_off[(size_t)i] + c;
+    }
+    std::vector<meme_cigar_task_t> tasks((size_t)task_off[(size_t)n]);
+    std::vector<int32_t> reg_w((size_t)task_off[(size_t)n]);
+#pragma omp parallel for schedule(static) num_threads(std::max(1, (int)w.nthreads))
+    for (int i = 0; i < n; i++) {
+        const mem_alnreg_v &v = w.regs[i];
+        int64_t t = task_off[(size_t)i];
+        for (size_t k = 0; k < v.n; k++) {
+            const mem_alnreg_t *ar = &v.a[k];
+            if (ar->rb < 0 || ar->re < 0) continue;
+            const int qb = ar->qb, qe = ar->qe;
+            const int64_t rb = ar->rb, re = ar->re;
+            int tmp = infer_bw(qe - qb, re - rb, ar->truesc, opt->a, opt->o_del, opt->e_del);        // L2334-2338
+            int w2 = infer_bw(qe - qb, re - rb, ar->truesc, opt->a, opt->o_ins, opt->e_ins);
+            w2 = w2 > tmp ? w2 : tmp;
+            if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+            meme_cigar_task_t &T = tasks[(size_t)t];
+            T.rb = rb; T.re = re; T.q_off = meme_glue_code_off(i) + qb; T.qlen = qe - qb; T.w = w2; T.truesc = ar->truesc; T.pad = 0;
+            reg_w[(size_t)t] = ar->w;
+            t++;
+        }
+    }
+    meme_glue_cigar_run(tasks, reg_w, task_off, w.seqs, n, opt, l_pac);
+}

@@ -6,8 +6,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include <mutex>
+#include <atomic>
 #include <thread>
 #include <chrono>
 #include "meme_glue.h"
@@ -35,6 +37,7 @@ struct Api {
     decltype(&meme_chain_set_contigs) chain_set_contigs = nullptr;
     decltype(&meme_chain_batch_multi) chain_batch_multi = nullptr;
     decltype(&meme_chain_warmup) chain_warmup = nullptr;
+    decltype(&meme_cigar_batch) cigar_batch = nullptr;
     bool ok = false;
 };
 
@@ -64,7 +67,8 @@ Api &api()
         a.chain_set_contigs = (decltype(a.chain_set_contigs))dlsym(a.so, "meme_chain_set_contigs");
         a.chain_batch_multi = (decltype(a.chain_batch_multi))dlsym(a.so, "meme_chain_batch_multi");
         a.chain_warmup = (decltype(a.chain_warmup))dlsym(a.so, "meme_chain_warmup");
-        a.ok = a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+        a.cigar_batch = (decltype(a.cigar_batch))dlsym(a.so, "meme_cigar_batch");
+        a.ok = a.cigar_batch && a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
                a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
@@ -99,6 +103,17 @@ mem_seed_t *g_seed_arena = nullptr;
 size_t g_seed_arena_cap = 0;
 double g_seed_s = 0;
 long g_seed_reads = 0;
+// MEME_B200_SAM=1: the global alignments of the SAM stage, computed for every region of the chunk before worker_sam runs
+std::vector<uint8_t> g_codes;                   // base codes of the chunk's reads (filled by meme_glue_seed_chunk)
+std::vector<int64_t> g_code_off;
+bool g_have_cigar = false;
+std::vector<meme_cigar_task_t> g_ctasks;
+std::vector<int32_t> g_creg_w;
+std::vector<int64_t> g_ctask_off;               // per read: its tasks
+std::vector<meme_cigar_result_t> g_cres;        // per device
+std::vector<int64_t> g_cres_begin;              // first task of each device's share
+std::vector<std::pair<const char *, int>> g_cptr;   // (seqs[i].seq, i), sorted by pointer
+std::atomic<long> g_cig_hit{0}, g_cig_miss{0};   // lookups of mem_reg2aln answered from the GPU results / left to its own code
 
 [[noreturn]] void die(const char *what, int rc)
 {
@@ -165,8 +180,9 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, const bntseq_t *bns, bseq1_t *se
     auto t0 = std::chrono::steady_clock::now();
     // base codes: nst_nt4_table of the ASCII read; worker_bwt converts seqs[i].seq in place later
     // (src/bwamem.cpp:L1277-1280) and later stages rely on that, so the reads are not touched here
-    static std::vector<uint8_t> codes;
-    static std::vector<int64_t> off;
+    std::vector<uint8_t> &codes = g_codes;
+    std::vector<int64_t> &off = g_code_off;
+    g_have_cigar = false;
     off.resize((size_t)n + 1);
     size_t tot = 0;
     for (int i = 0; i < n; i++) { off[i] = (int64_t)tot; tot += (size_t)seqs[i].l_seq; }
@@ -361,6 +377,90 @@ void meme_glue_dump_chains(const bseq1_t *seq, int nseq, const mem_chain_v *chai
     if (!f) { fprintf(stderr, "[meme_b200] cannot write %s\n", path); exit(EXIT_FAILURE); }
     fwrite(buf.data(), 1, buf.size(), f);
     fflush(f);
+}
+
+// ---- SAM stage: CIGAR / NM / MD of every region of the chunk from the GPU (MEME_B200_SAM=1) ----
+bool meme_glue_cigar_enabled()
+{
+    return env_on("MEME_B200_SAM") && (g_have || g_have_chains) && !g_index.empty();
+}
+
+int64_t meme_glue_code_off(int read) { return g_code_off[(size_t)read]; }
+
+// tasks: every region of the chunk (task_off[i] .. task_off[i+1] are read i's); reg_w: the regions' ar->w.  One
+// meme_cigar_batch per device on contiguous shares; the results stay in the handles' pinned arrays until the next chunk.
+void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
+                         int n_reads, const mem_opt_t *opt, int64_t l_pac)
+{
+    Api &a = api();
+    auto t0 = std::chrono::steady_clock::now();
+    g_ctasks.swap(tasks); g_creg_w.swap(reg_w); g_ctask_off.swap(task_off);
+    const int64_t n = (int64_t)g_ctasks.size();
+    const int nd = (int)g_index.size();
+    meme_cigar_opt_t co;
+    memset(&co, 0, sizeof co);
+    for (int k = 0; k < 25; k++) co.mat[k] = opt->mat[k];
+    co.o_del = opt->o_del; co.e_del = opt->e_del; co.o_ins = opt->o_ins; co.e_ins = opt->e_ins; co.w = opt->w; co.a = opt->a;
+    g_cres.resize((size_t)nd);
+    g_cres_begin.assign((size_t)nd + 1, 0);
+    for (int d = 0; d <= nd; d++) g_cres_begin[(size_t)d] = n * d / nd;
+    std::vector<int> rc((size_t)nd, 0);
+    std::vector<std::string> err((size_t)nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++)
+        th.emplace_back([&, d] {
+            const int64_t b = g_cres_begin[(size_t)d], e = g_cres_begin[(size_t)d + 1];
+            rc[(size_t)d] = a.cigar_batch(g_index[(size_t)d], g_ctasks.data() + b, e - b, g_codes.data(), (int64_t)g_code_off[(size_t)n_reads], l_pac, &co,
+                                          &g_cres[(size_t)d]);
+            if (rc[(size_t)d]) err[(size_t)d] = a.last_error();
+        });
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rc[(size_t)d]) { fprintf(stderr, "[meme_b200] meme_cigar_batch failed (%d): %s\n", rc[(size_t)d], err[(size_t)d].c_str()); exit(EXIT_FAILURE); }
+    g_cptr.resize((size_t)n_reads);
+    for (int i = 0; i < n_reads; i++) g_cptr[(size_t)i] = {seqs[i].seq, i};
+    std::sort(g_cptr.begin(), g_cptr.end());
+    g_have_cigar = true;
+    static bool at_exit = false;
+    if (!at_exit) {
+        at_exit = true;
+        atexit([] { fprintf(stderr, "[meme_b200] SAM stage: %ld alignments taken from the GPU results, %ld computed by mem_reg2aln itself "
+                            "(regions created after the pre-pass: mate rescue)\n", g_cig_hit.load(), g_cig_miss.load()); });
+    }
+    long ops = 0;
+    for (auto &r : g_cres) ops += (long)r.n_ops;
+    fprintf(stderr, "[meme_b200] global alignments of %ld regions on the GPU: %ld CIGAR operations, %.1f ms\n", (long)n, ops,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+}
+
+// mem_reg2aln asks for one region's alignment: true = *cigar (malloc'ed: n_cigar operations followed by the MD string, as
+// bwa_gen_cigar2 returns it), *n_cigar and *NM are set and the caller skips its own loop.  Regions the pre-pass has not seen
+// (created later by mate rescue) return false and take the caller's own code.
+bool meme_glue_take_cigar(const char *query, const mem_alnreg_t *ar, uint32_t **cigar, int *n_cigar, int *NM)
+{
+    if (!g_have_cigar) return false;
+    auto it = std::lower_bound(g_cptr.begin(), g_cptr.end(), std::make_pair(query, 0));
+    if (it == g_cptr.end() || it->first != query) { g_cig_miss++; return false; }
+    const int i = it->second;
+    for (int64_t t = g_ctask_off[(size_t)i]; t < g_ctask_off[(size_t)i + 1]; t++) {
+        const meme_cigar_task_t &k = g_ctasks[(size_t)t];
+        if (k.rb != ar->rb || k.re != ar->re || k.truesc != ar->truesc || g_creg_w[(size_t)t] != ar->w) continue;
+        if (k.q_off != g_code_off[(size_t)i] + ar->qb || k.qlen != ar->qe - ar->qb) continue;
+        size_t d = 0;
+        while (d + 1 < g_cres.size() && t >= g_cres_begin[d + 1]) d++;
+        const meme_cigar_result_t &R = g_cres[d];
+        const meme_cigar_rec_t &r = R.recs[t - g_cres_begin[d]];
+        if (r.n_cigar < 0) { g_cig_miss++; return false; }
+        g_cig_hit++;
+        uint32_t *c = (uint32_t *)malloc((size_t)r.n_cigar * 4 + (size_t)r.md_len);
+        if (!c) { fprintf(stderr, "[meme_b200] out of memory (cigar)\n"); exit(EXIT_FAILURE); }
+        memcpy(c, R.cigars + r.cigar_off, (size_t)r.n_cigar * 4);
+        memcpy(c + r.n_cigar, R.md + r.md_off, (size_t)r.md_len);
+        *cigar = c; *n_cigar = r.n_cigar; *NM = r.nm;
+        return true;
+    }
+    g_cig_miss++;
+    return false;
 }
 
 // Seed extension through the GPU: same contract as getScores8/16 / scalarBandedSWAWrapper (fills the six

@@ -9,6 +9,10 @@
 //   meme_glue_take_chains  first line of that function's per-read loop: with MEME_B200_CHAIN=1 the read's filtered chains
 //                          come from the GPU and the loop body (seeding, mem_chain_Learned, mem_chain_flt) is skipped  L1249
 //   meme_glue_dump_chains  after that loop (test instrumentation, MEME_B200_DUMP_CHAINS=path)          L1410
+//   meme_cigar_chunk       in mem_process_seqs(), before kt_for(worker_sam): with MEME_B200_SAM=1 the global alignment (score,
+//                          CIGAR, NM, MD) of every region of the chunk is computed on the GPU   src/bwamem.cpp:L1962
+//   meme_glue_take_cigar   in mem_reg2aln(), in front of the band-doubling loop around bwa_gen_cigar2: a region the pre-pass
+//                          has seen takes its result from there                                  src/bwamem.cpp:L2339
 //   meme_glue_bsw          first line of BandedPairWiseSW::getScores8/16 and scalarBandedSWAWrapper
 //                                                             src/bandedSWA.cpp:L242, L412, L1117, L1970, L2664, L3469, L4198
 //                          (per-call seam; reached only by callers other than the chunk-level driver below)
@@ -28,10 +32,17 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, const bntseq_t *bns, bseq1_t *se
 bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits);
 bool meme_glue_take_chains(bseq1_t *s, int l, mem_chain_v *chn);
 void meme_glue_dump_chains(const bseq1_t *seq, int nseq, const mem_chain_v *chain_ar);
+bool meme_glue_take_cigar(const char *query, const mem_alnreg_t *ar, uint32_t **cigar, int *n_cigar, int *NM);
 bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
                    int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b);
 
 // used by meme_extend.inl
+#include <vector>
+#include "../../include/meme_b200.h"
+bool meme_glue_cigar_enabled();
+int64_t meme_glue_code_off(int read);
+void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
+                         int n_reads, const mem_opt_t *opt, int64_t l_pac);
 bool meme_glue_bsw_enabled();
 bool meme_glue_bsw_text_mode();
 void meme_glue_pinned_reserve(int threads, long reads_per_chunk);

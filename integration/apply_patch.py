@@ -16,7 +16,22 @@ HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_d
 
 def patch_bwamem(src: str) -> str:
     out, n_seed, n_close, n_chunk, n_inc, n_aln, n_take, n_dump, in_k1 = [], 0, 0, 0, 0, 0, 0, 0, False
+    n_sam, n_cig, n_cig_end, in_r2a = 0, 0, 0, False
     for line in src.splitlines(keepends=True):
+        if line.startswith("mem_aln_t mem_reg2aln("):
+            in_r2a = True
+        if in_r2a and line.strip() == "i = 0; a.cigar = 0;" and not n_cig:
+            out.append("    if (meme_glue_take_cigar(query_, ar, &a.cigar, &a.n_cigar, &NM)) goto meme_cigar_done;   // meme_b200: GPU alignment of this region, if any\n")
+            n_cig += 1
+        if in_r2a and line.strip() == "} while (++i < 3 && score < ar->truesc - opt->a);" and not n_cig_end:
+            out.append(line)
+            out.append("meme_cigar_done:;   // meme_b200\n")
+            n_cig_end += 1
+            in_r2a = False
+            continue
+        if re.match(r"\s*kt_for\(worker_sam, &w,\s+n_\);", line):
+            out.append("    meme_cigar_chunk(w, n_);   // meme_b200: global alignments of all regions on the GPU\n")
+            n_sam += 1
         if line.startswith("int mem_kernel1_core_Learned("):
             in_k1 = True
         if in_k1 and line.strip() == "smems->n = 0;" and not n_take:
@@ -53,8 +68,10 @@ def patch_bwamem(src: str) -> str:
             continue
         if line.startswith("void mem_process_seqs(") and not n_aln:
             out.append("bool meme_extend_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
+            out.append("void meme_cigar_chunk(worker_t &w, int n);    // meme_b200 (meme_extend.inl)\n")
         out.append(line)
     assert (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump) == (1, 1, 1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump)
+    assert (n_sam, n_cig, n_cig_end) == (1, 1, 1), (n_sam, n_cig, n_cig_end)
     return "".join(out) + '\n#include "meme_extend.inl"   // meme_b200: chunk-level seed extension\n'
 
 

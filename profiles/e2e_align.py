@@ -41,7 +41,8 @@ lib = os.path.join(ROOT, "bwa-meme_b200", "libmeme_b200.so")
 sams = {}
 arms = [("reference_cpu", ref, {}), ("gpu_seed", b200, {"MEME_B200": "1"}),
         ("gpu_seed_bsw", b200, {"MEME_B200": "1", "MEME_B200_BSW": "1"}),
-        ("gpu_seed_chain_bsw", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"})]
+        ("gpu_seed_chain_bsw", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}),
+        ("gpu_all", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"})]
 if os.environ.get("ARMS"):
     arms = [a for a in arms if a[0] in os.environ["ARMS"].split(",") or a[0] == "reference_cpu"]
 nreads = N * (2 if PE else 1)
@@ -49,7 +50,7 @@ for name, exe, env in arms:
     e = dict(os.environ); e.update(env); e["MEME_B200_LIB"] = lib
     if os.environ.get("DEVICES") and name != "reference_cpu":
         e["MEME_B200_DEVICES"] = os.environ["DEVICES"]      # reads and extension pairs shard across these GPUs
-    if name.endswith("_bsw") and os.environ.get("DUMP"):
+    if (name.endswith("_bsw") or name == "gpu_all") and os.environ.get("DUMP"):
         e["MEME_B200_DUMP_PAIRS"] = os.environ["DUMP"]
     t0 = time.time()
     p = subprocess.run([exe, "mem", "-7", "-t", T, "-K", "100000000", prefix, *fqs, "-o", f"{d}/{name}.sam"], capture_output=True, text=True, env=e)
@@ -63,6 +64,8 @@ for name, exe, env in arms:
     gpu_lines = [l for l in p.stderr.splitlines() if "[meme_b200] seeded" in l]
     out["seed_stage_ms_per_chunk"] = [float(l.split("meme_")[-1].split()[1]) for l in gpu_lines if "this chunk" in l]
     if gpu_lines: out["gpu_seed_log"] = gpu_lines[-1]
+    cig_lines = [l for l in p.stderr.splitlines() if "[meme_b200] global alignments" in l]
+    if cig_lines: out["gpu_cigar_log"] = cig_lines[-1]
     ext_lines = [l for l in p.stderr.splitlines() if "[meme_b200] extended" in l]
     if ext_lines: out["gpu_extend_log"] = ext_lines[-1]
     if os.environ.get("E2E_VERBOSE"):

@@ -33,7 +33,9 @@ def _run(exe, args, env_extra):
 
 
 @pytest.mark.parametrize("hooks", [{"MEME_B200": "1"}, {"MEME_B200": "1", "MEME_B200_BSW": "1"}, {"MEME_B200": "1", "MEME_B200_CHAIN": "1"},
-                                   {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}])
+                                   {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"},
+                                   {"MEME_B200": "1", "MEME_B200_SAM": "1"},
+                                   {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"}])
 def test_single_end_sam_identical(pkg, golden_index, golden_reads, tmp_path, hooks):
     from bwa_meme_b200 import synth
     exe = _binary()
@@ -44,6 +46,8 @@ def test_single_end_sam_identical(pkg, golden_index, golden_reads, tmp_path, hoo
     synth.write_fastq(fq, codes, offs)
     sam, err = _run(exe, [golden_index, fq], hooks)
     assert ("seeded and chained 300 reads on the GPU" if "MEME_B200_CHAIN" in hooks else "seeded 300 reads on the GPU") in err
+    if "MEME_B200_SAM" in hooks:
+        assert "global alignments of" in err
     assert sam == open(os.path.join(GOLDEN, "mem7.sam")).read()
 
 
@@ -63,6 +67,10 @@ def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"})
     assert "seeded and chained" in err
+    assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+    # + the global alignments of the SAM stage; regions created later by mate rescue take the reference's own code
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"})
+    assert "global alignments of" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
 
 
@@ -100,6 +108,9 @@ def test_high_copy_repeats_sampled_hits_sam_identical(pkg, tmp_path):
     got, err = _run(exe, [prefix, fq], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"})
     assert "seeded and chained 400 reads on the GPU" in err
     assert got == want
+    got, err = _run(exe, [prefix, fq], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"})
+    assert "global alignments of" in err            # reads in 900-copy repeats: many regions per read, XA candidates
+    assert got == want
     # the case is really exercised: some SMEM has more than 500 hits
     from bwa_meme_b200 import capi
     ix = capi.MemeIndex(prefix, mode=3)
@@ -127,8 +138,9 @@ def test_two_gpus_sam_identical(pkg, golden_index, tmp_path):
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_BSW": "1", "MEME_B200_DEVICES": "0,1"})
     assert "resident on 2 GPU(s)" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
-    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_DEVICES": "0,1"})
-    assert "seeded and chained" in err
+    sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1",
+                                                  "MEME_B200_DEVICES": "0,1"})
+    assert "seeded and chained" in err and "global alignments of" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
 
 
