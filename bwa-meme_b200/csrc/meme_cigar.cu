@@ -7,14 +7,18 @@
 //
 // One thread per region.  Most regions (three quarters on 150 bp reads) need no matrix at all (equal lengths and an inferred
 // band of 0: the score is a sum over the diagonal); the others fill a banded matrix of a few thousand cells with a byte of
-// backtrack per cell.  Regions are therefore ordered by the size of that matrix before the alignment kernel runs (device
-// radix sort of an 8-bit cost class), so that the 32 regions of a warp do similar work.  Per-region scratch (DP row, backtrack
-// matrix) is carved out of two slice-sized arrays by exclusive scans of the per-region needs; tasks are processed in slices
-// of 2^18 so that the worst case (301 x 301 matrices for every region) stays bounded.  Three kernels per slice:
-// k_cigar_size (needs + cost class), k_cigar_align (alignment, CIGAR length, NM, MD length), k_cigar_emit (compact CIGAR
-// and MD strings at the offsets of a scan).
+// backtrack per cell.  Regions are ordered by (band of the first try, reference length) before the alignment kernel runs
+// (device radix sort of a 16-bit key), so that the 32 regions of a warp walk the same rows and columns at the same time, and
+// a warp's scratch -- DP rows, backtrack matrices, oriented queries -- is interleaved lane by lane: element k of lane l sits
+// at [k * 32 + l], so a step of the warp touches one 256-byte line of DP cells and one 32-byte sector of backtrack bytes (the
+// first version gave every region its own contiguous arrays: 6 Gcells/s; see profiles/r2/README.md).  Warp scratch is carved
+// out of slice-sized arrays by exclusive scans of the per-warp maxima; tasks are processed in slices of 2^18 so that the
+// worst case (301 x 301 matrices for every region) stays bounded.  Four kernels per slice: k_cigar_size (needs + sort key),
+// k_cigar_group (per-warp maxima), k_cigar_align (alignment, CIGAR length, NM, MD length), k_cigar_emit (compact CIGAR and
+// MD strings at the offsets of a scan).
 #include <cub/cub.cuh>
 #include <vector>
+#include <chrono>
 #include "meme_common.cuh"
 #include "meme_cigar_core.cuh"
 
@@ -23,9 +27,10 @@ using namespace cig;
 struct CigarWork {
     meme_cigar_task_t *d_tasks; size_t cap_tasks;
     uint8_t *d_codes; size_t cap_codes;
-    int64_t *d_z_off, *d_eh_off, *d_op_off, *d_md_off; size_t cap_z_off, cap_eh_off, cap_op_off, cap_md_off;
-    uint8_t *d_key, *d_key2; gu32 *d_idx, *d_idx2; size_t cap_key, cap_key2, cap_idx, cap_idx2;
-    uint8_t *d_z; size_t cap_z;
+    int64_t *d_z_off, *d_op_off, *d_md_off; size_t cap_z_off, cap_op_off, cap_md_off;
+    uint16_t *d_key, *d_key2; gu32 *d_idx, *d_idx2, *d_slot; size_t cap_key, cap_key2, cap_idx, cap_idx2, cap_slot;
+    int64_t *d_g_rows, *d_g_z; size_t cap_g_rows, cap_g_z;
+    uint8_t *d_z, *d_q; size_t cap_z, cap_q;
     EH *d_eh; size_t cap_eh;
     meme_cigar_rec_t *d_recs; size_t cap_recs;
     gu32 *d_ops; size_t cap_ops;
@@ -40,8 +45,8 @@ struct CigarWork {
 void meme_cigar_free(CigarWork *c)
 {
     if (!c) return;
-    void *dev[] = {c->d_tasks, c->d_codes, c->d_z_off, c->d_eh_off, c->d_op_off, c->d_md_off, c->d_key, c->d_key2, c->d_idx, c->d_idx2,
-                   c->d_z, c->d_eh, c->d_recs, c->d_ops, c->d_md, c->d_ctl};
+    void *dev[] = {c->d_tasks, c->d_codes, c->d_z_off, c->d_op_off, c->d_md_off, c->d_key, c->d_key2, c->d_idx, c->d_idx2, c->d_slot,
+                   c->d_g_rows, c->d_g_z, c->d_z, c->d_q, c->d_eh, c->d_recs, c->d_ops, c->d_md, c->d_ctl};
     for (void *p : dev) if (p) cudaFree(p);
     void *host[] = {c->h_recs, c->h_ops, c->h_md};
     for (void *p : host) if (p) cudaFreeHost(p);
@@ -66,34 +71,68 @@ __device__ __forceinline__ bool task_valid(const CigarArgs &A, const meme_cigar_
     return true;
 }
 
-__device__ __forceinline__ Seqs task_seqs(const CigarArgs &A, const meme_cigar_task_t &t)
+__global__ void k_cigar_size(CigarArgs A, int64_t *__restrict__ z_need, uint16_t *__restrict__ key, gu32 *__restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const meme_cigar_task_t t = A.tasks[i];
+    int64_t zb = 0;
+    int fb = 0, tl = 0;
+    if (task_valid(A, t)) {
+        tl = (int)(t.re - t.rb);
+        zb = z_bytes(A.opt, t.qlen, tl, t.w);
+        fb = first_band(A.opt, t.qlen, tl, t.w);
+    }
+    z_need[i] = zb;
+    // widest band first, longest reference first within a band; regions without a matrix last
+    const int kb = fb > 255 ? 255 : fb, kt = (tl >> 1) > 255 ? 255 : tl >> 1;
+    key[i] = (uint16_t)((255 - kb) << 8 | (255 - kt));
+    idx[i] = (gu32)i;
+}
+
+// one thread per group of 32 regions (a warp of the alignment kernel): rows of the DP row / query arrays and backtrack bytes
+// the group needs = the maxima over its regions
+__global__ void k_cigar_group(CigarArgs A, const gu32 *__restrict__ perm, const int64_t *__restrict__ z_need, int64_t n_groups,
+                              int64_t *__restrict__ g_rows, int64_t *__restrict__ g_z)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    int64_t rows = 0, zb = 0;
+    if (g < n_groups)
+        for (int l = 0; l < 32; l++) {
+            const int64_t tix = g * 32 + l;
+            if (tix >= A.n) break;
+            const int64_t i = perm[tix];
+            const meme_cigar_task_t t = A.tasks[i];
+            if (!task_valid(A, t)) continue;
+            rows = rows > t.qlen + 1 ? rows : t.qlen + 1;
+            zb = zb > z_need[i] ? zb : z_need[i];
+        }
+    g_rows[g] = rows; g_z[g] = zb;
+}
+
+struct CigarScratch { EH *eh; uint8_t *z, *q; const int64_t *g_rows, *g_z; };
+
+__device__ __forceinline__ Scr lane_scratch(const CigarScratch &W, int64_t tix)
+{
+    const int64_t g = tix >> 5, lane = tix & 31;
+    Scr C;
+    C.eh = W.eh + W.g_rows[g] * 32 + lane;
+    C.q = W.q + W.g_rows[g] * 32 + lane;
+    C.z = W.z + W.g_z[g] * 32 + lane;
+    C.stride = 32;
+    return C;
+}
+
+__device__ __forceinline__ Seqs task_seqs(const CigarArgs &A, const meme_cigar_task_t &t, const Scr &C)
 {
     Seqs S;
-    S.codes = A.codes; S.pac = (const gu64 *)A.pac; S.q_off = t.q_off; S.rb = t.rb; S.qlen = t.qlen; S.tlen = (int)(t.re - t.rb);
+    S.qs = C.q; S.stride = C.stride; S.pac = (const gu64 *)A.pac; S.rb = t.rb; S.qlen = t.qlen; S.tlen = (int)(t.re - t.rb);
     S.rev = t.rb >= A.l_pac;
     return S;
 }
 
-__global__ void k_cigar_size(CigarArgs A, int64_t *__restrict__ z_need, int64_t *__restrict__ eh_need, uint8_t *__restrict__ key, gu32 *__restrict__ idx)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > A.n) return;
-    if (i == A.n) { z_need[i] = 0; eh_need[i] = 0; return; }
-    const meme_cigar_task_t t = A.tasks[i];
-    int64_t zb = 0, eb = 0;
-    if (task_valid(A, t)) {
-        zb = z_bytes(A.opt, t.qlen, (int)(t.re - t.rb), t.w);
-        eb = t.qlen + 1;
-    }
-    z_need[i] = zb; eh_need[i] = eb;
-    // cost class: heavier first.  0 bytes (no matrix) last; otherwise by log2 of the matrix size
-    int cls = zb == 0 ? 0 : 64 - __clzll((unsigned long long)zb);
-    key[i] = (uint8_t)(255 - cls);
-    idx[i] = (gu32)i;
-}
-
-__global__ void __launch_bounds__(128) k_cigar_align(CigarArgs A, const gu32 *__restrict__ perm, const int64_t *__restrict__ z_off,
-                                                     const int64_t *__restrict__ eh_off, uint8_t *__restrict__ z, EH *__restrict__ eh,
+__global__ void __launch_bounds__(128) k_cigar_align(CigarArgs A, CigarScratch W, const gu32 *__restrict__ perm, gu32 *__restrict__ slot,
                                                      meme_cigar_rec_t *__restrict__ recs, int64_t *__restrict__ op_cnt,
                                                      int64_t *__restrict__ md_cnt, u64 *__restrict__ ctl)
 {
@@ -101,18 +140,19 @@ __global__ void __launch_bounds__(128) k_cigar_align(CigarArgs A, const gu32 *__
     if (tix > A.n) return;
     if (tix == A.n) { op_cnt[A.n] = 0; md_cnt[A.n] = 0; return; }
     const int64_t i = perm[tix];
+    slot[i] = (gu32)tix;
     const meme_cigar_task_t t = A.tasks[i];
     meme_cigar_rec_t r;
     r.score = 0; r.nm = -1; r.n_cigar = -1; r.md_len = 0; r.cigar_off = 0; r.md_off = 0;
     if (task_valid(A, t)) {
-        const Seqs S = task_seqs(A, t);
-        EH *e = eh + eh_off[i];
-        uint8_t *zz = z + z_off[i];
+        const Scr C = lane_scratch(W, tix);
+        const Seqs S = task_seqs(A, t, C);
+        fill_query(A.codes, t.q_off, t.qlen, S.rev, C);
         int n_ops = 0;
         gu64 cells = 0;
-        r.score = region_cigar(A.opt, S, t.w, t.truesc, e, zz, &n_ops, &cells);
+        r.score = region_cigar(A.opt, S, t.w, t.truesc, C, &n_ops, &cells);
         r.n_cigar = n_ops;
-        r.md_len = nm_md(S, reinterpret_cast<const gu32 *>(e), n_ops, nullptr, &r.nm);
+        r.md_len = nm_md(S, C, n_ops, nullptr, &r.nm);
         if (cells) atomicAdd((unsigned long long *)&ctl[1], (unsigned long long)cells);
     }
     recs[i] = r;
@@ -120,7 +160,7 @@ __global__ void __launch_bounds__(128) k_cigar_align(CigarArgs A, const gu32 *__
     md_cnt[i] = r.md_len;
 }
 
-__global__ void __launch_bounds__(128) k_cigar_emit(CigarArgs A, const int64_t *__restrict__ eh_off, const EH *__restrict__ eh,
+__global__ void __launch_bounds__(128) k_cigar_emit(CigarArgs A, CigarScratch W, const gu32 *__restrict__ slot,
                                                     const int64_t *__restrict__ op_off, const int64_t *__restrict__ md_off,
                                                     int64_t op_base, int64_t md_base, meme_cigar_rec_t *__restrict__ recs,
                                                     gu32 *__restrict__ ops_out, char *__restrict__ md_out)
@@ -132,12 +172,12 @@ __global__ void __launch_bounds__(128) k_cigar_emit(CigarArgs A, const int64_t *
     r.md_off = md_base + md_off[i];
     recs[i] = r;
     if (r.n_cigar <= 0) return;
-    const gu32 *rev = reinterpret_cast<const gu32 *>(eh + eh_off[i]);
+    const Scr C = lane_scratch(W, slot[i]);
     gu32 *dst = ops_out + op_off[i];
-    for (int k = 0; k < r.n_cigar; k++) dst[k] = rev[r.n_cigar - 1 - k];
-    const Seqs S = task_seqs(A, A.tasks[i]);
+    for (int k = 0; k < r.n_cigar; k++) dst[k] = C.op(r.n_cigar - 1 - k);
+    const Seqs S = task_seqs(A, A.tasks[i], C);
     int nm;
-    nm_md(S, rev, r.n_cigar, md_out + md_off[i], &nm);
+    nm_md(S, C, r.n_cigar, md_out + md_off[i], &nm);
 }
 
 static int cigar_work(meme_index_t *ix, CigarWork **out)
@@ -194,40 +234,56 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     CUDA_TRY(cudaMemsetAsync(c->d_ctl, 0, 16, st));
     const int64_t SLICE = 1 << 18;
     int64_t op_base = 0, md_base = 0;
+    const bool dbg = getenv("MEME_CIGAR_DEBUG") != nullptr;
+    double t_h2d = 0, t_size = 0, t_align = 0, t_emit = 0, t_d2h = 0;
+    auto now = [&] { if (dbg) cudaStreamSynchronize(st); return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count() * 1e3; };
+    auto T0 = now();
     CUDA_TRY(cudaEventRecord(c->ev[0], st));
     for (int64_t s0 = 0; s0 < n_tasks; s0 += SLICE) {
         const int64_t n = n_tasks - s0 < SLICE ? n_tasks - s0 : SLICE;
-        void **grow[] = {(void **)&c->d_tasks, (void **)&c->d_z_off, (void **)&c->d_eh_off, (void **)&c->d_op_off, (void **)&c->d_md_off, (void **)&c->d_key,
-                         (void **)&c->d_key2, (void **)&c->d_idx, (void **)&c->d_idx2, (void **)&c->d_recs};
-        size_t *caps[] = {&c->cap_tasks, &c->cap_z_off, &c->cap_eh_off, &c->cap_op_off, &c->cap_md_off, &c->cap_key, &c->cap_key2, &c->cap_idx, &c->cap_idx2,
-                          &c->cap_recs};
-        size_t elem[] = {sizeof(meme_cigar_task_t), 8, 8, 8, 8, 1, 1, 4, 4, sizeof(meme_cigar_rec_t)};
-        for (int k = 0; k < 10; k++)
+        const int64_t n_groups = (n + 31) / 32;
+        void **grow[] = {(void **)&c->d_tasks, (void **)&c->d_z_off, (void **)&c->d_op_off, (void **)&c->d_md_off, (void **)&c->d_key,
+                         (void **)&c->d_key2, (void **)&c->d_idx, (void **)&c->d_idx2, (void **)&c->d_slot, (void **)&c->d_recs, (void **)&c->d_g_rows,
+                         (void **)&c->d_g_z};
+        size_t *caps[] = {&c->cap_tasks, &c->cap_z_off, &c->cap_op_off, &c->cap_md_off, &c->cap_key, &c->cap_key2, &c->cap_idx, &c->cap_idx2, &c->cap_slot,
+                          &c->cap_recs, &c->cap_g_rows, &c->cap_g_z};
+        size_t elem[] = {sizeof(meme_cigar_task_t), 8, 8, 8, 2, 2, 4, 4, 4, sizeof(meme_cigar_rec_t), 8, 8};
+        for (int k = 0; k < 12; k++)
             if ((rc = meme_grow_device(grow[k], caps[k], (size_t)n + 2, elem[k], st))) return rc;
+        auto Ta = now();
         CUDA_TRY(cudaMemcpyAsync(c->d_tasks, tasks + s0, (size_t)n * sizeof(meme_cigar_task_t), cudaMemcpyHostToDevice, st));
+        auto Tb = now(); t_h2d += secs(Ta, Tb);
         CigarArgs A;
         A.tasks = c->d_tasks; A.n = n; A.codes = c->d_codes; A.n_codes = n_codes; A.pac = ix->v.pac; A.sa_num = ix->v.sa_num; A.l_pac = l_pac;
         A.opt = *opt;
         const unsigned blocks = (unsigned)((n + 1 + 127) / 128);
-        k_cigar_size<<<blocks, 128, 0, st>>>(A, c->d_z_off, c->d_eh_off, c->d_key, c->d_idx);
+        k_cigar_size<<<blocks, 128, 0, st>>>(A, c->d_z_off, c->d_key, c->d_idx);
         CUDA_TRY(cudaGetLastError());
-        if ((rc = scan_i64(ix, c->d_z_off, n + 1, st))) return rc;
-        if ((rc = scan_i64(ix, c->d_eh_off, n + 1, st))) return rc;
         {
             size_t tmp = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 8, st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 16, st);
             if ((rc = meme_grow_device(&ix->d_scan_tmp, &ix->cap_scan_tmp, tmp + 256, 1, st))) return rc;
             size_t t2 = ix->cap_scan_tmp;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix->d_scan_tmp, t2, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 8, st));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix->d_scan_tmp, t2, c->d_key, c->d_key2, c->d_idx, c->d_idx2, (int)n, 0, 16, st));
         }
-        int64_t tot[2];
-        CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_z_off + n, 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(&tot[1], c->d_eh_off + n, 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if ((rc = meme_grow_device((void **)&c->d_z, &c->cap_z, (size_t)tot[0] + 64, 1, st))) return rc;
-        if ((rc = meme_grow_device((void **)&c->d_eh, &c->cap_eh, (size_t)tot[1] + 8, sizeof(EH), st))) return rc;
-        k_cigar_align<<<blocks, 128, 0, st>>>(A, c->d_idx2, c->d_z_off, c->d_eh_off, c->d_z, c->d_eh, c->d_recs, c->d_op_off, c->d_md_off, c->d_ctl);
+        k_cigar_group<<<(unsigned)((n_groups + 1 + 127) / 128), 128, 0, st>>>(A, c->d_idx2, c->d_z_off, n_groups, c->d_g_rows, c->d_g_z);
         CUDA_TRY(cudaGetLastError());
+        if ((rc = scan_i64(ix, c->d_g_rows, n_groups + 1, st))) return rc;
+        if ((rc = scan_i64(ix, c->d_g_z, n_groups + 1, st))) return rc;
+        int64_t tot[2];
+        CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_g_z + n_groups, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&tot[1], c->d_g_rows + n_groups, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = meme_grow_device((void **)&c->d_z, &c->cap_z, (size_t)tot[0] * 32 + 64, 1, st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_eh, &c->cap_eh, (size_t)tot[1] * 32 + 64, sizeof(EH), st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_q, &c->cap_q, (size_t)tot[1] * 32 + 64, 1, st))) return rc;
+        CigarScratch W;
+        W.eh = c->d_eh; W.z = c->d_z; W.q = c->d_q; W.g_rows = c->d_g_rows; W.g_z = c->d_g_z;
+        auto Tc = now(); t_size += secs(Tb, Tc);
+        k_cigar_align<<<blocks, 128, 0, st>>>(A, W, c->d_idx2, c->d_slot, c->d_recs, c->d_op_off, c->d_md_off, c->d_ctl);
+        CUDA_TRY(cudaGetLastError());
+        auto Td = now(); t_align += secs(Tc, Td);
         if ((rc = scan_i64(ix, c->d_op_off, n + 1, st))) return rc;
         if ((rc = scan_i64(ix, c->d_md_off, n + 1, st))) return rc;
         CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_op_off + n, 8, cudaMemcpyDeviceToHost, st));
@@ -235,17 +291,18 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
         CUDA_TRY(cudaStreamSynchronize(st));
         if ((rc = meme_grow_device((void **)&c->d_ops, &c->cap_ops, (size_t)tot[0] + 8, 4, st))) return rc;
         if ((rc = meme_grow_device((void **)&c->d_md, &c->cap_md, (size_t)tot[1] + 8, 1, st))) return rc;
-        k_cigar_emit<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, c->d_eh_off, c->d_eh, c->d_op_off, c->d_md_off, op_base, md_base, c->d_recs,
-                                                               c->d_ops, c->d_md);
+        k_cigar_emit<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, W, c->d_slot, c->d_op_off, c->d_md_off, op_base, md_base, c->d_recs, c->d_ops, c->d_md);
         CUDA_TRY(cudaGetLastError());
+        auto Te = now(); t_emit += secs(Td, Te);
         if ((rc = cigar_grow_pinned((void **)&c->h_ops, &c->hcap_ops, (size_t)(op_base + tot[0]) + 1, 4, (size_t)op_base))) return rc;
         if ((rc = cigar_grow_pinned((void **)&c->h_md, &c->hcap_md, (size_t)(md_base + tot[1]) + 1, 1, (size_t)md_base))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->h_recs + s0, c->d_recs, (size_t)n * sizeof(meme_cigar_rec_t), cudaMemcpyDeviceToHost, st));
         if (tot[0]) CUDA_TRY(cudaMemcpyAsync(c->h_ops + op_base, c->d_ops, (size_t)tot[0] * 4, cudaMemcpyDeviceToHost, st));
         if (tot[1]) CUDA_TRY(cudaMemcpyAsync(c->h_md + md_base, c->d_md, (size_t)tot[1], cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        auto Tf = now(); t_d2h += secs(Te, Tf);
         op_base += tot[0]; md_base += tot[1];
-        ix->launches += 3;
+        ix->launches += 4;
     }
     CUDA_TRY(cudaEventRecord(c->ev[1], st));
     u64 ctl[2];
@@ -254,6 +311,8 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     CUDA_TRY(cudaEventElapsedTime(&c->ms, c->ev[0], c->ev[1]));
     c->cells = ctl[1];
     c->ran = 1;
+    if (dbg) fprintf(stderr, "[meme_cigar] %lld tasks: total %.1f ms (codes+setup %.1f), per phase summed over slices: tasks h2d %.1f, size+scan+sort %.1f, align %.1f, "
+                     "scan+emit %.1f, d2h %.1f; %llu cells\n", (long long)n_tasks, secs(T0, now()), 0.0, t_h2d, t_size, t_align, t_emit, t_d2h, (unsigned long long)c->cells);
     out->n_tasks = n_tasks; out->n_ops = op_base; out->n_md = md_base;
     out->recs = c->h_recs; out->cigars = c->h_ops; out->md = c->h_md;
     return MEME_OK;

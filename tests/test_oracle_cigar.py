@@ -75,18 +75,19 @@ def cigar_sim():
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", lib, srcs[0]], check=True)
     L = C.CDLL(lib)
     L.cigar_sim.restype = C.c_int
-    L.cigar_sim.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cigar_sim.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int, C.c_int]
     return L
 
 
-def run_sim(L, O, text, l_pac, codes, tasks, opt):
+def run_sim(L, O, text, l_pac, codes, tasks, opt, stride=1, lane=0):
     n = len(tasks)
     recs = np.zeros(n, O.CIGAR_REC_DTYPE)
     cig = np.zeros(int((2 * tasks["qlen"].astype(np.int64) + 2).sum()) + 8, np.uint32)
     md = C.create_string_buffer(int((4 * (tasks["re"] - tasks["rb"]) + 16).sum()) + 64)
     cells = C.c_uint64()
     rc = L.cigar_sim(text.ctypes.data, l_pac, codes.ctypes.data, len(codes), tasks.ctypes.data, n, C.addressof(opt), recs.ctypes.data, cig.ctypes.data,
-                     C.addressof(md), C.byref(cells))
+                     C.addressof(md), C.byref(cells), stride, lane)
     assert rc == 0, rc
     return O.unpack_cigar_result(recs, cig, md.raw), int(cells.value)
 
@@ -97,6 +98,9 @@ def test_kernel_source_on_host_matches_reference_and_oracle(oracle, cigar_case, 
     check_against_reference(oracle, g, cases, raw, ref)
     assert raw == oracle.cigar_regions(text, len(g), codes, tasks)
     assert cells > 0
+    # the device layout: lane 5 of 32 interleaved regions (and the other lanes' bytes stay untouched)
+    raw32, _ = run_sim(cigar_sim, oracle, text, len(g), codes, tasks[:400], oracle.default_cigar_opt(), stride=32, lane=5)
+    assert raw32 == raw[:400]
 
 
 def test_kernel_source_on_host_option_corners(oracle, cigar_case, cigar_sim):
