@@ -26,7 +26,7 @@ EXPORTS = [
     "meme_bsw_set_stream", "meme_bsw_batch", "meme_bsw_upload", "meme_bsw_run", "meme_bsw_download", "meme_bsw_cells",
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
-    "meme_cigar_batch", "meme_cigar_last",
+    "meme_cigar_batch", "meme_cigar_last", "meme_cigar_warmup",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -161,6 +161,7 @@ def lib():
         L.meme_chain_batch_multi.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.POINTER(SeedOpt), C.POINTER(ChainOpt), vp, vp]
         L.meme_cigar_batch.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(CigarOpt), C.POINTER(CigarResult)]
         L.meme_cigar_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
+        L.meme_cigar_warmup.argtypes = [vp, i64, C.c_int]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -327,6 +328,9 @@ class MemeIndex:
         return float(ms.value)
 
     # ---- global alignment of the SAM stage (mem_reg2aln's loop around bwa_gen_cigar2) ----
+    def cigar_warmup(self, n_regions: int, qlen: int = 150) -> None:
+        _check(lib().meme_cigar_warmup(self.h, int(n_regions), int(qlen)), "meme_cigar_warmup")
+
     def cigar_batch(self, tasks: np.ndarray, codes: np.ndarray, l_pac: int, opt: CigarOpt | None = None) -> dict:
         opt = opt or default_cigar_opt()
         tasks = np.ascontiguousarray(tasks, dtype=CIGAR_TASK_DTYPE)

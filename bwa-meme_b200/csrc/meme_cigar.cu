@@ -318,6 +318,42 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     return MEME_OK;
 }
 
+// Kernels loaded and the pinned result arrays sized for a chunk of n_regions regions of qlen-base queries before the first
+// timed chunk: one slice of short dummy regions (a quarter of them with a matrix) runs through every kernel.
+extern "C" int meme_cigar_warmup(meme_index_t *ix, int64_t n_regions, int qlen)
+{
+    if (!ix || n_regions < 0 || qlen < 1) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    CigarWork *c; int rc;
+    if ((rc = cigar_work(ix, &c))) return rc;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const int64_t l_pac = (int64_t)(ix->v.sa_num / 2);
+    const int64_t n = n_regions < (1 << 16) ? n_regions : (1 << 16);
+    const int ql = 24;
+    if (l_pac < 4 * ql || n == 0) return MEME_OK;
+    std::vector<meme_cigar_task_t> tasks((size_t)n);
+    std::vector<uint8_t> codes((size_t)n * ql);
+    u64 x = 88172645463325252ull;
+    for (auto &b : codes) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; b = (uint8_t)(x & 3); }
+    for (int64_t i = 0; i < n; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        meme_cigar_task_t &T = tasks[(size_t)i];
+        T.rb = (int64_t)(x % (u64)(l_pac - 2 * ql)); T.re = T.rb + ql + ((i & 3) == 0 ? 2 : 0);
+        T.q_off = i * ql; T.qlen = ql; T.w = (i & 3) == 0 ? 4 : 0; T.truesc = ql; T.pad = 0;
+    }
+    meme_cigar_opt_t o;
+    memset(&o, 0, sizeof o);
+    for (int a = 0; a < 5; a++) for (int b = 0; b < 5; b++) o.mat[a * 5 + b] = a == 4 || b == 4 ? -1 : a == b ? 1 : -4;
+    o.o_del = o.o_ins = 6; o.e_del = o.e_ins = 1; o.w = 100; o.a = 1;
+    meme_cigar_result_t r;
+    if ((rc = meme_cigar_batch(ix, tasks.data(), n, codes.data(), (int64_t)codes.size(), l_pac, &o, &r))) return rc;
+    if ((rc = cigar_grow_pinned((void **)&c->h_recs, &c->hcap_recs, (size_t)n_regions, sizeof(meme_cigar_rec_t), 0))) return rc;
+    if ((rc = cigar_grow_pinned((void **)&c->h_ops, &c->hcap_ops, (size_t)n_regions * 2, 4, 0))) return rc;
+    if ((rc = cigar_grow_pinned((void **)&c->h_md, &c->hcap_md, (size_t)n_regions * 12, 1, 0))) return rc;
+    if ((rc = meme_grow_device((void **)&c->d_codes, &c->cap_codes, (size_t)n_regions * (size_t)qlen / 2 + 64, 1, ix->stream))) return rc;
+    c->ran = 0;
+    return MEME_OK;
+}
+
 extern "C" int meme_cigar_last(meme_index_t *ix, float *ms, uint64_t *cells)
 {
     if (!ix || !ix->cigar || !ix->cigar->ran) { meme_set_error("no completed meme_cigar_batch"); return MEME_E_ARG; }

@@ -382,15 +382,19 @@ void meme_cigar_chunk(worker_t &w, int n)
     if (!meme_glue_cigar_enabled() || n <= 0) return;
     const mem_opt_t *opt = w.opt;
     const int64_t l_pac = w.fmi->idx->bns->l_pac;
-    std::vector<int64_t> task_off((size_t)n + 1, 0);
+    static std::vector<int64_t> task_off;          // one chunk at a time (mem_process_seqs); buffers reused across chunks
+    static std::vector<meme_cigar_task_t> tasks;
+    static std::vector<int32_t> reg_w;
+    task_off.resize((size_t)n + 1);
+    task_off[0] = 0;
     for (int i = 0; i < n; i++) {
         int c = 0;
         const mem_alnreg_v &v = w.regs[i];
         for (size_t k = 0; k < v.n; k++) if (v.a[k].rb >= 0 && v.a[k].re >= 0) c++;
         task_off[(size_t)i + 1] = task_off[(size_t)i] + c;
     }
-    std::vector<meme_cigar_task_t> tasks((size_t)task_off[(size_t)n]);
-    std::vector<int32_t> reg_w((size_t)task_off[(size_t)n]);
+    tasks.resize((size_t)task_off[(size_t)n]);
+    reg_w.resize((size_t)task_off[(size_t)n]);
 #pragma omp parallel for schedule(static) num_threads(std::max(1, (int)w.nthreads))
     for (int i = 0; i < n; i++) {
         const mem_alnreg_v &v = w.regs[i];

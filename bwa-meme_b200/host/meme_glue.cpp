@@ -38,6 +38,7 @@ struct Api {
     decltype(&meme_chain_batch_multi) chain_batch_multi = nullptr;
     decltype(&meme_chain_warmup) chain_warmup = nullptr;
     decltype(&meme_cigar_batch) cigar_batch = nullptr;
+    decltype(&meme_cigar_warmup) cigar_warmup = nullptr;
     bool ok = false;
 };
 
@@ -68,7 +69,8 @@ Api &api()
         a.chain_batch_multi = (decltype(a.chain_batch_multi))dlsym(a.so, "meme_chain_batch_multi");
         a.chain_warmup = (decltype(a.chain_warmup))dlsym(a.so, "meme_chain_warmup");
         a.cigar_batch = (decltype(a.cigar_batch))dlsym(a.so, "meme_cigar_batch");
-        a.ok = a.cigar_batch && a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+        a.cigar_warmup = (decltype(a.cigar_warmup))dlsym(a.so, "meme_cigar_warmup");
+        a.ok = a.cigar_warmup && a.cigar_batch && a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
                a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
@@ -112,7 +114,11 @@ std::vector<int32_t> g_creg_w;
 std::vector<int64_t> g_ctask_off;               // per read: its tasks
 std::vector<meme_cigar_result_t> g_cres;        // per device
 std::vector<int64_t> g_cres_begin;              // first task of each device's share
-std::vector<std::pair<const char *, int>> g_cptr;   // (seqs[i].seq, i), sorted by pointer
+// seqs[i].seq -> i: open-addressing table of read indexes (-1 = empty), filled by all threads
+std::vector<std::atomic<int32_t>> g_cslot;
+std::vector<const char *> g_cseq;
+size_t g_cmask = 0;
+inline size_t ptr_hash(const char *p) { uint64_t x = (uint64_t)(uintptr_t)p; x ^= x >> 29; x *= 0x9E3779B97F4A7C15ull; return (size_t)(x >> 20); }
 std::atomic<long> g_cig_hit{0}, g_cig_miss{0};   // lookups of mem_reg2aln answered from the GPU results / left to its own code
 
 [[noreturn]] void die(const char *what, int rc)
@@ -149,6 +155,7 @@ static void ensure_index()
             rc = a.seed_warmup(g_index[(size_t)d], warm / nd + 1, 150);
             if (rc) die("meme_seed_warmup", rc);
             if (env_on("MEME_B200_CHAIN") && (rc = a.chain_warmup(g_index[(size_t)d]))) die("meme_chain_warmup", rc);
+            if (env_on("MEME_B200_SAM") && (rc = a.cigar_warmup(g_index[(size_t)d], warm * 3 / nd + 1, 150))) die("meme_cigar_warmup", rc);
         }
         fprintf(stderr, "[meme_b200] warm-up batch of %ld reads in %.2f s\n", warm,
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
@@ -417,9 +424,21 @@ void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int3
     for (auto &t : th) t.join();
     for (int d = 0; d < nd; d++)
         if (rc[(size_t)d]) { fprintf(stderr, "[meme_b200] meme_cigar_batch failed (%d): %s\n", rc[(size_t)d], err[(size_t)d].c_str()); exit(EXIT_FAILURE); }
-    g_cptr.resize((size_t)n_reads);
-    for (int i = 0; i < n_reads; i++) g_cptr[(size_t)i] = {seqs[i].seq, i};
-    std::sort(g_cptr.begin(), g_cptr.end());
+    size_t slots = 1024;
+    while (slots < (size_t)n_reads * 3) slots <<= 1;
+    if (g_cslot.size() != slots) { std::vector<std::atomic<int32_t>> t(slots); g_cslot.swap(t); }
+    g_cmask = slots - 1;
+    g_cseq.resize((size_t)n_reads);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)slots; k++) g_cslot[(size_t)k].store(-1, std::memory_order_relaxed);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n_reads; i++) {
+        g_cseq[(size_t)i] = seqs[i].seq;
+        for (size_t h = ptr_hash(seqs[i].seq) & g_cmask;; h = (h + 1) & g_cmask) {
+            int32_t empty = -1;
+            if (g_cslot[h].compare_exchange_strong(empty, i, std::memory_order_relaxed)) break;
+        }
+    }
     g_have_cigar = true;
     static bool at_exit = false;
     if (!at_exit) {
@@ -439,9 +458,13 @@ void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int3
 bool meme_glue_take_cigar(const char *query, const mem_alnreg_t *ar, uint32_t **cigar, int *n_cigar, int *NM)
 {
     if (!g_have_cigar) return false;
-    auto it = std::lower_bound(g_cptr.begin(), g_cptr.end(), std::make_pair(query, 0));
-    if (it == g_cptr.end() || it->first != query) { g_cig_miss++; return false; }
-    const int i = it->second;
+    int i = -1;
+    for (size_t h = ptr_hash(query) & g_cmask;; h = (h + 1) & g_cmask) {
+        const int32_t v = g_cslot[h].load(std::memory_order_relaxed);
+        if (v < 0) break;
+        if (g_cseq[(size_t)v] == query) { i = v; break; }
+    }
+    if (i < 0) { g_cig_miss++; return false; }
     for (int64_t t = g_ctask_off[(size_t)i]; t < g_ctask_off[(size_t)i + 1]; t++) {
         const meme_cigar_task_t &k = g_ctasks[(size_t)t];
         if (k.rb != ar->rb || k.re != ar->re || k.truesc != ar->truesc || g_creg_w[(size_t)t] != ar->w) continue;
