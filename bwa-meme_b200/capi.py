@@ -27,6 +27,7 @@ EXPORTS = [
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
     "meme_cigar_batch", "meme_cigar_last", "meme_cigar_warmup",
+    "meme_matesw_batch", "meme_matesw_last", "meme_matesw_warmup",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -61,6 +62,18 @@ class CigarOpt(C.Structure):
 class CigarResult(C.Structure):
     _fields_ = [("n_tasks", C.c_int64), ("n_ops", C.c_int64), ("n_md", C.c_int64), ("recs", C.c_void_p), ("cigars", C.c_void_p),
                 ("md", C.c_void_p)]
+
+
+KSWR_DTYPE = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
+
+
+class MateswOpt(C.Structure):
+    _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+def default_matesw_opt(a: int = 1, b: int = 4, o_del: int = 6, e_del: int = 1, o_ins: int = 6, e_ins: int = 1) -> MateswOpt:
+    return MateswOpt(o_del, e_del, o_ins, e_ins, a, b)
 
 
 def default_cigar_opt(a: int = 1, b: int = 4, o_del: int = 6, e_del: int = 1, o_ins: int = 6, e_ins: int = 1, w: int = 100) -> CigarOpt:
@@ -162,6 +175,9 @@ def lib():
         L.meme_cigar_batch.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(CigarOpt), C.POINTER(CigarResult)]
         L.meme_cigar_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
         L.meme_cigar_warmup.argtypes = [vp, i64, C.c_int]
+        L.meme_matesw_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, C.POINTER(MateswOpt), vp]
+        L.meme_matesw_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
+        L.meme_matesw_warmup.argtypes = [vp, i64, C.c_int, C.c_int]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -328,6 +344,26 @@ class MemeIndex:
         return float(ms.value)
 
     # ---- global alignment of the SAM stage (mem_reg2aln's loop around bwa_gen_cigar2) ----
+    # ---- mate-rescue Smith-Waterman (mem_sam_pe_batch) ----
+    def matesw_warmup(self, n_pairs: int, len1: int = 640, len2: int = 150) -> None:
+        _check(lib().meme_matesw_warmup(self.h, int(n_pairs), int(len1), int(len2)), "meme_matesw_warmup")
+
+    def matesw_batch(self, segments, opt: "MateswOpt | None" = None) -> dict:
+        """segments: list of (pairs [SEQPAIR_DTYPE: idr, idq, len1, len2, h0 used], ref bytes, query bytes).
+        Returns {"aln": [KSWR_DTYPE array per segment], "ms", "cells"}."""
+        opt = opt or default_matesw_opt()
+        ns = len(segments)
+        ps = [np.ascontiguousarray(s[0], dtype=SEQPAIR_DTYPE) for s in segments]
+        rs = [np.ascontiguousarray(s[1], dtype=np.uint8) for s in segments]
+        qs = [np.ascontiguousarray(s[2], dtype=np.uint8) for s in segments]
+        outs = [np.zeros(len(p), dtype=KSWR_DTYPE) for p in ps]
+        ptr = lambda arrs: (C.c_void_p * max(ns, 1))(*[a.ctypes.data for a in arrs])
+        cnt = lambda arrs: (C.c_int64 * max(ns, 1))(*[len(a) for a in arrs])
+        _check(lib().meme_matesw_batch(self.h, ns, ptr(ps), cnt(ps), ptr(rs), cnt(rs), ptr(qs), cnt(qs), C.byref(opt), ptr(outs)), "meme_matesw_batch")
+        ms, cells = C.c_float(), C.c_uint64()
+        _check(lib().meme_matesw_last(self.h, C.byref(ms), C.byref(cells)), "meme_matesw_last")
+        return {"aln": outs, "ms": ms.value, "cells": cells.value}
+
     def cigar_warmup(self, n_regions: int, qlen: int = 150) -> None:
         _check(lib().meme_cigar_warmup(self.h, int(n_regions), int(qlen)), "meme_cigar_warmup")
 

@@ -99,9 +99,12 @@ struct meme_index {
     struct ChainWork *chain;
     // ---- global alignment of the SAM stage (meme_cigar.cu) ----
     struct CigarWork *cigar;
+    // ---- mate-rescue Smith-Waterman (meme_matesw.cu) ----
+    struct MateswWork *matesw;
 };
 void meme_chain_free(struct ChainWork *c);
 void meme_cigar_free(struct CigarWork *c);
+void meme_matesw_free(struct MateswWork *c);
 
 int meme_grow_device(void **p, size_t *cap, size_t need, size_t elem, cudaStream_t s);
 int meme_grow_pinned(void **p, size_t *cap, size_t need, size_t elem);

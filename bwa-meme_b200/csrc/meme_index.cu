@@ -380,6 +380,7 @@ extern "C" void meme_index_free(meme_index_t *ix)
     cudaStreamSynchronize(ix->stream);
     if (ix->chain) meme_chain_free(ix->chain);
     if (ix->cigar) meme_cigar_free(ix->cigar);
+    if (ix->matesw) meme_matesw_free(ix->matesw);
     void *dev[] = {ix->d_keys, ix->d_pos_lo, ix->d_pos_hi, ix->d_isa_lo, ix->d_isa_hi, ix->d_pac, ix->d_l1, ix->d_l2,
                    ix->d_codes, ix->d_read_off, ix->d_rd_pool_off, ix->d_rd_nsmem, ix->d_rd_nhit, ix->d_smem_off,
                    ix->d_hit_off, ix->d_pool, ix->d_ctrl, ix->d_scan_tmp, ix->d_smems, ix->d_hits, ix->d_redo,

@@ -315,6 +315,33 @@ int meme_bsw_attach_text(meme_bsw_t *b, const meme_index_t *ix);
 /* DP cells evaluated by the last run (band-limited, retries included), for GCUPS accounting. */
 int meme_bsw_cells(meme_bsw_t *b, uint64_t *cells);
 
+/* ---- mate rescue: batched local Smith-Waterman --------------------- */
+
+/* Byte-identical to the reference's kswr_t (src/ksw.h:L45-50). */
+typedef struct {
+    int32_t score, te, qe, score2, te2, tb, qb;
+} meme_kswr_t;
+
+/* Constructor arguments of kswv (src/kswv.h, src/bwamem_pair.cpp:L750): gap penalties, match score, mismatch penalty (positive). */
+typedef struct {
+    int32_t o_del, e_del, o_ins, e_ins, a, b;
+} meme_matesw_opt_t;
+
+/* Replaces sort_classify + mem_sam_pe_batch (src/bwamem.cpp:L1797-1826, src/bwamem_pair.cpp:L719-817: kswv::getScores8/16
+ * phase 0, selection of the pairs that reach their minimum score, reversal, phase 1) for a batch assembled by several host
+ * threads: nseg segments, each with its own SeqPair array and sequence buffers as mem_matesw_batch_pre fills them
+ * (src/bwamem_pair.cpp:L1060-1222: idr / idq relative to the segment's buffers, len1 = window length, len2 = mate length,
+ * h0 = the KSW_X* flags | minimum score; sequences are codes 0..4 and are NOT modified).  aln[s][k] receives the kswr_t of
+ * pairs[s][k], i.e. what the reference leaves in aln[pairs[k].regid].  No sorting, classing or SIMD-width padding is
+ * required from the caller.  Limits: mate length <= 496 (255 in the 8-bit class, h0 & KSW_XBYTE), window <= 32000. */
+int meme_matesw_batch(meme_index_t *ix, int32_t nseg, const meme_seqpair_t *const *pairs, const int64_t *n_pairs,
+                      const uint8_t *const *ref, const int64_t *n_ref, const uint8_t *const *qer, const int64_t *n_qer,
+                      const meme_matesw_opt_t *opt, meme_kswr_t *const *aln);
+/* CUDA-event duration (ms) of the kernels of the last meme_matesw_batch, and the DP cells they evaluated. */
+int meme_matesw_last(meme_index_t *ix, float *ms, uint64_t *cells);
+/* Kernel loaded and buffers sized for about n_pairs pairs of len1 x len2 ahead of the first timed chunk. */
+int meme_matesw_warmup(meme_index_t *ix, int64_t n_pairs, int len1, int len2);
+
 /* Pinned host memory for callers that assemble large batches (the chunk-level extension driver of the glue). */
 int  meme_pinned_alloc(size_t bytes, void **out);
 void meme_pinned_free(void *p);

@@ -1,4 +1,5 @@
-"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c, oracle/chain_oracle.c, oracle/cigar_oracle.c).
+"""ctypes bindings for the CPU oracle (oracle/seed_oracle.c, oracle/bsw_oracle.c, oracle/chain_oracle.c, oracle/cigar_oracle.c,
+oracle/matesw_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline leg -- never by the product package.
@@ -16,7 +17,8 @@ BUILD = os.path.join(HERE, "_build")
 
 def build(force: bool = False) -> None:
     os.makedirs(BUILD, exist_ok=True)
-    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so"), ("chain_oracle.c", "liboracle_chain.so"), ("cigar_oracle.c", "liboracle_cigar.so")):
+    for src, lib in (("seed_oracle.c", "liboracle_seed.so"), ("bsw_oracle.c", "liboracle_bsw.so"), ("chain_oracle.c", "liboracle_chain.so"), ("cigar_oracle.c", "liboracle_cigar.so"),
+                     ("matesw_oracle.c", "liboracle_matesw.so")):
         s, o = os.path.join(HERE, src), os.path.join(BUILD, lib)
         if not os.path.exists(s):
             continue
@@ -449,3 +451,50 @@ def sam_cigar(raw: dict, qb: int, qe: int, l_query: int, rev: bool) -> dict:
         if clip3:
             cig = cig + [clip3 << 4 | 3]
     return {"cigar": cig, "md": raw["md"], "nm": raw["nm"], "pos_shift": shift}
+
+
+# ---- mate-rescue Smith-Waterman oracle (oracle/matesw_oracle.c) ------------------------------------------------------------------
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
+MATESW_REC_DTYPE = np.dtype([("r_off", "<i8"), ("q_off", "<i8"), ("len1", "<i4"), ("len2", "<i4"), ("xtra", "<i4"), ("pad", "<i4")])
+KSWR_DTYPE = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+
+
+class MateswOpt(C.Structure):
+    _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+def default_matesw_opt(a: int = 1, b: int = 4, o_del: int = 6, e_del: int = 1, o_ins: int = 6, e_ins: int = 1) -> MateswOpt:
+    return MateswOpt(o_del, e_del, o_ins, e_ins, a, b)
+
+
+_matesw_lib = None
+
+
+def matesw_lib():
+    global _matesw_lib
+    if _matesw_lib is None:
+        build()
+        L = C.CDLL(os.path.join(BUILD, "liboracle_matesw.so"))
+        L.oracle_matesw.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(MateswOpt), C.c_void_p]
+        _matesw_lib = L
+    return _matesw_lib
+
+
+def matesw_batch(recs: np.ndarray, ref: np.ndarray, qer: np.ndarray, opt: MateswOpt | None = None) -> np.ndarray:
+    """mem_sam_pe_batch (kswv phases 0 and 1) for every pair; returns KSWR_DTYPE records."""
+    opt = opt or default_matesw_opt()
+    recs = np.ascontiguousarray(recs, dtype=MATESW_REC_DTYPE)
+    ref = np.ascontiguousarray(ref, dtype=np.uint8); qer = np.ascontiguousarray(qer, dtype=np.uint8)
+    out = np.zeros(len(recs), dtype=KSWR_DTYPE)
+    matesw_lib().oracle_matesw(recs.ctypes.data, len(recs), ref.ctypes.data, qer.ctypes.data, C.byref(opt), out.ctypes.data)
+    return out
+
+
+def matesw_write_cases(path: str, recs: np.ndarray, ref: np.ndarray, qer: np.ndarray, opt: MateswOpt | None = None) -> None:
+    """The input file of oracle/ref_matesw_shim.cpp."""
+    opt = opt or default_matesw_opt()
+    with open(path, "wb") as f:
+        f.write(np.array([len(recs), len(ref), len(qer)], np.int64).tobytes())
+        f.write(np.array([opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, opt.a, opt.b, 0, 0], np.int32).tobytes())
+        f.write(np.ascontiguousarray(recs, dtype=MATESW_REC_DTYPE).tobytes())
+        f.write(np.ascontiguousarray(ref, np.uint8).tobytes()); f.write(np.ascontiguousarray(qer, np.uint8).tobytes())

@@ -50,6 +50,22 @@ def sha(path):
 TEXTEND = {"length": 30000, "seed": 301, "start_a_run": 6, "end_t_run": 5, "bits": 16, "reads_seed": 1}
 
 
+MATESW_SETS = (("default", 1200, 11, {}), ("a2b3", 600, 12, {"a": 2, "b": 3}), ("gaps", 600, 13, {"o_del": 1, "e_del": 3, "o_ins": 12, "e_ins": 2}))
+
+
+def make_matesw(work):
+    """mem_sam_pe_batch of the reference (oracle/ref_matesw_shim.cpp; kswv exists in AVX512 builds only) on synthetic rescue pairs."""
+    import matesw_util as MU
+    if MU.shim_path() is None:
+        print("matesw: no AVX512 shim here, fixtures left as they are")
+        return
+    for name, n, seed, kw in MATESW_SETS:
+        recs, ref, qer = MU.make_matesw_cases(n, seed, a=kw.get("a", 1))
+        out = MU.run_shim(O, recs, ref, qer, O.default_matesw_opt(**kw), work)
+        np.save(os.path.join(HERE, f"matesw_ref_{name}.npy"), out)
+        print("matesw", name, len(out), "pairs,", int((out["tb"] >= 0).sum()), "with start positions,", int((out["score2"] > 0).sum()), "with a second hit")
+
+
 def make_textend(work):
     """Reads crossing the end of the text (and the forward/reverse junction) of a genome whose text ends in a T run."""
     g = synth.make_genome_textend(TEXTEND["length"], TEXTEND["seed"], TEXTEND["start_a_run"], TEXTEND["end_t_run"])
@@ -207,6 +223,7 @@ def main():
     make_textend(work)
     make_chains(work, fa, g)
     make_cigar(work)
+    make_matesw(work)
     shim = os.path.join(REF, f"bsw_shim_mode3.{ISA}")
     for seed, n, mq, mx, h0m in BSW_SETS:
         pairs, ref, qer = O.make_pairs(n, seed=seed, max_q=mq, max_extra_ref=mx, h0_max=h0m)
