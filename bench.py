@@ -503,6 +503,12 @@ def main_ours(a):
         line["chain"] = chain
         if world == 1 and not a.no_align:
             try:
+                from bwa_meme_b200 import e2e as _e2e
+                line["mate_rescue"] = _e2e.bench_matesw(ix, threads=host_cores(), oracle=None if a.no_cpu_baseline else ge.load_oracle())
+            except Exception as e:
+                line["mate_rescue"] = {"error": repr(e)[:400]}
+        if world == 1 and not a.no_align:
+            try:
                 line["align_e2e"], line["bsw"] = bench_align_and_bsw(a, device, local)
             except Exception as e:      # the headline (seeding) line must survive a failure of the secondary records
                 line["align_e2e"] = {"error": repr(e)[:400]}

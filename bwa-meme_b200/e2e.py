@@ -50,9 +50,10 @@ def sam_body(path: str) -> bytes:
 
 def compare_arms(prefix: str, fastqs: list[str], n_reads: int, read_len: int, threads: int, workdir: str, mode: int = 3,
                  gpu_env: dict | None = None, tag: str = "se") -> dict:
-    """reference CPU vs patched aligner with GPU seeding + chaining + seed extension on the same FASTQ."""
+    """reference CPU vs patched aligner with every GPU stage on (seeding + chaining, seed extension, the global alignments of
+    the SAM stage, mate-rescue Smith-Waterman) on the same FASTQ."""
     ref, b200, _ = binaries(mode)
-    gpu_env = gpu_env or {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}
+    gpu_env = gpu_env or {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1", "MEME_B200_MATE": "1"}
     out = {}
     r = run_mem(ref, prefix, fastqs, os.path.join(workdir, f"{tag}_ref.sam"), threads)
     g = run_mem(b200, prefix, fastqs, os.path.join(workdir, f"{tag}_gpu.sam"), threads, gpu_env)
@@ -60,7 +61,7 @@ def compare_arms(prefix: str, fastqs: list[str], n_reads: int, read_len: int, th
     bases = n_reads * read_len
     out["reference_cpu"] = {"Mbases_per_s": bases / r["real_s"] / 1e6, "real_s": r["real_s"], "threads": threads}
     out["gpu"] = {"Mbases_per_s": bases / g["real_s"] / 1e6, "real_s": g["real_s"], "threads": threads, "env": gpu_env,
-                  "log_tail": g["log"][-2:]}
+                  "log_tail": g["log"][-6:]}
     out["sam_identical"] = bool(same)
     out["reads"] = n_reads
     out["speedup"] = r["real_s"] / g["real_s"]
@@ -116,3 +117,77 @@ def bench_bsw_cpu(path: str, threads: int, reps: int = 2) -> dict | None:
     if p.returncode != 0:
         return {"error": p.stderr[-300:]}
     return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def make_rescue_pairs(n: int, read_len: int = 150, window: int = 626, seed: int = 9, a: int = 1):
+    """n mate-rescue pairs of the shape mem_matesw_batch_pre builds for 150 bp reads with a 400 +- 50 insert (window = high - low +
+    read length, src/bwamem_pair.cpp:L1108-1121): the mate is a copy of part of the window with 2 % substitutions (70 % of the
+    pairs; a fifth of those with a 3-base deletion) or unrelated to it.  Vectorised; returns (SEQPAIR array, ref bytes, query bytes)."""
+    from . import capi
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, size=(n, window), dtype=np.uint8)
+    st = rng.integers(0, window - read_len - 3, size=n)
+    idx = st[:, None] + np.arange(read_len)[None, :]
+    dele = rng.random(n) < 0.14
+    idx = idx + (dele[:, None] & (np.arange(read_len)[None, :] >= read_len // 2)) * 3
+    q = np.take_along_axis(ref, idx, axis=1)
+    mm = rng.random((n, read_len)) < 0.02
+    q = np.where(mm, (q + rng.integers(1, 4, size=(n, read_len), dtype=np.uint8)) & 3, q).astype(np.uint8)
+    unrelated = rng.random(n) < 0.3
+    q[unrelated] = rng.integers(0, 4, size=(int(unrelated.sum()), read_len), dtype=np.uint8)
+    pairs = np.zeros(n, capi.SEQPAIR_DTYPE)
+    pairs["idr"] = np.arange(n, dtype=np.int64) * window
+    pairs["idq"] = np.arange(n, dtype=np.int64) * read_len
+    pairs["len1"] = window; pairs["len2"] = read_len
+    pairs["h0"] = capi.KSW_XSUBO | capi.KSW_XSTART | (capi.KSW_XBYTE if read_len * a < 250 else 0) | (19 * a)
+    pairs["regid"] = np.arange(n)
+    return pairs, ref.reshape(-1), q.reshape(-1)
+
+
+def bench_matesw(ix, n: int = 400_000, threads: int = 16, reps: int = 3, oracle=None) -> dict:
+    """Row f2: meme_matesw_batch on n rescue pairs (host buffers in, kswr_t out) with the reference's own batch step (sort_classify +
+    mem_sam_pe_batch = kswv, oracle/_ref/matesw_shim `bench`, AVX512 hosts only) on the same pairs and all host threads beside it."""
+    import json
+    import tempfile
+    pairs, ref, qer = make_rescue_pairs(n)
+    segs = [(pairs, ref, qer)]
+    ix.matesw_batch(segs)
+    wall, kms = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = ix.matesw_batch(segs)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        kms.append(out["ms"])
+    cells = int(out["cells"])
+    rec = {"pairs": n, "window": int(pairs["len1"][0]), "read_len": int(pairs["len2"][0]), "kernel_ms": float(np.mean(kms)), "call_ms": float(np.mean(wall)),
+           "cells": cells, "gcups_kernel": cells / (float(np.mean(kms)) / 1e3) / 1e9, "pairs_per_s_call": n / (float(np.mean(wall)) / 1e3),
+           "h2d_bytes": int(len(ref) + len(qer) + 56 * n), "d2h_bytes": 28 * n,
+           "with_start_positions": int((out["aln"][0]["tb"] >= 0).sum()), "with_second_hit": int((out["aln"][0]["score2"] > 0).sum()),
+           "what": "kswv phases 0 + 1 (full local alignment of the mate against the rescue window, score2 / te2, start positions) for every pair, "
+                   "one thread per pair; cells counts both phases over the query padded as the reference pads it"}
+    if oracle is not None:
+        ns = 2000
+        want = oracle.matesw_batch(np.array([(int(p["idr"]), int(p["idq"]), int(p["len1"]), int(p["len2"]), int(p["h0"]), 0) for p in pairs[:ns]],
+                                            dtype=oracle.MATESW_REC_DTYPE), ref, qer)
+        rec["parity_sample"] = {"pairs": ns, "identical_to_oracle": bool(out["aln"][0][:ns].tolist() == want.tolist())}
+    shim = os.path.join(ROOT, "oracle", "_ref", "matesw_shim_mode3.avx512bw")
+    if host_isa() == "avx512bw" and os.path.exists(shim):
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "pairs.bin")
+            with open(path, "wb") as f:
+                f.write(np.array([n, len(ref), len(qer)], np.int64).tobytes())
+                f.write(np.array([6, 1, 6, 1, 1, 4, 0, 0], np.int32).tobytes())
+                r = np.zeros(n, dtype=[("r_off", "<i8"), ("q_off", "<i8"), ("len1", "<i4"), ("len2", "<i4"), ("xtra", "<i4"), ("pad", "<i4")])
+                r["r_off"] = pairs["idr"].astype(np.int64); r["q_off"] = pairs["idq"].astype(np.int64)
+                r["r_off"] = np.arange(n, dtype=np.int64) * int(pairs["len1"][0]); r["q_off"] = np.arange(n, dtype=np.int64) * int(pairs["len2"][0])
+                r["len1"] = pairs["len1"]; r["len2"] = pairs["len2"]; r["xtra"] = pairs["h0"]
+                f.write(r.tobytes()); f.write(ref.tobytes()); f.write(qer.tobytes())
+            p = subprocess.run([shim, path, "-", "bench", str(threads), "2"], capture_output=True, text=True)
+            if p.returncode == 0:
+                c = json.loads(p.stdout.strip().splitlines()[-1])
+                rec["cpu_baseline"] = {"ms_mean": c["ms_mean"], "pairs_per_s": n / (c["ms_mean"] / 1e3), "cores": threads, "kind": "reference",
+                                       "what": "sort_classify + mem_sam_pe_batch (kswv512_u8/16, both phases) in blocks of 512 pairs per host thread"}
+                rec["speedup_call_vs_cpu"] = c["ms_mean"] / float(np.mean(wall))
+            else:
+                rec["cpu_baseline"] = {"error": p.stderr[-300:]}
+    return rec

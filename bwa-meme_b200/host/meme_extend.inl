@@ -416,3 +416,66 @@ void meme_cigar_chunk(worker_t &w, int n)
     }
     meme_glue_cigar_run(tasks, reg_w, task_off, w.seqs, n, opt, l_pac);
 }
+
+
+// Called in front of kt_for(worker_sam) for paired-end chunks: the mate-rescue Smith-Waterman of the WHOLE chunk in one device
+// call (MEME_B200_MATE=1).  The reference collects the rescue pairs of a 512-read block with mem_sam_pe_batch_pre, aligns them
+// with kswv (mem_sam_pe_batch) and consumes the results in mem_sam_pe_batch_post, block by block inside worker_sam
+// (src/bwamem.cpp:L1851-1901).  mem_sam_pe_batch_pre only reads the regions, so it is run here first for every read pair -- the
+// reference's own function, nothing restated -- and the pairs it produces are copied into per-thread pinned arenas; worker_sam
+// then runs unchanged up to the point where it would call mem_sam_pe_batch and takes the block's results from here instead
+// (meme_glue_take_matesw: aln[regid] of a block = the results of its read pairs in the order they were produced).
+void meme_matesw_chunk(worker_t &w, int n)
+{
+    meme_glue_matesw_skip();       // nothing from an earlier chunk
+    if (!meme_glue_matesw_enabled() || !(w.opt->flag & MEM_F_PE) || (w.opt->flag & MEM_F_NO_RESCUE) || n < 2) return;
+    const int T = std::max(1, (int)w.nthreads);
+    const int np = n >> 1;
+    static std::vector<meme_ext::Arena> ar;
+    static std::vector<int64_t> pair_off;
+    if ((int)ar.size() < T) ar.resize((size_t)T);
+    {   // first chunk: the blocks the glue pinned when the index was loaded (best fit from its cache)
+        size_t sz[3];
+        meme_glue_matesw_arena_sizes(T, n, sz);
+        for (int t = 0; t < T; t++) {
+            meme_ext::Arena &A = ar[(size_t)t];
+            meme_ext::Arena::reserve(A.pairs, A.cap, (int64_t)(sz[0] / sizeof(SeqPair)));
+            meme_ext::Arena::reserve(A.ref, A.cap_ref, (int64_t)sz[1]);
+            meme_ext::Arena::reserve(A.qer, A.cap_qer, (int64_t)sz[2]);
+        }
+    }
+    pair_off.assign((size_t)np + 1, 0);
+    auto t0 = omp_get_wtime();
+    bool too_long = false;
+#pragma omp parallel num_threads(T)
+    {
+        const int tid = omp_get_thread_num();
+        const int p0 = (int)((int64_t)np * tid / T), p1 = (int)((int64_t)np * (tid + 1) / T);
+        meme_ext::Arena &A = ar[(size_t)tid];
+        A.reset();
+        for (int p = p0; p < p1; p++) {
+            int64_t pcnt = 0;
+            int32_t gcnt = 0, maxRefLen = 0, maxQerLen = 0;
+            mem_sam_pe_batch_pre(w.opt, w.fmi->idx->bns, w.fmi->idx->pac, w.pes, (uint64_t)((w.n_processed >> 1) + p), &w.seqs[2 * p], &w.regs[2 * p],
+                                 &w.mmc, pcnt, gcnt, maxRefLen, maxQerLen, tid);
+            pair_off[(size_t)p + 1] = pcnt;
+            const SeqPair *sp = w.mmc.seqPairArrayLeft128[tid];
+            const uint8_t *rbuf = w.mmc.seqBufLeftRef[tid * CACHE_LINE], *qbuf = w.mmc.seqBufLeftQer[tid * CACHE_LINE];
+            for (int64_t k = 0; k < pcnt; k++) {
+                SeqPair q = sp[k];
+                if (q.len1 > 32000 || q.len2 > 496 || ((q.h0 & KSW_XBYTE) && q.len2 > 255)) too_long = true;
+                uint8_t *r = A.take_ref(q.len1), *s = A.take_qer(q.len2);
+                memcpy(r, rbuf + q.idr, (size_t)q.len1);
+                memcpy(s, qbuf + q.idq, (size_t)q.len2);
+                q.idr = (int32_t)(r - A.ref); q.idq = (int32_t)(s - A.qer);
+                *A.new_pair() = q;
+            }
+        }
+    }
+    if (too_long) { meme_glue_matesw_skip(); return; }        // beyond the kernel's limits: this chunk takes the reference's own code
+    for (int p = 0; p < np; p++) pair_off[(size_t)p + 1] += pair_off[(size_t)p];
+    std::vector<SeqPair *> pp((size_t)T); std::vector<uint8_t *> rp((size_t)T), qp((size_t)T);
+    std::vector<int64_t> pn((size_t)T), rn((size_t)T), qn((size_t)T);
+    for (int t = 0; t < T; t++) { meme_ext::Arena &A = ar[(size_t)t]; pp[t] = A.pairs; pn[t] = A.n; rp[t] = A.ref; rn[t] = A.n_ref; qp[t] = A.qer; qn[t] = A.n_qer; }
+    meme_glue_matesw_run(T, pp.data(), pn.data(), rp.data(), rn.data(), qp.data(), qn.data(), w.opt, pair_off, (omp_get_wtime() - t0) * 1e3);
+}

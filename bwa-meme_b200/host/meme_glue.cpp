@@ -39,6 +39,8 @@ struct Api {
     decltype(&meme_chain_warmup) chain_warmup = nullptr;
     decltype(&meme_cigar_batch) cigar_batch = nullptr;
     decltype(&meme_cigar_warmup) cigar_warmup = nullptr;
+    decltype(&meme_matesw_batch) matesw_batch = nullptr;
+    decltype(&meme_matesw_warmup) matesw_warmup = nullptr;
     bool ok = false;
 };
 
@@ -70,7 +72,9 @@ Api &api()
         a.chain_warmup = (decltype(a.chain_warmup))dlsym(a.so, "meme_chain_warmup");
         a.cigar_batch = (decltype(a.cigar_batch))dlsym(a.so, "meme_cigar_batch");
         a.cigar_warmup = (decltype(a.cigar_warmup))dlsym(a.so, "meme_cigar_warmup");
-        a.ok = a.cigar_warmup && a.cigar_batch && a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
+        a.matesw_batch = (decltype(a.matesw_batch))dlsym(a.so, "meme_matesw_batch");
+        a.matesw_warmup = (decltype(a.matesw_warmup))dlsym(a.so, "meme_matesw_warmup");
+        a.ok = a.matesw_batch && a.matesw_warmup && a.cigar_warmup && a.cigar_batch && a.chain_warmup && a.chain_set_contigs && a.chain_batch_multi && a.index_load && a.seed_batch && a.bsw_create && a.bsw_batch && a.last_error && a.bsw_upload_segments &&
                a.bsw_download_segments && a.bsw_run_ext && a.bsw_set_match && a.bsw_attach_text && a.pinned_alloc && a.pinned_free && a.index_load_devices &&
                a.seed_batch_multi;
         if (!a.ok) { fprintf(stderr, "[meme_b200] libmeme_b200.so lacks required symbols\n"); exit(EXIT_FAILURE); }
@@ -155,6 +159,7 @@ static void ensure_index()
             rc = a.seed_warmup(g_index[(size_t)d], warm / nd + 1, 150);
             if (rc) die("meme_seed_warmup", rc);
             if (env_on("MEME_B200_CHAIN") && (rc = a.chain_warmup(g_index[(size_t)d]))) die("meme_chain_warmup", rc);
+            if (env_on("MEME_B200_MATE") && (rc = a.matesw_warmup(g_index[(size_t)d], warm / nd + 1, 640, 150))) die("meme_matesw_warmup", rc);
             if (env_on("MEME_B200_SAM") && (rc = a.cigar_warmup(g_index[(size_t)d], warm * 3 / nd + 1, 150))) die("meme_cigar_warmup", rc);
         }
         fprintf(stderr, "[meme_b200] warm-up batch of %ld reads in %.2f s\n", warm,
@@ -164,6 +169,12 @@ static void ensure_index()
             cpu_set_t cs;
             if (!getenv("MEME_B200_THREADS") && sched_getaffinity(0, sizeof cs, &cs) == 0) threads = CPU_COUNT(&cs);
             meme_glue_pinned_reserve(threads, warm);
+        }
+        if (env_on("MEME_B200_MATE")) {
+            int threads = getenv("MEME_B200_THREADS") ? atoi(getenv("MEME_B200_THREADS")) : (int)std::thread::hardware_concurrency();
+            cpu_set_t cs;
+            if (!getenv("MEME_B200_THREADS") && sched_getaffinity(0, sizeof cs, &cs) == 0) threads = CPU_COUNT(&cs);
+            meme_glue_pinned_reserve_matesw(threads, warm);
         }
     }
 }
@@ -486,6 +497,75 @@ bool meme_glue_take_cigar(const char *query, const mem_alnreg_t *ar, uint32_t **
     return false;
 }
 
+// ---- mate rescue: the Smith-Waterman pairs of a paired-end chunk on the GPU (MEME_B200_MATE=1) ----
+namespace {
+std::vector<meme_kswr_t> g_msw_res;              // results of all pairs of the chunk, in the order the pre-pass produced them
+std::vector<int64_t> g_msw_off;                  // per read pair: index of its first result
+bool g_have_msw = false;
+std::atomic<long> g_msw_taken{0}, g_msw_blocks{0};
+static_assert(sizeof(meme_kswr_t) == sizeof(kswr_t) && offsetof(meme_kswr_t, qb) == offsetof(kswr_t, qb) && offsetof(meme_kswr_t, te2) == offsetof(kswr_t, te2),
+              "meme_kswr_t must mirror kswr_t (src/ksw.h)");
+}
+
+bool meme_glue_matesw_enabled() { return env_on("MEME_B200_MATE") && !g_index.empty(); }
+void meme_glue_matesw_skip() { g_have_msw = false; }
+
+// nseg segments written by the host threads (contiguous shares of the read pairs, in order) -> one device batch per GPU
+void meme_glue_matesw_run(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer, const mem_opt_t *opt,
+                          std::vector<int64_t> &pair_off, double collect_ms)
+{
+    Api &a = api();
+    auto t0 = std::chrono::steady_clock::now();
+    g_have_msw = false;
+    g_msw_off.swap(pair_off);
+    int64_t n = 0;
+    std::vector<int64_t> base((size_t)nseg + 1, 0);
+    for (int s = 0; s < nseg; s++) { base[(size_t)s] = n; n += n_pairs[s]; }
+    base[(size_t)nseg] = n;
+    if (g_msw_off.empty() || g_msw_off.back() != n) { fprintf(stderr, "[meme_b200] mate rescue: %ld pairs collected, %ld counted\n", (long)n, g_msw_off.empty() ? -1L : (long)g_msw_off.back()); exit(EXIT_FAILURE); }
+    g_msw_res.resize((size_t)n + 1);
+    meme_matesw_opt_t mo = {opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->a, opt->b};
+    const int nd = (int)g_index.size();
+    std::vector<int> rc((size_t)nd, 0);
+    std::vector<std::string> err((size_t)nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++)
+        th.emplace_back([&, d] {
+            const int s0 = nseg * d / nd, s1 = nseg * (d + 1) / nd;        // whole segments per device
+            if (s1 <= s0) return;
+            std::vector<meme_kswr_t *> out((size_t)(s1 - s0));
+            for (int s = s0; s < s1; s++) out[(size_t)(s - s0)] = g_msw_res.data() + base[(size_t)s];
+            rc[(size_t)d] = a.matesw_batch(g_index[(size_t)d], s1 - s0, (const meme_seqpair_t *const *)(pairs + s0), n_pairs + s0, ref + s0, n_ref + s0, qer + s0, n_qer + s0,
+                                           &mo, out.data());
+            if (rc[(size_t)d]) err[(size_t)d] = a.last_error();
+        });
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rc[(size_t)d]) { fprintf(stderr, "[meme_b200] meme_matesw_batch failed (%d): %s\n", rc[(size_t)d], err[(size_t)d].c_str()); exit(EXIT_FAILURE); }
+    g_have_msw = true;
+    static bool at_exit = false;
+    if (!at_exit) {
+        at_exit = true;
+        atexit([] { fprintf(stderr, "[meme_b200] mate rescue: %ld Smith-Waterman results in %ld blocks of worker_sam taken from the GPU\n", g_msw_taken.load(), g_msw_blocks.load()); });
+    }
+    int64_t nr = 0;
+    for (int s = 0; s < nseg; s++) nr += n_ref[s];
+    fprintf(stderr, "[meme_b200] mate rescue: %ld Smith-Waterman pairs (%.0f MB of windows) on the GPU: collect %.1f ms, align %.1f ms\n", (long)n, nr / 1e6, collect_ms,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+}
+
+// worker_sam, where it would call mem_sam_pe_batch for the read pairs [pair_begin, pair_end) of a block: aln[regid] for the
+// block's pcnt pairs.  false = nothing from the GPU for this chunk (the caller runs the reference's own batch step).
+bool meme_glue_take_matesw(int pair_begin, int pair_end, int64_t pcnt, kswr_t *aln)
+{
+    if (!g_have_msw) return false;
+    const int64_t b = g_msw_off[(size_t)pair_begin], e = g_msw_off[(size_t)pair_end];
+    if (e - b != pcnt) { fprintf(stderr, "[meme_b200] mate rescue: block of read pairs %d..%d has %ld pairs, the pre-pass saw %ld\n", pair_begin, pair_end, (long)pcnt, (long)(e - b)); exit(EXIT_FAILURE); }
+    if (pcnt) memcpy(aln, g_msw_res.data() + b, (size_t)pcnt * sizeof(kswr_t));
+    g_msw_taken += (long)pcnt; g_msw_blocks++;
+    return true;
+}
+
 // Seed extension through the GPU: same contract as getScores8/16 / scalarBandedSWAWrapper (fills the six
 // result fields of every pair in place).  One handle per host thread (kt_for worker).
 bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
@@ -561,6 +641,31 @@ void meme_glue_pinned_reserve(int threads, long reads_per_chunk)
             total += b;
         }
     fprintf(stderr, "[meme_b200] %.2f GB of pinned pair arenas reserved for %d threads in %.2f s\n", total / 1e9, threads,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+
+// per-thread arenas of the mate-rescue pre-pass (meme_matesw_chunk asks for the same sizes on its first chunk)
+void meme_glue_matesw_arena_sizes(int threads, long reads_per_chunk, size_t sizes[3])
+{
+    const size_t est = (size_t)(reads_per_chunk / (threads > 0 ? threads : 1) + 1);      // about two rescue pairs per read pair
+    sizes[0] = est * sizeof(SeqPair); sizes[1] = est * 700; sizes[2] = est * 160;
+}
+
+void meme_glue_pinned_reserve_matesw(int threads, long reads_per_chunk)
+{
+    if (threads < 1 || reads_per_chunk < 1) return;
+    auto t0 = std::chrono::steady_clock::now();
+    size_t sizes[3], total = 0;
+    meme_glue_matesw_arena_sizes(threads, reads_per_chunk, sizes);
+    for (int t = 0; t < threads; t++)
+        for (size_t b : sizes) {
+            void *p = nullptr;
+            if (api().pinned_alloc(b, &p)) return;
+            std::lock_guard<std::mutex> lk(g_pin_mu);
+            g_pin_cache.push_back({p, b});
+            total += b;
+        }
+    fprintf(stderr, "[meme_b200] %.2f GB of pinned mate-rescue arenas reserved for %d threads in %.2f s\n", total / 1e9, threads,
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 }
 

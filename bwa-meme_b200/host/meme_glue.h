@@ -13,6 +13,11 @@
 //                          CIGAR, NM, MD) of every region of the chunk is computed on the GPU   src/bwamem.cpp:L1962
 //   meme_glue_take_cigar   in mem_reg2aln(), in front of the band-doubling loop around bwa_gen_cigar2: a region the pre-pass
 //                          has seen takes its result from there                                  src/bwamem.cpp:L2339
+//   meme_matesw_chunk      in mem_process_seqs(), before kt_for(worker_sam), paired-end chunks: with MEME_B200_MATE=1 the mate-rescue
+//                          Smith-Waterman pairs of the whole chunk (collected with the reference's own mem_sam_pe_batch_pre) are
+//                          aligned on the GPU                                                   src/bwamem.cpp:L1962
+//   meme_glue_take_matesw  in worker_sam(), in front of mem_sam_pe_batch: a block's kswr_t results come from the pre-pass
+//                                                                                              src/bwamem.cpp:L1877
 //   meme_glue_bsw          first line of BandedPairWiseSW::getScores8/16 and scalarBandedSWAWrapper
 //                                                             src/bandedSWA.cpp:L242, L412, L1117, L1970, L2664, L3469, L4198
 //                          (per-call seam; reached only by callers other than the chunk-level driver below)
@@ -24,6 +29,7 @@
 #pragma once
 #include <stdint.h>
 #include "bwamem.h"
+#include "ksw.h"
 #include "bandedSWA.h"
 #include "LearnedIndex_seeding.h"
 
@@ -33,6 +39,7 @@ bool meme_glue_take(const bseq1_t *s, mem_tlv *smems, u64v *hits);
 bool meme_glue_take_chains(bseq1_t *s, int l, mem_chain_v *chn);
 void meme_glue_dump_chains(const bseq1_t *seq, int nseq, const mem_chain_v *chain_ar);
 bool meme_glue_take_cigar(const char *query, const mem_alnreg_t *ar, uint32_t **cigar, int *n_cigar, int *NM);
+bool meme_glue_take_matesw(int pair_begin, int pair_end, int64_t pcnt, kswr_t *aln);
 bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, int n_pairs, int w, int o_del, int e_del,
                    int o_ins, int e_ins, int zdrop, int end_bonus, int a, int b);
 
@@ -43,9 +50,15 @@ bool meme_glue_cigar_enabled();
 int64_t meme_glue_code_off(int read);
 void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
                          int n_reads, const mem_opt_t *opt, int64_t l_pac);
+bool meme_glue_matesw_enabled();
+void meme_glue_matesw_skip();
+void meme_glue_matesw_run(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer, const mem_opt_t *opt,
+                          std::vector<int64_t> &pair_off, double collect_ms);
 bool meme_glue_bsw_enabled();
 bool meme_glue_bsw_text_mode();
 void meme_glue_pinned_reserve(int threads, long reads_per_chunk);
+void meme_glue_pinned_reserve_matesw(int threads, long reads_per_chunk);
+void meme_glue_matesw_arena_sizes(int threads, long reads_per_chunk, size_t sizes[3]);
 void *meme_glue_pinned_alloc(size_t bytes);
 void meme_glue_pinned_free(void *p);
 void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,

@@ -17,6 +17,7 @@ HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_d
 def patch_bwamem(src: str) -> str:
     out, n_seed, n_close, n_chunk, n_inc, n_aln, n_take, n_dump, in_k1 = [], 0, 0, 0, 0, 0, 0, 0, False
     n_sam, n_cig, n_cig_end, in_r2a = 0, 0, 0, False
+    n_msw = 0
     for line in src.splitlines(keepends=True):
         if line.startswith("mem_aln_t mem_reg2aln("):
             in_r2a = True
@@ -31,7 +32,11 @@ def patch_bwamem(src: str) -> str:
             continue
         if re.match(r"\s*kt_for\(worker_sam, &w,\s+n_\);", line):
             out.append("    meme_cigar_chunk(w, n_);   // meme_b200: global alignments of all regions on the GPU\n")
+            out.append("    meme_matesw_chunk(w, n_);   // meme_b200: mate-rescue Smith-Waterman of the whole chunk on the GPU\n")
             n_sam += 1
+        if line.strip() == "mem_sam_pe_batch(w->opt, &w->mmc, pcnt, pcnt8, aln, maxRefLen, maxQerLen, tid);" and not n_msw:
+            out.append("        if (!meme_glue_take_matesw(start >> 1, end >> 1, pcnt, aln))   // meme_b200: the block's mate-rescue results from the GPU, if any\n")
+            n_msw += 1
         if line.startswith("int mem_kernel1_core_Learned("):
             in_k1 = True
         if in_k1 and line.strip() == "smems->n = 0;" and not n_take:
@@ -69,9 +74,10 @@ def patch_bwamem(src: str) -> str:
         if line.startswith("void mem_process_seqs(") and not n_aln:
             out.append("bool meme_extend_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
             out.append("void meme_cigar_chunk(worker_t &w, int n);    // meme_b200 (meme_extend.inl)\n")
+            out.append("void meme_matesw_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
         out.append(line)
     assert (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump) == (1, 1, 1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump)
-    assert (n_sam, n_cig, n_cig_end) == (1, 1, 1), (n_sam, n_cig, n_cig_end)
+    assert (n_sam, n_cig, n_cig_end, n_msw) == (1, 1, 1, 1), (n_sam, n_cig, n_cig_end, n_msw)
     return "".join(out) + '\n#include "meme_extend.inl"   // meme_b200: chunk-level seed extension\n'
 
 

@@ -42,7 +42,7 @@ sams = {}
 arms = [("reference_cpu", ref, {}), ("gpu_seed", b200, {"MEME_B200": "1"}),
         ("gpu_seed_bsw", b200, {"MEME_B200": "1", "MEME_B200_BSW": "1"}),
         ("gpu_seed_chain_bsw", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1"}),
-        ("gpu_all", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"})]
+        ("gpu_all", b200, {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1", "MEME_B200_MATE": "1"})]
 if os.environ.get("ARMS"):
     arms = [a for a in arms if a[0] in os.environ["ARMS"].split(",") or a[0] == "reference_cpu"]
 nreads = N * (2 if PE else 1)
@@ -66,6 +66,8 @@ for name, exe, env in arms:
     if gpu_lines: out["gpu_seed_log"] = gpu_lines[-1]
     cig_lines = [l for l in p.stderr.splitlines() if "[meme_b200] global alignments" in l]
     if cig_lines: out["gpu_cigar_log"] = cig_lines[-1]
+    msw_lines = [l for l in p.stderr.splitlines() if "[meme_b200] mate rescue:" in l]
+    if msw_lines: out["gpu_matesw_log"] = msw_lines[-2:]
     ext_lines = [l for l in p.stderr.splitlines() if "[meme_b200] extended" in l]
     if ext_lines: out["gpu_extend_log"] = ext_lines[-1]
     if os.environ.get("E2E_VERBOSE"):

@@ -1,16 +1,12 @@
 #!/bin/bash
-# round-2 validation on one B200: all GPU tests, smoke, the full bench line, the reference arm, the ncu launch list of the bench command
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_gpu_final.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 1500 python bench.py > gpurun_out/r2_bench_final_1gpu.json 2> gpurun_out/r2_bench_final_1gpu.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench_final_1gpu.err | cut -c1-200
-python - <<'PY'
-import json
-j=json.loads(open('gpurun_out/r2_bench_final_1gpu.json').read().strip().splitlines()[-1])
-print('value', j['value'], 'e2e', j['e2e']['value'], 'frac', j['roofline']['frac'], 'cpu', j['cpu_baseline']['value'], 'wide', j['wide']['value'])
-a=j['align_e2e']; print('align se', a['se']['reference_cpu']['Mbases_per_s'], a['se']['gpu']['Mbases_per_s'], a['se']['sam_identical'], 'pe', a['pe']['reference_cpu']['Mbases_per_s'], a['pe']['gpu']['Mbases_per_s'], a['pe']['sam_identical'])
-b=j['bsw']; print('bsw gcups', b['gcups'], 'pairs/s', b['pairs_per_s'], 'cpu', b.get('cpu_baseline'))
-PY
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_final_reference.json 2> gpurun_out/r2_bench_final_reference.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/r2_bench_final_reference.json
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_ncu_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-align > /dev/null 2> gpurun_out/r2_ncu_launches_bench.err; echo "ncu rc=$?"; wc -l gpurun_out/r2_ncu_launches_bench.csv
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/r2_pytest_gpu_mate.log
+N=400000 timeout 600 python profiles/prof_matesw.py > gpurun_out/r2_matesw_bench.json 2> gpurun_out/r2_matesw_bench.err; echo "matesw bench rc=$?"; cut -c1-1200 gpurun_out/r2_matesw_bench.json
+E2E_VERBOSE=1 PE=1 ARMS=gpu_all N=1000000 timeout 1200 python profiles/e2e_align.py > gpurun_out/r2_e2e_pe_1M_mate2.jsonl 2>gpurun_out/r2_e2e_pe_1M_mate2.err; echo "pe rc=$?"; cut -c1-250 gpurun_out/r2_e2e_pe_1M_mate2.jsonl; grep "mate rescue\|Processed\|reserved" gpurun_out/r2_e2e_pe_1M_mate2.err | cut -c1-250
+E2E_VERBOSE=1 ARMS=gpu_all N=2000000 timeout 1200 python profiles/e2e_align.py > gpurun_out/r2_e2e_se_2M_mate2.jsonl 2>gpurun_out/r2_e2e_se_2M_mate2.err; echo "se rc=$?"; cut -c1-250 gpurun_out/r2_e2e_se_2M_mate2.jsonl
+# ncu: one launch each of the two new kernels
+N=131072 REPS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_matesw -c 1 -f -o gpurun_out/ncu_k_matesw python profiles/prof_matesw.py > gpurun_out/ncu_k_matesw.log 2>&1; echo "ncu matesw rc=$?"
+isa=avx512bw; grep -q " avx512bw" /proc/cpuinfo || isa=avx2
+MEME_B200_LIB=$PWD/bwa-meme_b200/libmeme_b200.so MEME_B200=1 MEME_B200_CHAIN=1 MEME_B200_BSW=1 MEME_B200_SAM=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cigar_align -s 2 -c 1 -f -o gpurun_out/ncu_k_cigar_align oracle/_ref/bwa-meme-b200_mode3.$isa mem -7 -t 16 -K 100000000 /tmp/meme_e2e/ref.fa /tmp/meme_e2e/se2000000.fq -o /tmp/meme_e2e/ncu.sam > gpurun_out/ncu_k_cigar_align.log 2>&1; echo "ncu cigar rc=$?"
+ls -la gpurun_out/*.ncu-rep

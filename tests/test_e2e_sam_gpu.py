@@ -72,6 +72,15 @@ def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1"})
     assert "global alignments of" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
+    # + the mate-rescue Smith-Waterman of the whole chunk (row f2): alone, and with every other stage
+    for hooks in ({"MEME_B200": "1", "MEME_B200_MATE": "1"},
+                  {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1", "MEME_B200_MATE": "1"}):
+        sam, err = _run(exe, [golden_index, f1, f2], hooks)
+        assert "mate rescue:" in err and "Smith-Waterman pairs" in err
+        if " avx512bw" in open("/proc/cpuinfo").read():        # kswv (and the seam in worker_sam) exists in AVX512 builds only
+            taken = [l for l in err.splitlines() if "Smith-Waterman results in" in l]
+            assert taken and int(taken[-1].split("mate rescue:")[1].split()[0]) > 0, err[-2000:]
+        assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
 
 
 def _ref_binary():
@@ -139,8 +148,8 @@ def test_two_gpus_sam_identical(pkg, golden_index, tmp_path):
     assert "resident on 2 GPU(s)" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
     sam, err = _run(exe, [golden_index, f1, f2], {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1",
-                                                  "MEME_B200_DEVICES": "0,1"})
-    assert "seeded and chained" in err and "global alignments of" in err
+                                                  "MEME_B200_MATE": "1", "MEME_B200_DEVICES": "0,1"})
+    assert "seeded and chained" in err and "global alignments of" in err and "mate rescue:" in err
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
 
 
