@@ -27,7 +27,7 @@ EXPORTS = [
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
     "meme_cigar_batch", "meme_cigar_last", "meme_cigar_warmup",
-    "meme_matesw_batch", "meme_matesw_last", "meme_matesw_warmup",
+    "meme_matesw_batch", "meme_matesw_last", "meme_matesw_warmup", "meme_sa_build",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -178,6 +178,7 @@ def lib():
         L.meme_matesw_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, C.POINTER(MateswOpt), vp]
         L.meme_matesw_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
         L.meme_matesw_warmup.argtypes = [vp, i64, C.c_int, C.c_int]
+        L.meme_sa_build.argtypes = [C.c_int, vp, i64, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -187,6 +188,18 @@ def lib():
 def _check(rc: int, what: str):
     if rc != 0:
         raise MemeError(f"{what} failed with {rc}: {lib().meme_last_error().decode()}")
+
+
+def sa_build(text: np.ndarray, device: int = 0, want_keys: bool = True) -> dict:
+    """meme_sa_build: suffix array (int64) of the fwd+RC text in the reference's order, the suffixes' 64-bit keys, the padding."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    n = len(text)
+    sa = np.empty(n, np.int64)
+    keys = np.empty(n, np.uint64) if want_keys else None
+    pad, rounds = C.c_int32(), C.c_int32()
+    _check(lib().meme_sa_build(int(device), text.ctypes.data, n, sa.ctypes.data, keys.ctypes.data if want_keys else None, C.byref(pad), C.byref(rounds)),
+           "meme_sa_build")
+    return {"sa": sa, "keys": keys, "pad": pad.value, "rounds": rounds.value}
 
 
 class MemeIndex:

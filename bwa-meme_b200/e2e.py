@@ -40,7 +40,8 @@ def run_mem(exe: str, prefix: str, fastqs: list[str], out_sam: str, threads: int
     proc = [l for l in p.stderr.splitlines() if "Processed" in l and "real sec" in l]
     real = sum(float(l.split("CPU sec,")[1].split("real sec")[0]) for l in proc)
     logs = [l for l in p.stderr.splitlines() if l.startswith("[meme_b200]")]
-    return {"real_s": real, "wall_s": wall, "chunks": len(proc), "log": logs, "stderr_tail": p.stderr[-6000:]}
+    chunk_s = [float(l.split("CPU sec,")[1].split("real sec")[0]) for l in proc]
+    return {"real_s": real, "wall_s": wall, "chunks": len(proc), "chunk_s": chunk_s, "log": logs, "stderr_tail": p.stderr[-6000:]}
 
 
 def sam_body(path: str) -> bytes:
@@ -59,8 +60,8 @@ def compare_arms(prefix: str, fastqs: list[str], n_reads: int, read_len: int, th
     g = run_mem(b200, prefix, fastqs, os.path.join(workdir, f"{tag}_gpu.sam"), threads, gpu_env)
     same = sam_body(os.path.join(workdir, f"{tag}_ref.sam")) == sam_body(os.path.join(workdir, f"{tag}_gpu.sam"))
     bases = n_reads * read_len
-    out["reference_cpu"] = {"Mbases_per_s": bases / r["real_s"] / 1e6, "real_s": r["real_s"], "threads": threads}
-    out["gpu"] = {"Mbases_per_s": bases / g["real_s"] / 1e6, "real_s": g["real_s"], "threads": threads, "env": gpu_env,
+    out["reference_cpu"] = {"Mbases_per_s": bases / r["real_s"] / 1e6, "real_s": r["real_s"], "chunk_s": r["chunk_s"], "threads": threads}
+    out["gpu"] = {"Mbases_per_s": bases / g["real_s"] / 1e6, "real_s": g["real_s"], "chunk_s": g["chunk_s"], "threads": threads, "env": gpu_env,
                   "log_tail": g["log"][-6:]}
     out["sam_identical"] = bool(same)
     out["reads"] = n_reads

@@ -10,8 +10,10 @@ repo's `meme_index_load`) opens:
   <p>.suffixarray_uint64_L{0,1,2}_PARAMETERS     (reference trainer is Rust and cannot be built
                                                   offline; see prmi_train.py)
 
-The suffix array is built by prefix doubling on torch tensors (CPU or CUDA): torch is
-plumbing here (sort / cumsum / gather), not a hot path.  Ordering is the reference's:
+On a GPU the suffix array and the keys come from the library's own builder (meme_sa_build,
+csrc/meme_sa.cu: prefix doubling with device radix sorts between small kernels); the same algorithm
+on torch tensors (suffix_array / rmi_keys below) serves CPU-only machines and pins the native one in
+tests/test_index_gpu.py.  Ordering is the reference's:
 the text `fwd + RC` is padded with P = max(longest A run, longest T run)+1 `T`s, suffixes
 compare with the usual end-of-string-is-smallest rule, and suffixes that start inside the
 padding are dropped (src/Learnedindex.cpp:L190-229, L242, L469-473).
@@ -168,11 +170,20 @@ def build_index(prefix: str, genome: np.ndarray, bits: int | None = None, device
     text = fwd_rc_text(genome)
     write_bntseq(prefix, genome, name)
     text.tofile(prefix + ".0123")
-    sa = suffix_array(text, device=device, verbose=verbose)
+    dev = torch.device(device)
+    if dev.type == "cuda" and not os.environ.get("MEME_INDEX_TORCH"):
+        # the library's own builder (meme_sa_build: prefix doubling with device radix sorts, csrc/meme_sa.cu)
+        from . import capi
+        r = capi.sa_build(text, device=dev.index or 0)
+        sa = torch.from_numpy(r["sa"])
+        pad = r["pad"]
+        keys = torch.from_numpy(r["keys"].view(np.int64)).to(dev)
+    else:
+        sa = suffix_array(text, device=device, verbose=verbose)
+        t8 = torch.as_tensor(text, dtype=torch.uint8).to(sa.device)
+        pad = pad_len_of(t8)
+        keys = rmi_keys(text, sa, pad)
     write_pos_packed(prefix + ".pos_packed", sa)
-    t8 = torch.as_tensor(text, dtype=torch.uint8).to(sa.device)
-    pad = pad_len_of(t8)
-    keys = rmi_keys(text, sa, pad)
     n = int(sa.numel())
     if write_keys_file:
         with open(prefix + ".suffixarray_uint64", "wb") as f:

@@ -346,6 +346,16 @@ int meme_matesw_warmup(meme_index_t *ix, int64_t n_pairs, int len1, int len2);
 int  meme_pinned_alloc(size_t bytes, void **out);
 void meme_pinned_free(void *p);
 
+/* ---- index pipeline ---------------------------------------------- */
+
+/* Suffix array of the fwd+RC text (codes 0..3, n bases) in the reference's order, and optionally the 64-bit key of every
+ * suffix: replaces the sais call and the key loop of the reference's index builder (buildSAandLEP / build_learned_index,
+ * src/Learnedindex.cpp:L134-555).  sa_out[n] is what the reference packs into <prefix>.pos_packed, keys_out[n] (may be NULL)
+ * what it writes to <prefix>.suffixarray_uint64 after the count; *pad_out = the number of `T`s the reference pads the text with
+ * (L190-229), *rounds_out = doubling rounds after the first sort.  Host pointers; prefix doubling with device radix sorts.
+ * Limit: n + pad < 2^31 (chr1 scale; 32-bit suffix ids). */
+int meme_sa_build(int device, const uint8_t *text, int64_t n, int64_t *sa_out, uint64_t *keys_out, int32_t *pad_out, int32_t *rounds_out);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char *meme_last_error(void);     /* thread-local text of the last failure */
 int         meme_device_count(void);

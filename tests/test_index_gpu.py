@@ -44,3 +44,41 @@ def test_missing_files_error(pkg, tmp_path):
     with pytest.raises(capi.MemeError) as e:
         capi.MemeIndex(str(tmp_path / "nope.fa"), mode=3)
     assert "cannot open" in str(e.value)
+
+
+def test_native_suffix_array_matches_reference_files_and_torch(pkg, golden_index, golden_meta, tmp_path):
+    """meme_sa_build (row f3: prefix doubling with device radix sorts) gives the suffix array and keys the reference's own builder
+    wrote for the golden genome (byte-equal files, sha256 from `bwa-meme index -a meme`), and agrees with the torch restatement
+    on low-entropy texts, homopolymer ends and a repeat-rich genome."""
+    import hashlib
+    import torch
+    from bwa_meme_b200 import capi, index_build, synth
+    text = np.fromfile(golden_index + ".0123", dtype=np.uint8)
+    r = capi.sa_build(text)
+    assert (r["sa"] == index_build.read_pos_packed(golden_index + ".pos_packed").astype(np.int64)).all()
+    raw = np.fromfile(golden_index + ".suffixarray_uint64", dtype=np.uint64)
+    assert int(raw[0]) == len(text) and (raw[1:] == r["keys"]).all()
+    # the whole pipeline through the native builder: every file byte-equal to the reference builder's
+    g = text[:len(text) // 2]
+    prefix = str(tmp_path / "native.fa")
+    index_build.build_index(prefix, g, bits=16, device="cuda")
+    for ext, want in golden_meta["sha256"].items():
+        if "PARAMETERS" in ext:
+            continue                       # the trainer is the repo's own (format-compatible), pinned by test_index_build.py
+        assert hashlib.sha256(open(prefix + ext, "rb").read()).hexdigest() == want, ext
+    rng = np.random.default_rng(7)
+    texts = [index_build.fwd_rc_text(rng.integers(0, 2, size=int(rng.integers(20, 3000)), dtype=np.uint8)) for _ in range(4)]
+    texts.append(index_build.fwd_rc_text(np.array([0, 0, 0, 1, 2, 3, 0, 0], np.uint8)))
+    texts.append(index_build.fwd_rc_text(np.zeros(500, np.uint8)))                         # one long A run + one long T run
+    texts.append(index_build.fwd_rc_text(synth.make_genome(200000, seed=9, n_families=6, copies=40, rep_len=800)))
+    big = index_build.fwd_rc_text(synth.make_genome_large(3000000, n_families=10, copies=30))          # several doubling rounds at 6 M suffixes
+    want = index_build.suffix_array(big, device="cuda")
+    got = capi.sa_build(big)
+    assert got["rounds"] >= 2 and (got["sa"] == want.cpu().numpy()).all()
+    for t in texts:
+        want = index_build.suffix_array(t)
+        pad = index_build.pad_len_of(torch.as_tensor(t))
+        got = capi.sa_build(t)
+        assert got["pad"] == pad
+        assert (got["sa"] == want.numpy()).all()
+        assert (got["keys"].view(np.int64) == index_build.rmi_keys(t, want, pad).numpy()).all()
