@@ -27,7 +27,7 @@ EXPORTS = [
     "meme_bsw_attach_text", "meme_bsw_upload_segments", "meme_bsw_download_segments", "meme_bsw_batch_ext", "meme_bsw_set_match", "meme_bsw_run_ext", "meme_bsw_download_w", "meme_pinned_alloc", "meme_pinned_free",
     "meme_chain_set_contigs", "meme_chain_run", "meme_chain_download", "meme_chain_last_ms", "meme_chain_batch_multi", "meme_chain_warmup",
     "meme_cigar_batch", "meme_cigar_last", "meme_cigar_warmup",
-    "meme_matesw_batch", "meme_matesw_last", "meme_matesw_warmup", "meme_sa_build",
+    "meme_matesw_batch", "meme_matesw_last", "meme_matesw_warmup", "meme_sa_build", "meme_prmi_train",
     "meme_last_error", "meme_device_count", "meme_version",
 ]
 
@@ -179,6 +179,7 @@ def lib():
         L.meme_matesw_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
         L.meme_matesw_warmup.argtypes = [vp, i64, C.c_int, C.c_int]
         L.meme_sa_build.argtypes = [C.c_int, vp, i64, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.meme_prmi_train.argtypes = [C.c_int, vp, i64, C.c_int32, vp, vp, i64, C.POINTER(i64), vp]
         L.meme_last_error.restype = C.c_char_p
         L.meme_version.restype = C.c_char_p
         _lib = L
@@ -200,6 +201,23 @@ def sa_build(text: np.ndarray, device: int = 0, want_keys: bool = True) -> dict:
     _check(lib().meme_sa_build(int(device), text.ctypes.data, n, sa.ctypes.data, keys.ctypes.data if want_keys else None, C.byref(pad), C.byref(rounds)),
            "meme_sa_build")
     return {"sa": sa, "keys": keys, "pad": pad.value, "rounds": rounds.value}
+
+
+RMI_REC_DTYPE = np.dtype([("alpha", "<f8"), ("beta", "<f8"), ("err", "<u8")])
+
+
+def prmi_train(keys: np.ndarray, bits: int, device: int = 0):
+    """meme_prmi_train: (l1 records, l2 records, stats) from the sorted uint64 keys."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    n = len(keys)
+    l2 = np.zeros(1 << bits, RMI_REC_DTYPE)
+    cap = n // 20 + 1
+    l1 = np.zeros(cap, RMI_REC_DTYPE)
+    n_l1 = C.c_int64()
+    stats = np.zeros(2, np.int64)
+    _check(lib().meme_prmi_train(int(device), keys.ctypes.data, n, int(bits), l2.ctypes.data, l1.ctypes.data, cap, C.byref(n_l1), stats.ctypes.data),
+           "meme_prmi_train")
+    return l1[:n_l1.value].copy(), l2, {"n_leaf": 1 << bits, "n_dense_leaf": int(stats[0]), "n_sub": int(n_l1.value), "max_window": int(stats[1])}
 
 
 class MemeIndex:

@@ -191,6 +191,14 @@ def build_index(prefix: str, genome: np.ndarray, bits: int | None = None, device
             f.write(keys.cpu().numpy().tobytes())
     if bits is None:
         bits = prmi_train.default_bits(n)
-    stats = prmi_train.train_and_write(prefix + ".suffixarray_uint64", keys, bits, verbose=verbose)
+    if dev.type == "cuda" and not os.environ.get("MEME_INDEX_TORCH"):
+        from . import capi                      # the library's own trainer (meme_prmi_train, csrc/meme_prmi.cu)
+        l1, l2, stats = capi.prmi_train(r["keys"], bits, device=dev.index or 0)
+        base = prefix + ".suffixarray_uint64"
+        np.array([bits], dtype=np.uint64).tofile(base + "_L0_PARAMETERS")
+        l1.tofile(base + "_L1_PARAMETERS")
+        l2.tofile(base + "_L2_PARAMETERS")
+    else:
+        stats = prmi_train.train_and_write(prefix + ".suffixarray_uint64", keys, bits, verbose=verbose)
     stats.update({"sa_num": n, "l_pac": int(genome.shape[0]), "pad": pad, "bits": bits})
     return stats

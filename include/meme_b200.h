@@ -356,6 +356,16 @@ void meme_pinned_free(void *p);
  * Limit: n + pad < 2^31 (chr1 scale; 32-bit suffix ids). */
 int meme_sa_build(int device, const uint8_t *text, int64_t n, int64_t *sa_out, uint64_t *keys_out, int32_t *pad_out, int32_t *rounds_out);
 
+/* P-RMI training on the device: the `pwl{BIT},linear,linear_spline` model files of the reference's Rust trainer
+ * (RMI/rmi_lib/src/train/two_layer.rs; build_rmis_dna.sh) from the n sorted keys of meme_sa_build.  l2_out: 2^bits records of
+ * 24 bytes {f64 alpha, f64 beta, u64 err} (<prefix>.suffixarray_uint64_L2_PARAMETERS), l1_out: the sub-models of dense leaves
+ * (_L1_PARAMETERS; l1_cap >= n / 20 + 1 records, *n_l1 = records written, at least one); _L0_PARAMETERS is the single word `bits`.
+ * Format-compatible with the reference loader (learned_index_load, src/LearnedIndex_seeding.cpp:L74-122); the values are this
+ * repo's own (the last-mile search is self-correcting, so alignment results do not depend on them).  stats_out (may be NULL):
+ * [0] dense leaves, [1] widest error window of a plain leaf. */
+int meme_prmi_train(int device, const uint64_t *keys, int64_t n, int32_t bits, void *l2_out, void *l1_out, int64_t l1_cap, int64_t *n_l1,
+                    int64_t *stats_out);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char *meme_last_error(void);     /* thread-local text of the last failure */
 int         meme_device_count(void);

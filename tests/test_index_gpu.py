@@ -82,3 +82,38 @@ def test_native_suffix_array_matches_reference_files_and_torch(pkg, golden_index
         assert got["pad"] == pad
         assert (got["sa"] == want.numpy()).all()
         assert (got["keys"].view(np.int64) == index_build.rmi_keys(t, want, pad).numpy()).all()
+
+
+@pytest.mark.parametrize("bits", [4, 10, 16])
+def test_native_trainer_error_bounds_hold(pkg, golden_index, mid_index, bits):
+    """meme_prmi_train (row f3): for every training key the true rank lies inside [pred - below, pred + above] of the model the
+    reference's lookup selects (learned_index_lookup, restated in prmi_train.lookup_numpy), with plain and dense leaves, and
+    unseen keys stay within one of it; the seeding kernel gives the same SMEMs with these models as with the torch-trained ones."""
+    from bwa_meme_b200 import capi, prmi_train
+    for prefix in (golden_index, mid_index[0]):
+        raw = np.fromfile(prefix + ".suffixarray_uint64", dtype=np.uint64)
+        n, keys = int(raw[0]), raw[1:]
+        l1, l2, stats = capi.prmi_train(keys, bits)
+        assert l2.shape[0] == 1 << bits and l1.shape[0] >= 1
+        if bits == 4:
+            assert stats["n_dense_leaf"] > 0 and (l2["err"] >> np.uint64(63)).any()
+        pos, below, above = prmi_train.lookup_numpy(l1, l2, keys, n)
+        d = pos - np.arange(n)
+        assert (d <= below).all() and (-d <= above).all()
+        rng = np.random.default_rng(3)
+        q = keys[rng.integers(0, n, 20000)] ^ (np.uint64(1) << rng.integers(0, 50, 20000).astype(np.uint64))
+        pos, below, above = prmi_train.lookup_numpy(l1, l2, q, n)
+        d = pos - np.searchsorted(keys, q)
+        assert (d <= below + 1).all() and (-d <= above + 1).all()
+
+
+def test_native_index_seeds_like_torch_index(pkg, golden_genome, golden_index, golden_reads, tmp_path):
+    from bwa_meme_b200 import capi, index_build
+    prefix = str(tmp_path / "native.fa")
+    index_build.build_index(prefix, golden_genome, bits=10, device="cuda")       # few leaves: dense ones with sub-models
+    a, b = capi.MemeIndex(prefix, mode=3), capi.MemeIndex(golden_index, mode=3)
+    codes, offs = golden_reads[150]
+    ra, rb = a.seed(codes, offs), b.seed(codes, offs)
+    a.close(); b.close()
+    for k in ("smems", "hits", "smem_off", "hit_off"):
+        assert (ra[k] == rb[k]).all()
