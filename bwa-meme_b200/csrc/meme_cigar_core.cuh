@@ -34,6 +34,7 @@ typedef unsigned int gu32;
 typedef unsigned long long gu64;
 
 #define CIG_MINUS_INF (-0x40000000)
+#define CIG_BATCH 8
 
 struct Seqs {               // one region's two sequences, oriented as bwa_gen_cigar2 aligns them
     const uint8_t *qs;      // query segment, already oriented: base j at qs[j * stride]
@@ -112,27 +113,40 @@ MEME_HD int global_align(const meme_cigar_opt_t &o, const Seqs &S, int w, const 
         h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : CIG_MINUS_INF;
         const int64_t zi = (int64_t)i * n_col - beg;
         *cells += (gu64)(end - beg);
-        for (j = beg; j < end; ++j) {
-            EH &p = C.row(j);
-            int h, m = p.h, e = p.e;
-            uint8_t d;
-            p.h = h1;
-            m += (int)(int8_t)(rowbits >> (8 * S.q(j)));
-            d = m >= e ? 0 : 1;
-            h = m >= e ? m : e;
-            d = h >= f ? d : 2;
-            h = h >= f ? h : f;
-            h1 = h;
-            t = m - oe_del;
-            e -= o.e_del;
-            d |= e > t ? 1 << 2 : 0;
-            e = e > t ? e : t;
-            p.e = e;
-            t = m - oe_ins;
-            f -= o.e_ins;
-            d |= f > t ? 2 << 4 : 0;
-            f = f > t ? f : t;
-            C.zz(zi + j) = d;
+        // the cells of a row depend on each other only through h1 / f, never through the row array (cell j is read, then
+        // written, and no other cell of this row touches it): the loads of CIG_BATCH cells are issued together, so that a
+        // thread has several memory requests in flight instead of one per cell (ncu: 33 warps stalled on long_scoreboard
+        // per issued instruction with one)
+        for (j = beg; j < end; j += CIG_BATCH) {
+            EH c[CIG_BATCH];
+            int qv[CIG_BATCH];
+#pragma unroll
+            for (int u = 0; u < CIG_BATCH; ++u)
+                if (j + u < end) { c[u] = C.row(j + u); qv[u] = S.q(j + u); }
+#pragma unroll
+            for (int u = 0; u < CIG_BATCH; ++u) {
+                if (j + u >= end) break;
+                int h, m = c[u].h, e = c[u].e;
+                uint8_t d;
+                const int hprev = h1;
+                m += (int)(int8_t)(rowbits >> (8 * qv[u]));
+                d = m >= e ? 0 : 1;
+                h = m >= e ? m : e;
+                d = h >= f ? d : 2;
+                h = h >= f ? h : f;
+                h1 = h;
+                t = m - oe_del;
+                e -= o.e_del;
+                d |= e > t ? 1 << 2 : 0;
+                e = e > t ? e : t;
+                EH &p = C.row(j + u);
+                p.h = hprev; p.e = e;
+                t = m - oe_ins;
+                f -= o.e_ins;
+                d |= f > t ? 2 << 4 : 0;
+                f = f > t ? f : t;
+                C.zz(zi + j + u) = d;
+            }
         }
         C.row(end).h = h1; C.row(end).e = CIG_MINUS_INF;
     }

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <vector>
 #include <omp.h>
+#include <thread>
 
 namespace meme_ext {
 
@@ -383,7 +384,6 @@ void meme_cigar_chunk(worker_t &w, int n)
     const mem_opt_t *opt = w.opt;
     const int64_t l_pac = w.fmi->idx->bns->l_pac;
     static std::vector<int64_t> task_off;          // one chunk at a time (mem_process_seqs); buffers reused across chunks
-    static std::vector<meme_cigar_task_t> tasks;
     static std::vector<int32_t> reg_w;
     task_off.resize((size_t)n + 1);
     task_off[0] = 0;
@@ -393,7 +393,7 @@ void meme_cigar_chunk(worker_t &w, int n)
         for (size_t k = 0; k < v.n; k++) if (v.a[k].rb >= 0 && v.a[k].re >= 0) c++;
         task_off[(size_t)i + 1] = task_off[(size_t)i] + c;
     }
-    tasks.resize((size_t)task_off[(size_t)n]);
+    meme_cigar_task_t *tasks = meme_glue_cigar_tasks(task_off[(size_t)n]);
     reg_w.resize((size_t)task_off[(size_t)n]);
 #pragma omp parallel for schedule(static) num_threads(std::max(1, (int)w.nthreads))
     for (int i = 0; i < n; i++) {
@@ -414,7 +414,7 @@ void meme_cigar_chunk(worker_t &w, int n)
             t++;
         }
     }
-    meme_glue_cigar_run(tasks, reg_w, task_off, w.seqs, n, opt, l_pac);
+    meme_glue_cigar_run(reg_w, task_off, w.seqs, n, opt, l_pac);
 }
 
 
@@ -425,14 +425,24 @@ void meme_cigar_chunk(worker_t &w, int n)
 // reference's own function, nothing restated -- and the pairs it produces are copied into per-thread pinned arenas; worker_sam
 // then runs unchanged up to the point where it would call mem_sam_pe_batch and takes the block's results from here instead
 // (meme_glue_take_matesw: aln[regid] of a block = the results of its read pairs in the order they were produced).
-void meme_matesw_chunk(worker_t &w, int n)
+static std::vector<meme_ext::Arena> g_msw_ar;
+static std::vector<int64_t> g_msw_pair_off;
+static double g_msw_collect_ms = 0;
+
+static bool meme_matesw_wanted(worker_t &w, int n)
+{
+    return meme_glue_matesw_enabled() && (w.opt->flag & MEM_F_PE) && !(w.opt->flag & MEM_F_NO_RESCUE) && n >= 2;
+}
+
+// host part: the chunk's rescue pairs into the per-thread arenas.  false = nothing to run on the device for this chunk.
+static bool meme_matesw_collect(worker_t &w, int n)
 {
     meme_glue_matesw_skip();       // nothing from an earlier chunk
-    if (!meme_glue_matesw_enabled() || !(w.opt->flag & MEM_F_PE) || (w.opt->flag & MEM_F_NO_RESCUE) || n < 2) return;
+    if (!meme_matesw_wanted(w, n)) return false;
+    std::vector<meme_ext::Arena> &ar = g_msw_ar;
+    std::vector<int64_t> &pair_off = g_msw_pair_off;
     const int T = std::max(1, (int)w.nthreads);
     const int np = n >> 1;
-    static std::vector<meme_ext::Arena> ar;
-    static std::vector<int64_t> pair_off;
     if ((int)ar.size() < T) ar.resize((size_t)T);
     {   // first chunk: the blocks the glue pinned when the index was loaded (best fit from its cache)
         size_t sz[3];
@@ -472,10 +482,41 @@ void meme_matesw_chunk(worker_t &w, int n)
             }
         }
     }
-    if (too_long) { meme_glue_matesw_skip(); return; }        // beyond the kernel's limits: this chunk takes the reference's own code
+    if (too_long) { meme_glue_matesw_skip(); return false; }        // beyond the kernel's limits: this chunk takes the reference's own code
     for (int p = 0; p < np; p++) pair_off[(size_t)p + 1] += pair_off[(size_t)p];
+    g_msw_collect_ms = (omp_get_wtime() - t0) * 1e3;
+    return true;
+}
+
+// device part: one call per GPU on the collected segments
+static void meme_matesw_run(worker_t &w)
+{
+    std::vector<meme_ext::Arena> &ar = g_msw_ar;
+    const int T = std::max(1, (int)w.nthreads);
     std::vector<SeqPair *> pp((size_t)T); std::vector<uint8_t *> rp((size_t)T), qp((size_t)T);
     std::vector<int64_t> pn((size_t)T), rn((size_t)T), qn((size_t)T);
     for (int t = 0; t < T; t++) { meme_ext::Arena &A = ar[(size_t)t]; pp[t] = A.pairs; pn[t] = A.n; rp[t] = A.ref; rn[t] = A.n_ref; qp[t] = A.qer; qn[t] = A.n_qer; }
-    meme_glue_matesw_run(T, pp.data(), pn.data(), rp.data(), rn.data(), qp.data(), qn.data(), w.opt, pair_off, (omp_get_wtime() - t0) * 1e3);
+    meme_glue_matesw_run(T, pp.data(), pn.data(), rp.data(), rn.data(), qp.data(), qn.data(), w.opt, g_msw_pair_off, g_msw_collect_ms);
+}
+
+void meme_matesw_chunk(worker_t &w, int n)
+{
+    if (meme_matesw_collect(w, n)) meme_matesw_run(w);
+}
+
+// Both pre-passes of the SAM stage.  The global alignments keep the GPU busy for most of their 70 ms while the host waits, and
+// collecting the rescue pairs is host work only, so the two can overlap (MEME_B200_OVERLAP=1: the alignments are driven from a
+// second thread).  Measured on 1 M pairs: 5 % per chunk in steady state, but the first chunk pays 0.26 s for the second thread's
+// cold start, so it is off by default (profiles/r2/README.md).
+void meme_sam_prepass(worker_t &w, int n)
+{
+    if (!meme_glue_cigar_enabled() || !meme_matesw_wanted(w, n) || !getenv("MEME_B200_OVERLAP")) {
+        meme_cigar_chunk(w, n);
+        meme_matesw_chunk(w, n);
+        return;
+    }
+    std::thread cig([&] { meme_cigar_chunk(w, n); });
+    const bool have = meme_matesw_collect(w, n);
+    cig.join();
+    if (have) meme_matesw_run(w);
 }

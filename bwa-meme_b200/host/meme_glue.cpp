@@ -110,10 +110,20 @@ size_t g_seed_arena_cap = 0;
 double g_seed_s = 0;
 long g_seed_reads = 0;
 // MEME_B200_SAM=1: the global alignments of the SAM stage, computed for every region of the chunk before worker_sam runs
-std::vector<uint8_t> g_codes;                   // base codes of the chunk's reads (filled by meme_glue_seed_chunk)
+// base codes of the chunk's reads (filled by meme_glue_seed_chunk), in page-locked memory: the seeding and the SAM-stage calls
+// both upload them, and a pageable source halves the copy rate
+struct PinnedBytes {
+    uint8_t *p = nullptr; size_t n = 0, cap = 0;
+    uint8_t *data() { return p; }
+    size_t size() const { return n; }
+    void resize(size_t need);
+};
+PinnedBytes g_codes;
 std::vector<int64_t> g_code_off;
 bool g_have_cigar = false;
-std::vector<meme_cigar_task_t> g_ctasks;
+PinnedBytes g_ctask_buf;                        // the chunk's meme_cigar_task_t array (page-locked: it is uploaded as it is)
+meme_cigar_task_t *g_ctasks = nullptr;
+int64_t g_n_ctasks = 0;
 std::vector<int32_t> g_creg_w;
 std::vector<int64_t> g_ctask_off;               // per read: its tasks
 std::vector<meme_cigar_result_t> g_cres;        // per device
@@ -129,6 +139,19 @@ std::atomic<long> g_cig_hit{0}, g_cig_miss{0};   // lookups of mem_reg2aln answe
 {
     fprintf(stderr, "[meme_b200] %s failed (%d): %s\n", what, rc, api().last_error());
     exit(EXIT_FAILURE);      // the reference's own error protocol
+}
+
+void PinnedBytes::resize(size_t need)
+{
+    if (need > cap) {
+        void *q = nullptr;
+        const size_t ncap = need + need / 8 + 4096;
+        int rc = api().pinned_alloc(ncap, &q);
+        if (rc) die("meme_pinned_alloc", rc);
+        if (p) api().pinned_free(p);              // contents are rewritten by every chunk
+        p = (uint8_t *)q; cap = ncap;
+    }
+    n = need;
 }
 
 }  // namespace
@@ -162,6 +185,12 @@ static void ensure_index()
             if (env_on("MEME_B200_MATE") && (rc = a.matesw_warmup(g_index[(size_t)d], warm / nd + 1, 640, 150))) die("meme_matesw_warmup", rc);
             if (env_on("MEME_B200_SAM") && (rc = a.cigar_warmup(g_index[(size_t)d], warm * 3 / nd + 1, 150))) die("meme_cigar_warmup", rc);
         }
+        // the chunk-sized host buffers of the glue, touched once so that the first chunk does not pay their page faults
+        g_codes.resize((size_t)warm * 152 + 1);
+        memset(g_codes.data(), 0, g_codes.size());
+        if (env_on("MEME_B200_SAM")) g_ctask_buf.resize((size_t)warm * 3 * sizeof(meme_cigar_task_t));
+        g_code_off.resize((size_t)warm + 1);
+        memset(g_code_off.data(), 0, g_code_off.size() * sizeof(g_code_off[0]));
         fprintf(stderr, "[meme_b200] warm-up batch of %ld reads in %.2f s\n", warm,
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
         if (env_on("MEME_B200_BSW")) {
@@ -198,7 +227,7 @@ void meme_glue_seed_chunk(const mem_opt_t *opt, const bntseq_t *bns, bseq1_t *se
     auto t0 = std::chrono::steady_clock::now();
     // base codes: nst_nt4_table of the ASCII read; worker_bwt converts seqs[i].seq in place later
     // (src/bwamem.cpp:L1277-1280) and later stages rely on that, so the reads are not touched here
-    std::vector<uint8_t> &codes = g_codes;
+    PinnedBytes &codes = g_codes;
     std::vector<int64_t> &off = g_code_off;
     g_have_cigar = false;
     off.resize((size_t)n + 1);
@@ -407,13 +436,21 @@ int64_t meme_glue_code_off(int read) { return g_code_off[(size_t)read]; }
 
 // tasks: every region of the chunk (task_off[i] .. task_off[i+1] are read i's); reg_w: the regions' ar->w.  One
 // meme_cigar_batch per device on contiguous shares; the results stay in the handles' pinned arrays until the next chunk.
-void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
+meme_cigar_task_t *meme_glue_cigar_tasks(int64_t n)
+{
+    g_ctask_buf.resize((size_t)(n > 0 ? n : 1) * sizeof(meme_cigar_task_t));
+    g_ctasks = (meme_cigar_task_t *)g_ctask_buf.data();
+    g_n_ctasks = n;
+    return g_ctasks;
+}
+
+void meme_glue_cigar_run(std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
                          int n_reads, const mem_opt_t *opt, int64_t l_pac)
 {
     Api &a = api();
     auto t0 = std::chrono::steady_clock::now();
-    g_ctasks.swap(tasks); g_creg_w.swap(reg_w); g_ctask_off.swap(task_off);
-    const int64_t n = (int64_t)g_ctasks.size();
+    g_creg_w.swap(reg_w); g_ctask_off.swap(task_off);
+    const int64_t n = g_n_ctasks;
     const int nd = (int)g_index.size();
     meme_cigar_opt_t co;
     memset(&co, 0, sizeof co);
@@ -428,7 +465,7 @@ void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int3
     for (int d = 0; d < nd; d++)
         th.emplace_back([&, d] {
             const int64_t b = g_cres_begin[(size_t)d], e = g_cres_begin[(size_t)d + 1];
-            rc[(size_t)d] = a.cigar_batch(g_index[(size_t)d], g_ctasks.data() + b, e - b, g_codes.data(), (int64_t)g_code_off[(size_t)n_reads], l_pac, &co,
+            rc[(size_t)d] = a.cigar_batch(g_index[(size_t)d], g_ctasks + b, e - b, g_codes.data(), (int64_t)g_code_off[(size_t)n_reads], l_pac, &co,
                                           &g_cres[(size_t)d]);
             if (rc[(size_t)d]) err[(size_t)d] = a.last_error();
         });

@@ -9,11 +9,12 @@
 //   meme_glue_take_chains  first line of that function's per-read loop: with MEME_B200_CHAIN=1 the read's filtered chains
 //                          come from the GPU and the loop body (seeding, mem_chain_Learned, mem_chain_flt) is skipped  L1249
 //   meme_glue_dump_chains  after that loop (test instrumentation, MEME_B200_DUMP_CHAINS=path)          L1410
-//   meme_cigar_chunk       in mem_process_seqs(), before kt_for(worker_sam): with MEME_B200_SAM=1 the global alignment (score,
+//   meme_sam_prepass       in mem_process_seqs(), before kt_for(worker_sam) = meme_cigar_chunk + meme_matesw_chunk:
+//   meme_cigar_chunk       with MEME_B200_SAM=1 the global alignment (score,
 //                          CIGAR, NM, MD) of every region of the chunk is computed on the GPU   src/bwamem.cpp:L1962
 //   meme_glue_take_cigar   in mem_reg2aln(), in front of the band-doubling loop around bwa_gen_cigar2: a region the pre-pass
 //                          has seen takes its result from there                                  src/bwamem.cpp:L2339
-//   meme_matesw_chunk      in mem_process_seqs(), before kt_for(worker_sam), paired-end chunks: with MEME_B200_MATE=1 the mate-rescue
+//   meme_matesw_chunk      paired-end chunks: with MEME_B200_MATE=1 the mate-rescue
 //                          Smith-Waterman pairs of the whole chunk (collected with the reference's own mem_sam_pe_batch_pre) are
 //                          aligned on the GPU                                                   src/bwamem.cpp:L1962
 //   meme_glue_take_matesw  in worker_sam(), in front of mem_sam_pe_batch: a block's kswr_t results come from the pre-pass
@@ -48,7 +49,8 @@ bool meme_glue_bsw(SeqPair *pairs, uint8_t *seq_buf_ref, uint8_t *seq_buf_qer, i
 #include "../../include/meme_b200.h"
 bool meme_glue_cigar_enabled();
 int64_t meme_glue_code_off(int read);
-void meme_glue_cigar_run(std::vector<meme_cigar_task_t> &tasks, std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
+meme_cigar_task_t *meme_glue_cigar_tasks(int64_t n);      // the chunk's task array, page-locked, owned by the glue
+void meme_glue_cigar_run(std::vector<int32_t> &reg_w, std::vector<int64_t> &task_off, const bseq1_t *seqs,
                          int n_reads, const mem_opt_t *opt, int64_t l_pac);
 bool meme_glue_matesw_enabled();
 void meme_glue_matesw_skip();

@@ -31,8 +31,7 @@ def patch_bwamem(src: str) -> str:
             in_r2a = False
             continue
         if re.match(r"\s*kt_for\(worker_sam, &w,\s+n_\);", line):
-            out.append("    meme_cigar_chunk(w, n_);   // meme_b200: global alignments of all regions on the GPU\n")
-            out.append("    meme_matesw_chunk(w, n_);   // meme_b200: mate-rescue Smith-Waterman of the whole chunk on the GPU\n")
+            out.append("    meme_sam_prepass(w, n_);   // meme_b200: global alignments of all regions + mate-rescue Smith-Waterman of the whole chunk on the GPU\n")
             n_sam += 1
         if line.strip() == "mem_sam_pe_batch(w->opt, &w->mmc, pcnt, pcnt8, aln, maxRefLen, maxQerLen, tid);" and not n_msw:
             out.append("        if (!meme_glue_take_matesw(start >> 1, end >> 1, pcnt, aln))   // meme_b200: the block's mate-rescue results from the GPU, if any\n")
@@ -73,8 +72,7 @@ def patch_bwamem(src: str) -> str:
             continue
         if line.startswith("void mem_process_seqs(") and not n_aln:
             out.append("bool meme_extend_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
-            out.append("void meme_cigar_chunk(worker_t &w, int n);    // meme_b200 (meme_extend.inl)\n")
-            out.append("void meme_matesw_chunk(worker_t &w, int n);   // meme_b200 (meme_extend.inl)\n")
+            out.append("void meme_sam_prepass(worker_t &w, int n);    // meme_b200 (meme_extend.inl)\n")
         out.append(line)
     assert (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump) == (1, 1, 1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump)
     assert (n_sam, n_cig, n_cig_end, n_msw) == (1, 1, 1, 1), (n_sam, n_cig, n_cig_end, n_msw)
