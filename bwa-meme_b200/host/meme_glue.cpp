@@ -1,6 +1,7 @@
 // meme_glue.cpp -- see meme_glue.h.  Compiled together with the (patched) reference sources; binds
 // libmeme_b200.so with dlopen so that the aligner has no link-time CUDA dependency.
 #include <dlfcn.h>
+#include <malloc.h>
 #include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -160,6 +161,16 @@ static void ensure_index()
 {
     if (!g_index.empty()) return;
     Api &a = api();
+    if (!getenv("MEME_B200_NO_MALLOPT")) {
+        // Every chunk allocates and frees several hundred MB of small blocks (regions, chains, SAM strings) from 16 threads while
+        // the aligner's reader and writer threads do the same; with glibc's defaults the arenas are trimmed and re-grown every
+        // chunk, and the page faults and mmap calls of all threads serialise on the address-space lock (the extension driver's
+        // pair construction ran 4x slower whenever the reader thread was parsing).  The reference's own build links mimalloc for
+        // this; the recipe here cannot (oracle/Makefile.ref), so the glue at least tells glibc to keep what it has.
+        mallopt(M_TRIM_THRESHOLD, 0x7fffffff);
+        mallopt(M_MMAP_THRESHOLD, 32 << 20);
+        mallopt(M_TOP_PAD, 64 << 20);
+    }
     int mode = getenv("MEME_B200_MODE") ? atoi(getenv("MEME_B200_MODE")) : MODE;
     if (const char *ds = getenv("MEME_B200_DEVICES")) {
         for (const char *p = ds; *p;) { g_devices.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; }
