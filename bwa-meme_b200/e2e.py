@@ -56,11 +56,18 @@ def compare_arms(prefix: str, fastqs: list[str], n_reads: int, read_len: int, th
     ref, b200, _ = binaries(mode)
     gpu_env = gpu_env or {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1", "MEME_B200_MATE": "1"}
     out = {}
-    r = run_mem(ref, prefix, fastqs, os.path.join(workdir, f"{tag}_ref.sam"), threads)
+    # The patched aligner's glue raises glibc's malloc trim / mmap thresholds (meme_glue.cpp: ensure_index); the unmodified reference
+    # gets the same settings through glibc's environment tunables, and the faster of its two runs is the baseline.
+    tuned = {"MALLOC_TRIM_THRESHOLD_": str(0x7fffffff), "MALLOC_MMAP_THRESHOLD_": str(32 << 20), "MALLOC_TOP_PAD_": str(64 << 20)}
+    r0 = run_mem(ref, prefix, fastqs, os.path.join(workdir, f"{tag}_ref.sam"), threads)
+    r1 = run_mem(ref, prefix, fastqs, os.path.join(workdir, f"{tag}_ref_tuned.sam"), threads, tuned)
+    r = r1 if r1["real_s"] < r0["real_s"] else r0
     g = run_mem(b200, prefix, fastqs, os.path.join(workdir, f"{tag}_gpu.sam"), threads, gpu_env)
-    same = sam_body(os.path.join(workdir, f"{tag}_ref.sam")) == sam_body(os.path.join(workdir, f"{tag}_gpu.sam"))
+    same = sam_body(os.path.join(workdir, f"{tag}_ref.sam")) == sam_body(os.path.join(workdir, f"{tag}_gpu.sam")) == sam_body(os.path.join(workdir, f"{tag}_ref_tuned.sam"))
     bases = n_reads * read_len
-    out["reference_cpu"] = {"Mbases_per_s": bases / r["real_s"] / 1e6, "real_s": r["real_s"], "chunk_s": r["chunk_s"], "threads": threads}
+    out["reference_cpu"] = {"Mbases_per_s": bases / r["real_s"] / 1e6, "real_s": r["real_s"], "chunk_s": r["chunk_s"], "threads": threads,
+                            "malloc": "glibc defaults" if r is r0 else "glibc tunables as in the patched aligner's glue",
+                            "real_s_glibc_defaults": r0["real_s"], "real_s_glibc_tuned": r1["real_s"]}
     out["gpu"] = {"Mbases_per_s": bases / g["real_s"] / 1e6, "real_s": g["real_s"], "chunk_s": g["chunk_s"], "threads": threads, "env": gpu_env,
                   "log_tail": g["log"][-6:]}
     out["sam_identical"] = bool(same)
