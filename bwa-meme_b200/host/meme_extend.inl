@@ -427,6 +427,11 @@ void meme_cigar_chunk(worker_t &w, int n)
 // (meme_glue_take_matesw: aln[regid] of a block = the results of its read pairs in the order they were produced).
 static std::vector<meme_ext::Arena> g_msw_ar;
 static std::vector<int64_t> g_msw_pair_off;
+// what mem_sam_pe_batch_pre leaves in `gar` (pair index or -1 per region and orientation) for every read pair, so that worker_sam
+// does not have to run it a second time: per host thread the values, per read pair where they are
+static std::vector<std::vector<int32_t>> g_msw_gar;
+static std::vector<int64_t> g_msw_gar_off;      // per read pair: offset in its thread's values; [np] unused
+static std::vector<int32_t> g_msw_gar_cnt;
 static double g_msw_collect_ms = 0;
 
 static bool meme_matesw_wanted(worker_t &w, int n)
@@ -444,6 +449,9 @@ static bool meme_matesw_collect(worker_t &w, int n)
     const int T = std::max(1, (int)w.nthreads);
     const int np = n >> 1;
     if ((int)ar.size() < T) ar.resize((size_t)T);
+    if ((int)g_msw_gar.size() < T) g_msw_gar.resize((size_t)T);
+    g_msw_gar_off.resize((size_t)np + 1);
+    g_msw_gar_cnt.resize((size_t)np + 1);
     {   // first chunk: the blocks the glue pinned when the index was loaded (best fit from its cache)
         size_t sz[3];
         meme_glue_matesw_arena_sizes(T, n, sz);
@@ -463,12 +471,18 @@ static bool meme_matesw_collect(worker_t &w, int n)
         const int p0 = (int)((int64_t)np * tid / T), p1 = (int)((int64_t)np * (tid + 1) / T);
         meme_ext::Arena &A = ar[(size_t)tid];
         A.reset();
+        std::vector<int32_t> &G = g_msw_gar[(size_t)tid];
+        G.clear();
         for (int p = p0; p < p1; p++) {
             int64_t pcnt = 0;
             int32_t gcnt = 0, maxRefLen = 0, maxQerLen = 0;
             mem_sam_pe_batch_pre(w.opt, w.fmi->idx->bns, w.fmi->idx->pac, w.pes, (uint64_t)((w.n_processed >> 1) + p), &w.seqs[2 * p], &w.regs[2 * p],
                                  &w.mmc, pcnt, gcnt, maxRefLen, maxQerLen, tid);
             pair_off[(size_t)p + 1] = pcnt;
+            const int32_t *gar = (const int32_t *)w.mmc.seqPairArrayAux[tid];
+            g_msw_gar_off[(size_t)p] = (int64_t)G.size();
+            g_msw_gar_cnt[(size_t)p] = gcnt;
+            G.insert(G.end(), gar, gar + gcnt);
             const SeqPair *sp = w.mmc.seqPairArrayLeft128[tid];
             const uint8_t *rbuf = w.mmc.seqBufLeftRef[tid * CACHE_LINE], *qbuf = w.mmc.seqBufLeftQer[tid * CACHE_LINE];
             for (int64_t k = 0; k < pcnt; k++) {
@@ -497,6 +511,29 @@ static void meme_matesw_run(worker_t &w)
     std::vector<int64_t> pn((size_t)T), rn((size_t)T), qn((size_t)T);
     for (int t = 0; t < T; t++) { meme_ext::Arena &A = ar[(size_t)t]; pp[t] = A.pairs; pn[t] = A.n; rp[t] = A.ref; rn[t] = A.n_ref; qp[t] = A.qer; qn[t] = A.n_qer; }
     meme_glue_matesw_run(T, pp.data(), pn.data(), rp.data(), rn.data(), qp.data(), qn.data(), w.opt, g_msw_pair_off, g_msw_collect_ms);
+}
+
+// worker_sam, in front of its own mem_sam_pe_batch_pre loop over the read pairs [pb, pe) of a block: what that loop would leave
+// behind -- the block's `gar` array (pair indexes relative to the block) and pair count -- from the chunk-level pre-pass.
+// false: nothing collected for this chunk, the caller runs its loop.
+bool meme_matesw_restore(worker_t *w, int pb, int pe, int tid, int64_t *pcnt)
+{
+    if (!meme_glue_matesw_have() || !getenv("MEME_B200_MATE_RESTORE")) return false;
+    const int np = (int)g_msw_pair_off.size() - 1;
+    const int T = std::max(1, (int)w->nthreads);
+    int32_t *gar = (int32_t *)w->mmc.seqPairArrayAux[tid];
+    const int64_t base = g_msw_pair_off[(size_t)pb];
+    int64_t g = 0;
+    for (int p = pb; p < pe; p++) {
+        int t = (int)(((int64_t)p * T + T - 1) / np);                      // owner of read pair p in the static partition of the pre-pass
+        while (t > 0 && (int)((int64_t)np * t / T) > p) t--;
+        while (t + 1 < T && (int)((int64_t)np * (t + 1) / T) <= p) t++;
+        const int32_t *src = g_msw_gar[(size_t)t].data() + g_msw_gar_off[(size_t)p];
+        const int64_t shift = g_msw_pair_off[(size_t)p] - base;
+        for (int k = 0; k < g_msw_gar_cnt[(size_t)p]; k++) gar[g++] = src[k] < 0 ? -1 : (int32_t)(src[k] + shift);
+    }
+    *pcnt = g_msw_pair_off[(size_t)pe] - base;
+    return true;
 }
 
 void meme_matesw_chunk(worker_t &w, int n)

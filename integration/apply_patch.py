@@ -17,7 +17,7 @@ HOOK_BSW = ("    if (meme_glue_bsw({arr}, seqBufRef, seqBufQer, numPairs, w, o_d
 def patch_bwamem(src: str) -> str:
     out, n_seed, n_close, n_chunk, n_inc, n_aln, n_take, n_dump, in_k1 = [], 0, 0, 0, 0, 0, 0, 0, False
     n_sam, n_cig, n_cig_end, in_r2a = 0, 0, 0, False
-    n_msw = 0
+    n_msw = n_msw_pre = 0
     for line in src.splitlines(keepends=True):
         if line.startswith("mem_aln_t mem_reg2aln("):
             in_r2a = True
@@ -33,6 +33,13 @@ def patch_bwamem(src: str) -> str:
         if re.match(r"\s*kt_for\(worker_sam, &w,\s+n_\);", line):
             out.append("    meme_sam_prepass(w, n_);   // meme_b200: global alignments of all regions + mate-rescue Smith-Waterman of the whole chunk on the GPU\n")
             n_sam += 1
+        if line.startswith("static void worker_sam("):
+            out.append("bool meme_matesw_restore(worker_t *w, int pb, int pe, int tid, int64_t *pcnt);   // meme_b200 (meme_extend.inl)\n")
+        if line.strip() == "int32_t gcnt = 0;" and not n_msw_pre:
+            out.append(line)
+            out.append("        if (!meme_matesw_restore(w, start >> 1, end >> 1, tid, &pcnt))   // meme_b200: the block's rescue pairs were collected by the chunk-level pre-pass\n")
+            n_msw_pre += 1
+            continue
         if line.strip() == "mem_sam_pe_batch(w->opt, &w->mmc, pcnt, pcnt8, aln, maxRefLen, maxQerLen, tid);" and not n_msw:
             out.append("        if (!meme_glue_take_matesw(start >> 1, end >> 1, pcnt, aln))   // meme_b200: the block's mate-rescue results from the GPU, if any\n")
             n_msw += 1
@@ -75,7 +82,7 @@ def patch_bwamem(src: str) -> str:
             out.append("void meme_sam_prepass(worker_t &w, int n);    // meme_b200 (meme_extend.inl)\n")
         out.append(line)
     assert (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump) == (1, 1, 1, 1, 1, 1, 1), (n_inc, n_seed, n_close, n_chunk, n_aln, n_take, n_dump)
-    assert (n_sam, n_cig, n_cig_end, n_msw) == (1, 1, 1, 1), (n_sam, n_cig, n_cig_end, n_msw)
+    assert (n_sam, n_cig, n_cig_end, n_msw, n_msw_pre) == (1, 1, 1, 1, 1), (n_sam, n_cig, n_cig_end, n_msw, n_msw_pre)
     return "".join(out) + '\n#include "meme_extend.inl"   // meme_b200: chunk-level seed extension\n'
 
 
