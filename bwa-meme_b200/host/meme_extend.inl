@@ -519,20 +519,23 @@ static void meme_matesw_run(worker_t &w)
 bool meme_matesw_restore(worker_t *w, int pb, int pe, int tid, int64_t *pcnt)
 {
     if (!meme_glue_matesw_have() || !getenv("MEME_B200_MATE_RESTORE")) return false;
-    const int np = (int)g_msw_pair_off.size() - 1;
+    const std::vector<int64_t> &off = meme_glue_matesw_off();          // per read pair: index of its first result (the glue owns it now)
+    const int np = (int)off.size() - 1;
     const int T = std::max(1, (int)w->nthreads);
+    if (np < 1 || pe > np || (int)g_msw_gar.size() < T) return false;
     int32_t *gar = (int32_t *)w->mmc.seqPairArrayAux[tid];
-    const int64_t base = g_msw_pair_off[(size_t)pb];
+    const int64_t base = off[(size_t)pb];
     int64_t g = 0;
     for (int p = pb; p < pe; p++) {
         int t = (int)(((int64_t)p * T + T - 1) / np);                      // owner of read pair p in the static partition of the pre-pass
+        if (t >= T) t = T - 1;
         while (t > 0 && (int)((int64_t)np * t / T) > p) t--;
         while (t + 1 < T && (int)((int64_t)np * (t + 1) / T) <= p) t++;
         const int32_t *src = g_msw_gar[(size_t)t].data() + g_msw_gar_off[(size_t)p];
-        const int64_t shift = g_msw_pair_off[(size_t)p] - base;
+        const int64_t shift = off[(size_t)p] - base;
         for (int k = 0; k < g_msw_gar_cnt[(size_t)p]; k++) gar[g++] = src[k] < 0 ? -1 : (int32_t)(src[k] + shift);
     }
-    *pcnt = g_msw_pair_off[(size_t)pe] - base;
+    *pcnt = off[(size_t)pe] - base;
     return true;
 }
 

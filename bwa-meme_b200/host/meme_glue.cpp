@@ -558,6 +558,7 @@ static_assert(sizeof(meme_kswr_t) == sizeof(kswr_t) && offsetof(meme_kswr_t, qb)
 bool meme_glue_matesw_enabled() { return env_on("MEME_B200_MATE") && !g_index.empty(); }
 void meme_glue_matesw_skip() { g_have_msw = false; }
 bool meme_glue_matesw_have() { return g_have_msw; }
+const std::vector<int64_t> &meme_glue_matesw_off() { return g_msw_off; }
 
 // nseg segments written by the host threads (contiguous shares of the read pairs, in order) -> one device batch per GPU
 void meme_glue_matesw_run(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer, const mem_opt_t *opt,

@@ -54,6 +54,7 @@ void meme_glue_cigar_run(std::vector<int32_t> &reg_w, std::vector<int64_t> &task
                          int n_reads, const mem_opt_t *opt, int64_t l_pac);
 bool meme_glue_matesw_enabled();
 bool meme_glue_matesw_have();
+const std::vector<int64_t> &meme_glue_matesw_off();
 void meme_glue_matesw_skip();
 void meme_glue_matesw_run(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer, const mem_opt_t *opt,
                           std::vector<int64_t> &pair_off, double collect_ms);

@@ -74,6 +74,7 @@ def test_paired_end_sam_identical(pkg, golden_index, tmp_path):
     assert sam == open(os.path.join(GOLDEN, "mem7_pe.sam")).read()
     # + the mate-rescue Smith-Waterman of the whole chunk (row f2): alone, and with every other stage
     for hooks in ({"MEME_B200": "1", "MEME_B200_MATE": "1"},
+                  {"MEME_B200": "1", "MEME_B200_MATE": "1", "MEME_B200_MATE_RESTORE": "1"},      # worker_sam skips its own collection pass
                   {"MEME_B200": "1", "MEME_B200_CHAIN": "1", "MEME_B200_BSW": "1", "MEME_B200_SAM": "1", "MEME_B200_MATE": "1"}):
         sam, err = _run(exe, [golden_index, f1, f2], hooks)
         assert "mate rescue:" in err and "Smith-Waterman pairs" in err
