@@ -8,7 +8,7 @@ fn, per = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
-        fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+        fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "").split("(")[0]
         per[fn] = collections.Counter()
         continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
@@ -17,7 +17,7 @@ for line in out.splitlines():
 want = ["LDGSTS", "LDG", "LDS", "STS", "ATOMS", "VIADDMNMX", "VIMNMX3", "VIMNMX", "PRMT", "REDUX", "DFMA", "MEMBAR", "UBLKCP", "UTMALDG", "SYNCS", "BSSY", "WARPSYNC"]
 print(f"{'kernel':70s} {'instr':>6s} {'KB':>5s}  " + " ".join(f"{w:>9s}" for w in want))
 for fn, c in per.items():
-    if not any(k in fn for k in ("k_flat<", "k_grp<", "k_bsw", "k_gather2", "k_pack_reads", "k_build_keys", "k_rmi_lookup")):
+    if not any(k in fn for k in ("k_flat<", "k_grp<", "k_bsw", "k_gather2", "k_pack_reads", "k_build_keys", "k_rmi_lookup", "k_chain", "k_cigar", "k_matesw", "k_sa_", "k_leaf", "k_sub_fit", "k_errors")):
         continue
     if ("k_flat<" in fn or "k_grp<" in fn) and not fn.endswith("false>") :
         continue                     # the STATS instantiations only differ by counters
