@@ -42,6 +42,13 @@ def test_fails_loudly_without_gpu(built, pkg, golden_index):
     assert "no CPU path" in str(e.value) or "-6" in str(e.value)
     with pytest.raises(capi.MemeError):
         capi.MemeBsw()
+    # the index pipeline has no CPU path behind the C ABI either (index_build.py's torch code is separate tooling)
+    import numpy as np
+    with pytest.raises(capi.MemeError):
+        capi.sa_build(np.zeros(64, np.uint8))
+    with pytest.raises(capi.MemeError):
+        capi.prmi_train(np.arange(100, dtype=np.uint64), 4)
+    assert capi.KSWR_DTYPE.itemsize == 28       # kswr_t, src/ksw.h:L45-50
 
 
 def test_version_string(built, pkg):

@@ -72,3 +72,36 @@ def test_cuda_matches_oracle_many_pairs_edges_and_limits(pkg, oracle, ix):
         ix.matesw_batch([(bad, segs[0][1], segs[0][2])])
     with pytest.raises(RuntimeError, match="range"):
         ix.matesw_batch([segs[0]], capi.default_matesw_opt(e_del=0))
+
+
+def test_cuda_matches_oracle_at_the_limits(pkg, oracle, ix):
+    """The longest mates the kernel takes (496 bases in the 16-bit class, 255 in the 8-bit class with a match score that keeps
+    KSW_XBYTE legal), windows of several thousand bases, and a poly-A window against a poly-A mate (every row maximum equal)."""
+    from bwa_meme_b200 import capi
+    rng = np.random.default_rng(31)
+    base = U.XSUBO | U.XSTART
+    ref_parts, qer_parts, rows = [], [], []
+    ro = qo = 0
+
+    def add(win, q, xtra):
+        nonlocal ro, qo
+        rows.append((ro, qo, len(win), len(q), xtra, 0))
+        ref_parts.append(win); qer_parts.append(q)
+        ro += len(win); qo += len(q)
+
+    for l1, l2, xtra in ((5000, 496, base | 19), (3000, 255, base | U.XBYTE | 19), (31999, 150, base | U.XBYTE | 19), (700, 249, base | U.XBYTE | 19),
+                         (2000, 400, base | 30), (640, 150, base | U.XBYTE | 19)):
+        win = rng.integers(0, 4, size=l1).astype(np.uint8)
+        st = int(rng.integers(0, l1 - l2))
+        q = win[st:st + l2].copy()
+        mm = rng.random(l2) < 0.03
+        q[mm] = (q[mm] + 1) & 3
+        add(win, q, xtra)
+    add(np.zeros(600, np.uint8), np.zeros(150, np.uint8), base | U.XBYTE | 19)
+    add(np.full(600, 3, np.uint8), np.zeros(150, np.uint8), base | U.XBYTE | 19)
+    recs = np.array(rows, dtype=oracle.MATESW_REC_DTYPE)
+    ref, qer = np.concatenate(ref_parts), np.concatenate(qer_parts)
+    want = oracle.matesw_batch(recs, ref, qer)
+    out = ix.matesw_batch(to_segments(capi, recs, ref, qer, (3,)))
+    assert np.concatenate(out["aln"]).tolist() == want.tolist()
+    assert want["score"][0] > 255 and want["tb"][0] >= 0
