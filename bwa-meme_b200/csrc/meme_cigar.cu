@@ -228,6 +228,7 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     CUDA_TRY(cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
     c->ran = 0; c->ms = 0; c->cells = 0;
+    const auto Tin = std::chrono::steady_clock::now();
     if ((rc = meme_grow_device((void **)&c->d_codes, &c->cap_codes, (size_t)n_codes + 64, 1, st))) return rc;
     if (n_codes) CUDA_TRY(cudaMemcpyAsync(c->d_codes, codes, (size_t)n_codes, cudaMemcpyHostToDevice, st));
     if ((rc = cigar_grow_pinned((void **)&c->h_recs, &c->hcap_recs, (size_t)n_tasks + 1, sizeof(meme_cigar_rec_t), 0))) return rc;
@@ -235,7 +236,7 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     const int64_t SLICE = 1 << 18;
     int64_t op_base = 0, md_base = 0;
     const bool dbg = getenv("MEME_CIGAR_DEBUG") != nullptr;
-    double t_h2d = 0, t_size = 0, t_align = 0, t_emit = 0, t_d2h = 0;
+    double t_h2d = 0, t_size = 0, t_align = 0, t_emit = 0, t_d2h = 0, t_grow = 0;
     auto now = [&] { if (dbg) cudaStreamSynchronize(st); return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count() * 1e3; };
     auto T0 = now();
@@ -243,6 +244,7 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     for (int64_t s0 = 0; s0 < n_tasks; s0 += SLICE) {
         const int64_t n = n_tasks - s0 < SLICE ? n_tasks - s0 : SLICE;
         const int64_t n_groups = (n + 31) / 32;
+        auto Tg = now();
         void **grow[] = {(void **)&c->d_tasks, (void **)&c->d_z_off, (void **)&c->d_op_off, (void **)&c->d_md_off, (void **)&c->d_key,
                          (void **)&c->d_key2, (void **)&c->d_idx, (void **)&c->d_idx2, (void **)&c->d_slot, (void **)&c->d_recs, (void **)&c->d_g_rows,
                          (void **)&c->d_g_z};
@@ -251,7 +253,7 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
         size_t elem[] = {sizeof(meme_cigar_task_t), 8, 8, 8, 2, 2, 4, 4, 4, sizeof(meme_cigar_rec_t), 8, 8};
         for (int k = 0; k < 12; k++)
             if ((rc = meme_grow_device(grow[k], caps[k], (size_t)n + 2, elem[k], st))) return rc;
-        auto Ta = now();
+        auto Ta = now(); t_grow += secs(Tg, Ta);
         CUDA_TRY(cudaMemcpyAsync(c->d_tasks, tasks + s0, (size_t)n * sizeof(meme_cigar_task_t), cudaMemcpyHostToDevice, st));
         auto Tb = now(); t_h2d += secs(Ta, Tb);
         CigarArgs A;
@@ -275,6 +277,9 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
         CUDA_TRY(cudaMemcpyAsync(&tot[0], c->d_g_z + n_groups, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(&tot[1], c->d_g_rows + n_groups, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (dbg && ((size_t)tot[0] * 32 + 64 > c->cap_z || (size_t)tot[1] * 32 + 64 > c->cap_eh))
+            fprintf(stderr, "[meme_cigar] slice at %lld grows its scratch: backtrack %zu -> %zu bytes, rows %zu -> %zu cells\n", (long long)s0, c->cap_z,
+                    (size_t)tot[0] * 32 + 64, c->cap_eh, (size_t)tot[1] * 32 + 64);
         if ((rc = meme_grow_device((void **)&c->d_z, &c->cap_z, (size_t)tot[0] * 32 + 64, 1, st))) return rc;
         if ((rc = meme_grow_device((void **)&c->d_eh, &c->cap_eh, (size_t)tot[1] * 32 + 64, sizeof(EH), st))) return rc;
         if ((rc = meme_grow_device((void **)&c->d_q, &c->cap_q, (size_t)tot[1] * 32 + 64, 1, st))) return rc;
@@ -312,23 +317,26 @@ extern "C" int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks
     c->cells = ctl[1];
     c->ran = 1;
     if (dbg) fprintf(stderr, "[meme_cigar] %lld tasks: total %.1f ms (codes+setup %.1f), per phase summed over slices: tasks h2d %.1f, size+scan+sort %.1f, align %.1f, "
-                     "scan+emit %.1f, d2h %.1f; %llu cells\n", (long long)n_tasks, secs(T0, now()), 0.0, t_h2d, t_size, t_align, t_emit, t_d2h, (unsigned long long)c->cells);
+                     "scan+emit %.1f, d2h %.1f, grow %.1f; %llu cells\n", (long long)n_tasks, secs(Tin, now()), secs(Tin, T0), t_h2d, t_size, t_align, t_emit, t_d2h, t_grow, (unsigned long long)c->cells);
     out->n_tasks = n_tasks; out->n_ops = op_base; out->n_md = md_base;
     out->recs = c->h_recs; out->cigars = c->h_ops; out->md = c->h_md;
     return MEME_OK;
 }
 
-// Kernels loaded and the pinned result arrays sized for a chunk of n_regions regions of qlen-base queries before the first
-// timed chunk: one slice of short dummy regions (a quarter of them with a matrix) runs through every kernel.
+// Kernels loaded and every array sized for chunks of about n_regions regions of qlen-base queries before the first timed chunk:
+// one full slice of dummy regions runs through every kernel -- a quarter of them with a matrix and a local score they cannot
+// reach, so that the band doubles to its widest and the scratch arrays take their worst-case size for this read length -- and
+// the pinned result arrays are sized for the whole chunk.  After this a chunk of the expected shape allocates nothing (on some
+// boxes a cudaMalloc / cudaFree inside a timed chunk was seen to take 0.7-3.6 s).
 extern "C" int meme_cigar_warmup(meme_index_t *ix, int64_t n_regions, int qlen)
 {
-    if (!ix || n_regions < 0 || qlen < 1) { meme_set_error("bad argument"); return MEME_E_ARG; }
+    if (!ix || n_regions < 0 || qlen < 1 || qlen > 1000) { meme_set_error("bad argument"); return MEME_E_ARG; }
     CigarWork *c; int rc;
     if ((rc = cigar_work(ix, &c))) return rc;
     CUDA_TRY(cudaSetDevice(ix->device));
     const int64_t l_pac = (int64_t)(ix->v.sa_num / 2);
-    const int64_t n = n_regions < (1 << 16) ? n_regions : (1 << 16);
-    const int ql = 24;
+    const int64_t n = n_regions < (1 << 18) ? n_regions : (1 << 18);
+    const int ql = l_pac > 8 * (int64_t)qlen ? qlen : 24;
     if (l_pac < 4 * ql || n == 0) return MEME_OK;
     std::vector<meme_cigar_task_t> tasks((size_t)n);
     std::vector<uint8_t> codes((size_t)n * ql);
@@ -337,8 +345,9 @@ extern "C" int meme_cigar_warmup(meme_index_t *ix, int64_t n_regions, int qlen)
     for (int64_t i = 0; i < n; i++) {
         x ^= x << 13; x ^= x >> 7; x ^= x << 17;
         meme_cigar_task_t &T = tasks[(size_t)i];
-        T.rb = (int64_t)(x % (u64)(l_pac - 2 * ql)); T.re = T.rb + ql + ((i & 3) == 0 ? 2 : 0);
-        T.q_off = i * ql; T.qlen = ql; T.w = (i & 3) == 0 ? 4 : 0; T.truesc = ql; T.pad = 0;
+        const bool matrix = (i & 3) == 0;
+        T.rb = (int64_t)(x % (u64)(l_pac - 2 * ql)); T.re = T.rb + ql + (matrix ? 2 : 0);
+        T.q_off = i * ql; T.qlen = ql; T.w = matrix ? 30 : 0; T.truesc = matrix ? ql : 0; T.pad = 0;
     }
     meme_cigar_opt_t o;
     memset(&o, 0, sizeof o);
@@ -350,6 +359,14 @@ extern "C" int meme_cigar_warmup(meme_index_t *ix, int64_t n_regions, int qlen)
     if ((rc = cigar_grow_pinned((void **)&c->h_ops, &c->hcap_ops, (size_t)n_regions * 2, 4, 0))) return rc;
     if ((rc = cigar_grow_pinned((void **)&c->h_md, &c->hcap_md, (size_t)n_regions * 12, 1, 0))) return rc;
     if ((rc = meme_grow_device((void **)&c->d_codes, &c->cap_codes, (size_t)n_regions * (size_t)qlen / 2 + 64, 1, ix->stream))) return rc;
+    if (n == (1 << 18)) {
+        // backtrack scratch for a slice in which half of the warps hold full-width matrices (a GB-sized cudaFree + cudaMalloc
+        // inside the first timed chunk was measured at 0.26-0.8 s); HBM has the room
+        const size_t groups = (size_t)n / 32, full = (size_t)ql * (size_t)(ql + 32);
+        if ((rc = meme_grow_device((void **)&c->d_z, &c->cap_z, groups / 2 * 32 * full + 64, 1, ix->stream))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_eh, &c->cap_eh, groups * 32 * (size_t)(ql + 34) + 64, sizeof(EH), ix->stream))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_q, &c->cap_q, groups * 32 * (size_t)(ql + 34) + 64, 1, ix->stream))) return rc;
+    }
     c->ran = 0;
     return MEME_OK;
 }

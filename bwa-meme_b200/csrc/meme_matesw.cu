@@ -219,6 +219,15 @@ extern "C" int meme_matesw_warmup(meme_index_t *ix, int64_t n_pairs, int len1, i
     if ((rc = meme_grow_pinned((void **)&c->h_perm, &c->hcap_perm, (size_t)n_pairs + 64, 4))) return rc;
     if ((rc = meme_grow_device((void **)&c->d_ref, &c->cap_ref, (size_t)n_pairs * (size_t)len1 + 64, 1, st))) return rc;
     if ((rc = meme_grow_device((void **)&c->d_qer, &c->cap_qer, (size_t)n_pairs * (size_t)len2 + 64, 1, st))) return rc;
+    {   // the per-pair arrays and the row-maximum scratch of one launch slice
+        const size_t slice = (size_t)(n_pairs < (1 << 17) ? n_pairs : (1 << 17));
+        if ((rc = meme_grow_device((void **)&c->d_tasks, &c->cap_tasks, (size_t)n_pairs + 64, sizeof(MswTask), st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_perm, &c->cap_perm, (size_t)n_pairs + 64, 4, st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_out, &c->cap_out, (size_t)n_pairs + 64, sizeof(meme_kswr_t), st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_rm_off, &c->cap_rm_off, slice / 32 + 2, 8, st))) return rc;
+        if ((rc = meme_grow_device((void **)&c->d_rm, &c->cap_rm, (slice + 32) * ((size_t)len1 + 1) + 64, 2, st))) return rc;
+        if ((rc = meme_grow_pinned((void **)&c->h_rm_off, &c->hcap_rm_off, (size_t)n_pairs / 32 + 2, 8))) return rc;
+    }
     const int64_t n = n_pairs < 2048 ? n_pairs : 2048;
     if (n == 0) return MEME_OK;
     std::vector<meme_seqpair_t> pairs((size_t)n);

@@ -52,7 +52,7 @@ struct Arena {
 };
 
 struct ThreadState {
-    Arena left, right;
+    Arena left[2], right[2];            // [half of the chunk]: the second half's pairs are built while the first half's run on the GPU
     std::vector<uint32_t> srt;          // seeds of every chain in ascending score order, read after read
     std::vector<uint64_t> key;
 };
@@ -75,8 +75,9 @@ static inline void seed_coverage(mem_alnreg_t *a)
 
 // step 1 for one read: regions and extension pairs of all seeds of all chains
 static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *ref_string, const bseq1_t *seq,
-                         int l, mem_chain_v *chn, mem_alnreg_v *av, ThreadState &T, const bool by_position)
+                         int l, mem_chain_v *chn, mem_alnreg_v *av, ThreadState &T, const int half, const bool by_position)
 {
+    Arena &AL = T.left[half], &AR = T.right[half];
     const int64_t l_pac = bns->l_pac;
     const uint8_t *query = (const uint8_t *)seq->seq;
     const int l_query = seq->l_seq;
@@ -123,21 +124,21 @@ static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_
             a->c = c;
             a->rb = a->qb = a->re = a->qe = H0_;
             if (s->qbeg) {                              // left extension: reversed query prefix against reversed reference
-                SeqPair *sp = T.left.new_pair();
+                SeqPair *sp = AL.new_pair();
                 memset(sp, 0, sizeof(SeqPair));
                 const int64_t tl = s->rbeg - rmax0;
                 sp->h0 = s->len * opt->a;
                 sp->seqid = l; sp->regid = (int)av->n - 1;
                 sp->len2 = s->qbeg; sp->len1 = (int32_t)tl;
-                sp->idq = (int32_t)T.left.n_qer;
-                uint8_t *qs = T.left.take_qer(s->qbeg);
+                sp->idq = (int32_t)AL.n_qer;
+                uint8_t *qs = AL.take_qer(s->qbeg);
                 for (int i = 0; i < s->qbeg; ++i) qs[i] = query[s->qbeg - 1 - i];
                 if (by_position) {                      // the reversed reference = the text read backwards from rbeg - 1
                     const uint64_t p = tl > 0 ? (uint64_t)(s->rbeg - 1) : 0;
                     sp->idr = (int32_t)(uint32_t)p; sp->id = (int32_t)((uint32_t)(p >> 32) | 0x80000000u);
                 } else {
-                    sp->idr = (int32_t)T.left.n_ref;
-                    uint8_t *rs = T.left.take_ref(tl);
+                    sp->idr = (int32_t)AL.n_ref;
+                    uint8_t *rs = AL.take_ref(tl);
                     for (int64_t i = 0; i < tl; ++i) rs[i] = rseq[tl - 1 - i];
                 }
                 a->qb = s->qbeg; a->rb = s->rbeg;
@@ -147,19 +148,19 @@ static void collect_read(const mem_opt_t *opt, const bntseq_t *bns, const uint8_
             if (s->qbeg + s->len != l_query) {          // right extension
                 const int64_t qe = s->qbeg + s->len, re = s->rbeg + s->len - rmax0;
                 assert(re >= 0);
-                SeqPair *sp = T.right.new_pair();
+                SeqPair *sp = AR.new_pair();
                 memset(sp, 0, sizeof(SeqPair));
                 sp->h0 = H0_;                           // known after the left side
                 sp->seqid = l; sp->regid = (int)av->n - 1;
                 sp->len2 = (int32_t)(l_query - qe); sp->len1 = (int32_t)(rmax1 - rmax0 - re);
-                sp->idq = (int32_t)T.right.n_qer;
-                memcpy(T.right.take_qer(sp->len2), query + qe, (size_t)sp->len2);
+                sp->idq = (int32_t)AR.n_qer;
+                memcpy(AR.take_qer(sp->len2), query + qe, (size_t)sp->len2);
                 if (by_position) {
                     const uint64_t p = (uint64_t)(rmax0 + re);
                     sp->idr = (int32_t)(uint32_t)p; sp->id = (int32_t)(uint32_t)(p >> 32);
                 } else {
-                    sp->idr = (int32_t)T.right.n_ref;
-                    memcpy(T.right.take_ref(sp->len1), rseq + re, (size_t)sp->len1);
+                    sp->idr = (int32_t)AR.n_ref;
+                    memcpy(AR.take_ref(sp->len1), rseq + re, (size_t)sp->len1);
                 }
                 a->qe = (int)qe; a->re = rmax0 + re;
             } else {
@@ -268,108 +269,149 @@ bool meme_extend_chunk(worker_t &w, int n)
     if ((int)g_ts.size() < T) g_ts.resize((size_t)T);
     g_srt_off.resize((size_t)n + 1);
     double t0 = omp_get_wtime();
-    // ---- 1. regions + pairs: blocks of reads handed out dynamically (a host thread that shares its core with the aligner's
-    //         reader / writer threads takes fewer), one arena pair per host thread ----
+    // Blocks of reads are handed out dynamically (a host thread that shares its core with the aligner's reader / writer threads
+    // takes fewer), one arena set per host thread.  The chunk is cut into two halves of blocks: while one half's pairs run on
+    // the GPU (one call in flight at a time, driven by the glue's per-device threads), the host builds, folds or finishes the
+    // other half (MEME_B200_EXT_HALVES=0: one piece, as before).
     const int BLK = 1024, n_blk = (n + BLK - 1) / BLK;
+    const int n_half = (n_blk >= 8 && !(getenv("MEME_B200_EXT_HALVES") && atoi(getenv("MEME_B200_EXT_HALVES")) == 0) &&
+                        !getenv("MEME_B200_DUMP_PAIRS")) ? 2 : 1;              // (the pair dump wants one left and one right batch)
+    const int blk_cut[3] = {0, n_half == 2 ? n_blk / 2 : n_blk, n_blk};
     g_blk_owner.resize((size_t)n_blk);
+    double t_pairs = 0, t_left = 0, t_fold = 0, t_right = 0, t_finish = 0;
+    int64_t tot_left = 0, tot_right = 0;
 #pragma omp parallel num_threads(T)
     {
-        const int t = omp_get_thread_num();
-        ThreadState &S = g_ts[(size_t)t];
-        S.left.reset(); S.right.reset(); S.srt.clear();
-        {   // first chunk: the arenas take their typical share (up to 6 pairs per read, 200 + 100 sequence bytes per pair),
-            // from the blocks the glue page-locked at index load when it could
-            const int64_t est = (int64_t)(n / T + 1) * 6;
-            for (Arena *A : {&S.left, &S.right}) {
+        ThreadState &S = g_ts[(size_t)omp_get_thread_num()];
+        S.srt.clear();
+        for (int h = 0; h < 2; h++) { S.left[h].reset(); S.right[h].reset(); }
+        // first chunk: the arenas take their typical share (up to 6 pairs per read, 200 + 100 sequence bytes per pair), from
+        // the blocks the glue page-locked at index load when it could
+        const int64_t est = (int64_t)(n / T + 1) * 6 / n_half;
+        for (int h = 0; h < n_half; h++)
+            for (Arena *A : {&S.left[h], &S.right[h]}) {
                 Arena::reserve(A->pairs, A->cap, est); if (!by_position) Arena::reserve(A->ref, A->cap_ref, est * 200); Arena::reserve(A->qer, A->cap_qer, est * 100);
                 Arena::reserve(A->w_used, A->cap_w, est);
             }
-        }
+    }
+    // ---- 1. regions + pairs of one half ----
+    auto build_pairs = [&](int h) {
+        const double ta = omp_get_wtime();
+#pragma omp parallel num_threads(T)
+        {
+            const int t = omp_get_thread_num();
+            ThreadState &S = g_ts[(size_t)t];
 #pragma omp for schedule(dynamic, 1)
-        for (int b = 0; b < n_blk; b++) {
-            g_blk_owner[(size_t)b] = t;
-            const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
-            for (int l = r0; l < r1; l++) {
-                g_srt_off[(size_t)l] = (int64_t)S.srt.size();
-                collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S, by_position);
+            for (int b = blk_cut[h]; b < blk_cut[h + 1]; b++) {
+                g_blk_owner[(size_t)b] = t;
+                const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
+                for (int l = r0; l < r1; l++) {
+                    g_srt_off[(size_t)l] = (int64_t)S.srt.size();
+                    collect_read(opt, bns, pac, w.ref_string, &w.seqs[l], l, &w.chain_ar[l], &w.regs[l], S, h, by_position);
+                }
             }
         }
-    }
-    double t1 = omp_get_wtime();
+        t_pairs += omp_get_wtime() - ta;
+    };
+    // ---- 2. one side of one half on the device: start (returns at once), wait ----
     std::vector<SeqPair *> pp((size_t)T);
     std::vector<int64_t> np((size_t)T), nr((size_t)T), nq((size_t)T);
     std::vector<uint8_t *> pr((size_t)T), pq((size_t)T);
     std::vector<int32_t *> pw((size_t)T);
-    int64_t tot_left = 0, tot_right = 0;
-    // ---- 2a. left side on the device, folded into the regions (L2968-3161) ----
-    for (int t = 0; t < T; t++) {
-        Arena &A = g_ts[(size_t)t].left;
-        Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
-        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = by_position ? nullptr : A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer;
-        nq[(size_t)t] = A.n_qer; pw[(size_t)t] = A.w_used; tot_left += A.n;
-    }
-    meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 0, opt->o_del,
-                           opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->pen_clip5, opt->a, opt->b, pw.data());
-    double t2 = omp_get_wtime();
+    void *job = nullptr;
+    double t_job = 0;
+    auto start_side = [&](int h, bool right) {
+        int64_t tot = 0;
+        for (int t = 0; t < T; t++) {
+            Arena &A = right ? g_ts[(size_t)t].right[h] : g_ts[(size_t)t].left[h];
+            Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
+            pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = by_position ? nullptr : A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer;
+            nq[(size_t)t] = A.n_qer; pw[(size_t)t] = A.w_used; tot += A.n;
+        }
+        (right ? tot_right : tot_left) += tot;
+        t_job = omp_get_wtime();
+        job = tot ? meme_glue_bsw_segments_start(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, right ? 1 : 0, opt->o_del,
+                                                 opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, right ? opt->pen_clip3 : opt->pen_clip5, opt->a, opt->b, pw.data())
+                  : nullptr;
+    };
+    auto wait_side = [&](bool right) {
+        const double ta = omp_get_wtime();
+        if (job) meme_glue_bsw_segments_wait(job);
+        job = nullptr;
+        (right ? t_right : t_left) += omp_get_wtime() - ta;          // what the host waited, not what the device took
+    };
+    // ---- 2a'. left side folded into the regions (L2968-3161); the right side starts from the region's score so far (L3168-3173) ----
+    auto fold_left = [&](int h) {
+        const double ta = omp_get_wtime();
 #pragma omp parallel num_threads(T)
-    {
-        ThreadState &S = g_ts[(size_t)omp_get_thread_num()];
-        for (int64_t k = 0; k < S.left.n; k++) {
-            const SeqPair *sp = &S.left.pairs[k];
-            mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
-            a->score = sp->score;
-            if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip5) { a->qb -= sp->qle; a->rb -= sp->tle; a->truesc = a->score; }
-            else { a->qb = 0; a->rb -= sp->gtle; a->truesc = sp->gscore; }
-            a->w = max_(a->w, S.left.w_used[k]);
-            seed_coverage(a);
-        }
-        // the right side starts from the region's score so far (L3168-3173)
-        for (int64_t k = 0; k < S.right.n; k++) {
-            SeqPair *sp = &S.right.pairs[k];
-            sp->h0 = w.regs[sp->seqid].a[sp->regid].score;
-        }
-    }
-    // ---- 2b. right side (L3175-3376) ----
-    for (int t = 0; t < T; t++) {
-        Arena &A = g_ts[(size_t)t].right;
-        Arena::grow(A.w_used, A.cap_w, 0, A.n + 1);
-        pp[(size_t)t] = A.pairs; np[(size_t)t] = A.n; pr[(size_t)t] = by_position ? nullptr : A.ref; nr[(size_t)t] = A.n_ref; pq[(size_t)t] = A.qer;
-        nq[(size_t)t] = A.n_qer; pw[(size_t)t] = A.w_used; tot_right += A.n;
-    }
-    double t3 = omp_get_wtime();
-    meme_glue_bsw_segments(T, pp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data(), opt->w, MAX_BAND_TRY, 1, opt->o_del,
-                           opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, opt->pen_clip3, opt->a, opt->b, pw.data());
-    double t4 = omp_get_wtime();
-    // ---- 3. fold the right side, purge contained seeds, finish every read ----
-#pragma omp parallel num_threads(T)
-    {
-        const int t = omp_get_thread_num();
-        ThreadState &S = g_ts[(size_t)t];
-        for (int64_t k = 0; k < S.right.n; k++) {
-            const SeqPair *sp = &S.right.pairs[k];
-            mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
-            a->score = sp->score;
-            if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip3) { a->qe += sp->qle; a->re += sp->tle; a->truesc += a->score - sp->h0; }
-            else { a->qe = w.seqs[sp->seqid].l_seq; a->re += sp->gtle; a->truesc += sp->gscore - sp->h0; }
-            a->w = max_(a->w, S.right.w_used[k]);
-            seed_coverage(a);
-        }
-        // every region has both sides folded before any read is finished (a block may be finished by another thread than
-        // the one that built its pairs)
-#pragma omp barrier
-#pragma omp for schedule(dynamic, 1)
-        for (int b = 0; b < n_blk; b++) {
-            uint32_t *srt = g_ts[(size_t)g_blk_owner[(size_t)b]].srt.data();
-            const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
-            for (int l = r0; l < r1; l++) {
-                purge_contained(opt, &w.seqs[l], &w.chain_ar[l], &w.regs[l], srt + g_srt_off[(size_t)l]);
-                finish_read(opt, bns, pac, &w.seqs[l], &w.chain_ar[l], &w.regs[l]);
+        {
+            ThreadState &S = g_ts[(size_t)omp_get_thread_num()];
+            Arena &L = S.left[h], &R = S.right[h];
+            for (int64_t k = 0; k < L.n; k++) {
+                const SeqPair *sp = &L.pairs[k];
+                mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
+                a->score = sp->score;
+                if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip5) { a->qb -= sp->qle; a->rb -= sp->tle; a->truesc = a->score; }
+                else { a->qb = 0; a->rb -= sp->gtle; a->truesc = sp->gscore; }
+                a->w = max_(a->w, L.w_used[k]);
+                seed_coverage(a);
+            }
+            for (int64_t k = 0; k < R.n; k++) {
+                SeqPair *sp = &R.pairs[k];
+                sp->h0 = w.regs[sp->seqid].a[sp->regid].score;
             }
         }
+        t_fold += omp_get_wtime() - ta;
+    };
+    // ---- 3. fold the right side, purge contained seeds, finish every read of the half ----
+    auto finish_half = [&](int h) {
+        const double ta = omp_get_wtime();
+#pragma omp parallel num_threads(T)
+        {
+            ThreadState &S = g_ts[(size_t)omp_get_thread_num()];
+            Arena &R = S.right[h];
+            for (int64_t k = 0; k < R.n; k++) {
+                const SeqPair *sp = &R.pairs[k];
+                mem_alnreg_t *a = &w.regs[sp->seqid].a[sp->regid];
+                a->score = sp->score;
+                if (sp->gscore <= 0 || sp->gscore <= a->score - opt->pen_clip3) { a->qe += sp->qle; a->re += sp->tle; a->truesc += a->score - sp->h0; }
+                else { a->qe = w.seqs[sp->seqid].l_seq; a->re += sp->gtle; a->truesc += sp->gscore - sp->h0; }
+                a->w = max_(a->w, R.w_used[k]);
+                seed_coverage(a);
+            }
+            // every region of the half has both sides folded before any of its reads is finished (a block may be finished by
+            // another thread than the one that built its pairs)
+#pragma omp barrier
+#pragma omp for schedule(dynamic, 1)
+            for (int b = blk_cut[h]; b < blk_cut[h + 1]; b++) {
+                uint32_t *srt = g_ts[(size_t)g_blk_owner[(size_t)b]].srt.data();
+                const int r0 = b * BLK, r1 = std::min(n, r0 + BLK);
+                for (int l = r0; l < r1; l++) {
+                    purge_contained(opt, &w.seqs[l], &w.chain_ar[l], &w.regs[l], srt + g_srt_off[(size_t)l]);
+                    finish_read(opt, bns, pac, &w.seqs[l], &w.chain_ar[l], &w.regs[l]);
+                }
+            }
+        }
+        t_finish += omp_get_wtime() - ta;
+    };
+    if (n_half == 1) {
+        build_pairs(0);
+        start_side(0, false); wait_side(false);
+        fold_left(0);
+        start_side(0, true); wait_side(true);
+        finish_half(0);
+    } else {
+        build_pairs(0);
+        start_side(0, false); build_pairs(1); wait_side(false);        // left(A)  || pairs(B)
+        start_side(1, false); fold_left(0);   wait_side(false);        // left(B)  || fold(A)
+        start_side(0, true);  fold_left(1);   wait_side(true);         // right(A) || fold(B)
+        start_side(1, true);  finish_half(0); wait_side(true);         // right(B) || finish(A)
+        finish_half(1);
     }
-    double t5 = omp_get_wtime();
-    fprintf(stderr, "[meme_b200] extended %d reads on the GPU: %ld left + %ld right pairs; pairs %.1f ms, left %.1f ms, fold %.1f ms, "
-            "right %.1f ms, finish %.1f ms\n", n, (long)tot_left, (long)tot_right, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
+    const double t1 = t0 + t_pairs, t2 = t1 + t_left, t3 = t2 + t_fold, t4 = t3 + t_right, t5 = t4 + t_finish;
+    (void)t_job;
+    fprintf(stderr, "[meme_b200] extended %d reads on the GPU (%d piece%s): %ld left + %ld right pairs; pairs %.1f ms, left %.1f ms, fold %.1f ms, "
+            "right %.1f ms, finish %.1f ms (left / right = what the host waited for the device)\n", n, n_half, n_half > 1 ? "s, overlapped" : "", (long)tot_left, (long)tot_right, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
             (t4 - t3) * 1e3, (t5 - t4) * 1e3);
     return true;
 }

@@ -209,6 +209,7 @@ static void ensure_index()
             cpu_set_t cs;
             if (!getenv("MEME_B200_THREADS") && sched_getaffinity(0, sizeof cs, &cs) == 0) threads = CPU_COUNT(&cs);
             meme_glue_pinned_reserve(threads, warm);
+            meme_glue_bsw_warmup(warm);
         }
         if (env_on("MEME_B200_MATE")) {
             int threads = getenv("MEME_B200_THREADS") ? atoi(getenv("MEME_B200_THREADS")) : (int)std::thread::hardware_concurrency();
@@ -481,6 +482,7 @@ void meme_glue_cigar_run(std::vector<int32_t> &reg_w, std::vector<int64_t> &task
             if (rc[(size_t)d]) err[(size_t)d] = a.last_error();
         });
     for (auto &t : th) t.join();
+    const double t_call = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3;
     for (int d = 0; d < nd; d++)
         if (rc[(size_t)d]) { fprintf(stderr, "[meme_b200] meme_cigar_batch failed (%d): %s\n", rc[(size_t)d], err[(size_t)d].c_str()); exit(EXIT_FAILURE); }
     size_t slots = 1024;
@@ -507,8 +509,8 @@ void meme_glue_cigar_run(std::vector<int32_t> &reg_w, std::vector<int64_t> &task
     }
     long ops = 0;
     for (auto &r : g_cres) ops += (long)r.n_ops;
-    fprintf(stderr, "[meme_b200] global alignments of %ld regions on the GPU: %ld CIGAR operations, %.1f ms\n", (long)n, ops,
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+    fprintf(stderr, "[meme_b200] global alignments of %ld regions on the GPU: %ld CIGAR operations, %.1f ms (device calls %.1f ms)\n", (long)n, ops,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3, t_call);
 }
 
 // mem_reg2aln asks for one region's alignment: true = *cigar (malloc'ed: n_cigar operations followed by the MD string, as
@@ -677,11 +679,12 @@ void meme_glue_pinned_reserve(int threads, long reads_per_chunk)
 {
     if (threads < 1 || reads_per_chunk < 1) return;
     auto t0 = std::chrono::steady_clock::now();
-    // the same sizes meme_extend.inl asks for on its first chunk (6 pairs per read of head-room, 56 + 200 + 100 + 4 bytes each)
-    const size_t est = (size_t)(reads_per_chunk / threads + 1) * 6;
+    // the same sizes meme_extend.inl asks for on its first chunk (6 pairs per read of head-room, 56 + 200 + 100 + 4 bytes each;
+    // per host thread two sides x two halves of the chunk)
+    const size_t est = (size_t)(reads_per_chunk / threads + 1) * 6 / 2;
     const size_t sizes[4] = {est * sizeof(SeqPair), est * 200, est * 100, est * 4};
     size_t total = 0;
-    for (int t = 0; t < threads * 2; t++)
+    for (int t = 0; t < threads * 4; t++)
         for (size_t b : sizes) {
             if (b == est * 200 && meme_glue_bsw_text_mode()) continue;     // no reference bytes: pairs name text positions
             void *p = nullptr;
@@ -738,13 +741,12 @@ void meme_glue_pinned_free(void *p) { api().pinned_free(p); }
 
 // One side of the extension of a whole chunk: segments written by the host threads -> one device batch with the band
 // retries decided by the kernel -> results back into the same pair arrays (and the band width that was final).
-void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
-                            int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
-                            int a, int b, int32_t **w_used)
+// one kernel-B handle per device, created on first use (or by the warm-up at index load)
+static std::vector<meme_bsw_t *> &bsw_handles()
 {
-    Api &A = api();
     static std::vector<meme_bsw_t *> hs;
     if (hs.empty()) {
+        Api &A = api();
         if (g_devices.empty()) g_devices.push_back(getenv("MEME_B200_DEVICE") ? atoi(getenv("MEME_B200_DEVICE")) : 0);
         for (int dev : g_devices) {
             meme_bsw_t *h = nullptr;
@@ -757,6 +759,62 @@ void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t
             hs.push_back(h);
         }
     }
+    return hs;
+}
+
+// Kernel B loaded and its device buffers sized for a chunk before the first timed chunk: one throw-away batch of short dummy
+// pairs per device, about as many as a chunk of `reads` reads produces on its larger (right) side.
+void meme_glue_bsw_warmup(long reads)
+{
+    if (reads < 1) return;
+    auto t0 = std::chrono::steady_clock::now();
+    Api &A = api();
+    std::vector<meme_bsw_t *> &hs = bsw_handles();
+    const int nd = (int)hs.size();
+    const int64_t n = (int64_t)reads * 9 / 2 / nd + 1024;           // ~4.1 right-side pairs per read, with head-room
+    const int len = 80;
+    std::vector<meme_seqpair_t> pairs((size_t)n);
+    std::vector<uint8_t> qer((size_t)n * len, 0), ref;
+    const bool text = meme_glue_bsw_text_mode();
+    if (!text) ref.assign((size_t)n * len, 1);
+    memset(pairs.data(), 0, pairs.size() * sizeof(meme_seqpair_t));
+    for (int64_t k = 0; k < n; k++) {
+        meme_seqpair_t &p = pairs[(size_t)k];
+        p.idq = (int32_t)(k * len); p.len1 = len; p.len2 = len; p.h0 = 20; p.regid = (int32_t)k;
+        p.idr = text ? (int32_t)(k & 255) : (int32_t)(k * len); p.id = 0;
+    }
+    meme_bsw_opt_t o = {6, 1, 6, 1, 100, 5, 1, 4};
+    for (int d = 0; d < nd; d++) {
+        const meme_seqpair_t *pp = pairs.data(); meme_seqpair_t *pw = pairs.data();
+        const int64_t np = n, nr = text ? 0 : (int64_t)ref.size(), nq = (int64_t)qer.size();
+        const uint8_t *pr = text ? nullptr : ref.data(), *pq = qer.data();
+        std::vector<int32_t> wu((size_t)n);
+        int32_t *pwu = wu.data();
+        int rc = A.bsw_set_match(hs[(size_t)d], 1);
+        if (!rc) rc = A.bsw_upload_segments(hs[(size_t)d], 1, &pp, &np, &pr, &nr, &pq, &nq);
+        if (!rc) rc = A.bsw_run_ext(hs[(size_t)d], 100, 2, 1, &o);
+        if (!rc) rc = A.bsw_download_segments(hs[(size_t)d], 1, &pw, &np, &pwu);
+        if (rc) die("kernel-B warm-up", rc);
+    }
+    fprintf(stderr, "[meme_b200] kernel-B warm-up batch of %ld pairs per device in %.2f s\n", (long)n,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+
+namespace {
+struct BswJob {          // one extension batch in flight: a driving host thread per device, and copies of the caller's segment arrays
+    std::vector<std::thread> th;
+    std::vector<int> rcs;
+    std::vector<std::string> errs;
+    std::vector<SeqPair *> pairs; std::vector<int64_t> n_pairs, n_ref, n_qer; std::vector<uint8_t *> ref, qer; std::vector<int32_t *> w_used;
+};
+}
+
+void *meme_glue_bsw_segments_start(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
+                            int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
+                            int a, int b, int32_t **w_used)
+{
+    Api &A = api();
+    std::vector<meme_bsw_t *> &hs = bsw_handles();
     static_assert(sizeof(SeqPair) == sizeof(meme_seqpair_t), "SeqPair layout");
     meme_bsw_opt_t o = {o_del, e_del, o_ins, e_ins, zdrop, end_bonus, a, b};
     // MEME_B200_DUMP_PAIRS=<path>: the extension pairs of the first chunk (left side, then right side with its real h0)
@@ -788,29 +846,50 @@ void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t
             dumped++;
         }
     }
-    // the segments (one per host thread) are dealt round-robin to the devices; every device runs its share concurrently
+    // the segments (one per host thread) are dealt round-robin to the devices; every device runs its share concurrently, driven
+    // by one host thread each; the caller may do other work until it waits for the job
     const int nd = (int)hs.size();
-    std::vector<std::thread> th;
-    std::vector<int> rcs((size_t)nd, 0);
-    std::vector<std::string> errs((size_t)nd);
+    BswJob *J = new BswJob;
+    J->rcs.assign((size_t)nd, 0); J->errs.resize((size_t)nd);
+    J->pairs.assign(pairs, pairs + nseg); J->n_pairs.assign(n_pairs, n_pairs + nseg); J->ref.assign(ref, ref + nseg); J->n_ref.assign(n_ref, n_ref + nseg);
+    J->qer.assign(qer, qer + nseg); J->n_qer.assign(n_qer, n_qer + nseg); J->w_used.assign(w_used, w_used + nseg);
+    std::vector<meme_bsw_t *> *hp = &hs;
     for (int d = 0; d < nd; d++) {
-        th.emplace_back([&, d] {
+        J->th.emplace_back([J, hp, d, nd, nseg, a, w, tries, prev_is_h0, o] {
+            Api &A = api();
             std::vector<const meme_seqpair_t *> sp; std::vector<meme_seqpair_t *> spw; std::vector<int64_t> np, nr, nq;
             std::vector<const uint8_t *> pr, pq; std::vector<int32_t *> pw;
             for (int s = d; s < nseg; s += nd) {
-                sp.push_back((const meme_seqpair_t *)pairs[s]); spw.push_back((meme_seqpair_t *)pairs[s]); np.push_back(n_pairs[s]);
-                pr.push_back(ref[s]); nr.push_back(n_ref[s]); pq.push_back(qer[s]); nq.push_back(n_qer[s]); pw.push_back(w_used[s]);
+                sp.push_back((const meme_seqpair_t *)J->pairs[(size_t)s]); spw.push_back((meme_seqpair_t *)J->pairs[(size_t)s]); np.push_back(J->n_pairs[(size_t)s]);
+                pr.push_back(J->ref[(size_t)s]); nr.push_back(J->n_ref[(size_t)s]); pq.push_back(J->qer[(size_t)s]); nq.push_back(J->n_qer[(size_t)s]);
+                pw.push_back(J->w_used[(size_t)s]);
             }
             const int k = (int)sp.size();
-            int rc = A.bsw_set_match(hs[(size_t)d], a);
-            if (!rc) rc = A.bsw_upload_segments(hs[(size_t)d], k, sp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data());
-            if (!rc) rc = A.bsw_run_ext(hs[(size_t)d], w, tries, prev_is_h0, &o);
-            if (!rc) rc = A.bsw_download_segments(hs[(size_t)d], k, spw.data(), np.data(), pw.data());
-            rcs[(size_t)d] = rc;
-            if (rc) errs[(size_t)d] = A.last_error();
+            meme_bsw_t *h = (*hp)[(size_t)d];
+            int rc = A.bsw_set_match(h, a);
+            if (!rc) rc = A.bsw_upload_segments(h, k, sp.data(), np.data(), pr.data(), nr.data(), pq.data(), nq.data());
+            if (!rc) rc = A.bsw_run_ext(h, w, tries, prev_is_h0, &o);
+            if (!rc) rc = A.bsw_download_segments(h, k, spw.data(), np.data(), pw.data());
+            J->rcs[(size_t)d] = rc;
+            if (rc) J->errs[(size_t)d] = A.last_error();
         });
     }
-    for (auto &t : th) t.join();
-    for (int d = 0; d < nd; d++)
-        if (rcs[(size_t)d]) { fprintf(stderr, "[meme_b200] seed extension on GPU %d failed (%d): %s\n", g_devices[(size_t)d], rcs[(size_t)d], errs[(size_t)d].c_str()); exit(EXIT_FAILURE); }
+    return J;
+}
+
+void meme_glue_bsw_segments_wait(void *job)
+{
+    BswJob *J = (BswJob *)job;
+    for (auto &t : J->th) t.join();
+    for (size_t d = 0; d < J->rcs.size(); d++)
+        if (J->rcs[d]) { fprintf(stderr, "[meme_b200] seed extension on GPU %d failed (%d): %s\n", g_devices[d], J->rcs[d], J->errs[d].c_str()); exit(EXIT_FAILURE); }
+    delete J;
+}
+
+void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
+                            int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
+                            int a, int b, int32_t **w_used)
+{
+    meme_glue_bsw_segments_wait(meme_glue_bsw_segments_start(nseg, pairs, n_pairs, ref, n_ref, qer, n_qer, w, tries, prev_is_h0, o_del, e_del, o_ins, e_ins,
+                                                             zdrop, end_bonus, a, b, w_used));
 }

@@ -61,6 +61,7 @@ void meme_glue_matesw_run(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t *
 bool meme_glue_bsw_enabled();
 bool meme_glue_bsw_text_mode();
 void meme_glue_pinned_reserve(int threads, long reads_per_chunk);
+void meme_glue_bsw_warmup(long reads);
 void meme_glue_pinned_reserve_matesw(int threads, long reads_per_chunk);
 void meme_glue_matesw_arena_sizes(int threads, long reads_per_chunk, size_t sizes[3]);
 void *meme_glue_pinned_alloc(size_t bytes);
@@ -68,3 +69,9 @@ void meme_glue_pinned_free(void *p);
 void meme_glue_bsw_segments(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
                             int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
                             int a, int b, int32_t **w_used);
+// the same in two steps: start returns at once (the batch is driven by one host thread per device), wait returns when the results
+// are in the pair arrays; one job at a time
+void *meme_glue_bsw_segments_start(int nseg, SeqPair **pairs, int64_t *n_pairs, uint8_t **ref, int64_t *n_ref, uint8_t **qer, int64_t *n_qer,
+                                   int w, int tries, int prev_is_h0, int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus,
+                                   int a, int b, int32_t **w_used);
+void meme_glue_bsw_segments_wait(void *job);
