@@ -586,13 +586,13 @@ void meme_matesw_chunk(worker_t &w, int n)
     if (meme_matesw_collect(w, n)) meme_matesw_run(w);
 }
 
-// Both pre-passes of the SAM stage.  The global alignments keep the GPU busy for most of their 70 ms while the host waits, and
-// collecting the rescue pairs is host work only, so the two can overlap (MEME_B200_OVERLAP=1: the alignments are driven from a
-// second thread).  Measured on 1 M pairs: 5 % per chunk in steady state, but the first chunk pays 0.26 s for the second thread's
-// cold start, so it is off by default (profiles/r2/README.md).
+// Both pre-passes of the SAM stage.  The global alignments keep the GPU busy for most of their time while the host waits, and
+// collecting the rescue pairs is host work only, so with both stages on the alignments are driven from a second thread while the
+// workers collect (MEME_B200_NO_OVERLAP=1: one after the other).  Measured on 1 M pairs, alternating runs on one box: 221-224
+// against 203-209 Mbases/s (profiles/r2/README.md; a first attempt lost to a cold-start stall that was the warm-up's fault).
 void meme_sam_prepass(worker_t &w, int n)
 {
-    if (!meme_glue_cigar_enabled() || !meme_matesw_wanted(w, n) || !getenv("MEME_B200_OVERLAP")) {
+    if (!meme_glue_cigar_enabled() || !meme_matesw_wanted(w, n) || getenv("MEME_B200_NO_OVERLAP")) {
         meme_cigar_chunk(w, n);
         meme_matesw_chunk(w, n);
         return;

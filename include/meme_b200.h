@@ -246,8 +246,10 @@ typedef struct {
  * handle, valid until the next call. */
 int meme_cigar_batch(meme_index_t *ix, const meme_cigar_task_t *tasks, int64_t n_tasks, const uint8_t *codes, int64_t n_codes,
                      int64_t l_pac, const meme_cigar_opt_t *opt, meme_cigar_result_t *out);
-/* Kernels loaded and the pinned result arrays sized for about n_regions regions of qlen-base reads per call, ahead of the
- * first timed chunk (the reference has no counterpart: its first chunk costs what the others cost). */
+/* Kernels loaded and every array sized for about n_regions regions of qlen-base reads per call, ahead of the first timed
+ * chunk: one slice of dummy regions with worst-case bands runs through every kernel, the backtrack scratch is sized for a
+ * slice in which half of the warps hold full-width matrices (3.6 GB at 150 bases), the pinned result arrays for the whole
+ * chunk.  (The reference has no counterpart: its first chunk costs what the others cost.) */
 int meme_cigar_warmup(meme_index_t *ix, int64_t n_regions, int qlen);
 /* CUDA-event duration (ms) of the kernels of the last meme_cigar_batch, and the DP cells they evaluated. */
 int meme_cigar_last(meme_index_t *ix, float *ms, uint64_t *cells);
